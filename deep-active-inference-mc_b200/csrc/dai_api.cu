@@ -1,0 +1,802 @@
+// C ABI (include/dai_b200.h): handle, weight repacking, workspaces and the orchestration of
+// the kernels into the reference's EFE evaluators (src/torchmodel.py:210-393).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dai_b200.h"
+#include "dai_kernels.h"
+#include "dai_tc.h"
+
+using namespace dai;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct WeightSpec {
+    const char* key;
+    int ndim;
+    int64_t shape[4];
+};
+
+// state_dict of model_top / model_mid / model_down (src/torchmodel.py:19-25,41-52,84-128; D1 repaired)
+const WeightSpec kSpecs[] = {
+    {"qpi_net.0.weight", 2, {128, 10}},      {"qpi_net.0.bias", 1, {128}},
+    {"qpi_net.2.weight", 2, {128, 128}},     {"qpi_net.2.bias", 1, {128}},
+    {"qpi_net.4.weight", 2, {4, 128}},       {"qpi_net.4.bias", 1, {4}},
+    {"ps_net.0.weight", 2, {512, 14}},       {"ps_net.0.bias", 1, {512}},
+    {"ps_net.3.weight", 2, {512, 512}},      {"ps_net.3.bias", 1, {512}},
+    {"ps_net.6.weight", 2, {512, 512}},      {"ps_net.6.bias", 1, {512}},
+    {"ps_net.9.weight", 2, {20, 512}},       {"ps_net.9.bias", 1, {20}},
+    {"qs_net.0.weight", 4, {32, 1, 3, 3}},   {"qs_net.0.bias", 1, {32}},
+    {"qs_net.2.weight", 4, {32, 32, 3, 3}},  {"qs_net.2.bias", 1, {32}},
+    {"qs_net.4.weight", 4, {64, 32, 3, 3}},  {"qs_net.4.bias", 1, {64}},
+    {"qs_net.6.weight", 4, {64, 64, 3, 3}},  {"qs_net.6.bias", 1, {64}},
+    {"qs_net.9.weight", 2, {256, 576}},      {"qs_net.9.bias", 1, {256}},
+    {"qs_net.12.weight", 2, {256, 256}},     {"qs_net.12.bias", 1, {256}},
+    {"qs_net.15.weight", 2, {256, 256}},     {"qs_net.15.bias", 1, {256}},
+    {"qs_net.18.weight", 2, {20, 256}},      {"qs_net.18.bias", 1, {20}},
+    {"po_net.0.weight", 2, {256, 10}},       {"po_net.0.bias", 1, {256}},
+    {"po_net.3.weight", 2, {256, 256}},      {"po_net.3.bias", 1, {256}},
+    {"po_net.6.weight", 2, {256, 256}},      {"po_net.6.bias", 1, {256}},
+    {"po_net.9.weight", 2, {16384, 256}},    {"po_net.9.bias", 1, {16384}},
+    {"po_net.13.weight", 4, {64, 64, 3, 3}}, {"po_net.13.bias", 1, {64}},
+    {"po_net.15.weight", 4, {64, 64, 3, 3}}, {"po_net.15.bias", 1, {64}},
+    {"po_net.17.weight", 4, {64, 32, 3, 3}}, {"po_net.17.bias", 1, {32}},
+    {"po_net.19.weight", 4, {32, 1, 3, 3}},  {"po_net.19.bias", 1, {1}},
+};
+constexpr int kNumSpecs = sizeof(kSpecs) / sizeof(kSpecs[0]);
+
+constexpr int kDecChunk = 1024;   // decoder rows per activation chunk (896 KB of activations per row)
+constexpr int kQsChunk = 2048;    // encoder rows per chunk (166 KB of conv features per row)
+
+}  // namespace
+
+struct dai_handle {
+    dai_config cfg{};
+    int device = 0;
+    std::string err;
+    std::map<std::string, std::vector<float>> raw;
+    bool committed = false;
+    DevWeights w{};
+    TcWeights tcw{};
+    std::vector<void*> wallocs;
+    uint64_t seed = 1234, call = 0;
+    uint64_t launches = 0, calls = 0;
+    // workspaces (grow-only)
+    DevBuf ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
+        pi_eye, traj, root, stage_in, stage_out, scratch;
+    float* pinned = nullptr;   // small host result buffer
+    size_t pinned_cap = 0;
+};
+
+namespace {
+
+int fail(dai_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(h, DAI_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define RET(call)                 \
+    do {                          \
+        int rc__ = (call);        \
+        if (rc__ != DAI_OK) return rc__; \
+    } while (0)
+
+int reserve(dai_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return DAI_OK;
+    if (b.p) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(h, DAI_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return DAI_OK;
+}
+
+template <class T>
+T* ptr(DevBuf& b) { return static_cast<T*>(b.p); }
+
+NoiseKey make_key(const dai_handle* h, uint64_t call, uint32_t step) {
+    const uint64_t k = h->seed + call;
+    NoiseKey nk;
+    nk.k0 = (uint32_t)(k & 0xffffffffu);
+    nk.k1 = (uint32_t)(k >> 32);
+    nk.step = step;
+    nk.training = h->cfg.training;
+    return nk;
+}
+
+int check_ready(dai_handle* h) {
+    if (!h) return DAI_E_INVALID;
+    if (!h->committed) return fail(h, DAI_E_WEIGHTS, "weights not committed (dai_set_weight x46, then dai_commit_weights)");
+    CK(cudaSetDevice(h->device));
+    return DAI_OK;
+}
+
+int post_launch(dai_handle* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, DAI_E_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+    return DAI_OK;
+}
+
+// ---- weight repacking ----------------------------------------------------------------
+
+int upload(dai_handle* h, const std::vector<float>& v, float** out) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float));
+    if (e != cudaSuccess) return fail(h, DAI_E_NOMEM, "cudaMalloc(weights) failed: %s", cudaGetErrorString(e));
+    h->wallocs.push_back(p);
+    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = static_cast<float*>(p);
+    return DAI_OK;
+}
+
+// torch Linear (N,K) -> [Kpad][N]
+std::vector<float> transpose_pad(const std::vector<float>& W, int N, int K, int Kpad) {
+    std::vector<float> t((size_t)Kpad * N, 0.0f);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) t[(size_t)k * N + n] = W[(size_t)n * K + k];
+    return t;
+}
+
+// ConvTranspose2d (Cin,Cout,3,3) -> [tap][Cin][Cout]
+std::vector<float> pack_convT(const std::vector<float>& W, int Cin, int Cout) {
+    std::vector<float> p((size_t)9 * Cin * Cout);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = W[((size_t)ci * Cout + co) * 9 + t];
+    return p;
+}
+
+// Conv2d (Cout,Cin,3,3) -> [tap][Cin][Cout]
+std::vector<float> pack_conv(const std::vector<float>& W, int Cout, int Cin) {
+    std::vector<float> p((size_t)9 * Cin * Cout);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = W[((size_t)co * Cin + ci) * 9 + t];
+    return p;
+}
+
+int commit(dai_handle* h) {
+    for (int i = 0; i < kNumSpecs; ++i)
+        if (!h->raw.count(kSpecs[i].key)) return fail(h, DAI_E_WEIGHTS, "missing weight %s", kSpecs[i].key);
+    for (void* p : h->wallocs) cudaFree(p);
+    h->wallocs.clear();
+    auto& R = h->raw;
+    DevWeights& w = h->w;
+    // Ps
+    RET(upload(h, transpose_pad(R["ps_net.0.weight"], 512, 14, 16), &w.ps_w0t));
+    RET(upload(h, R["ps_net.0.bias"], &w.ps_b0));
+    RET(upload(h, transpose_pad(R["ps_net.3.weight"], 512, 512, 512), &w.ps_w1t));
+    RET(upload(h, R["ps_net.3.bias"], &w.ps_b1));
+    RET(upload(h, transpose_pad(R["ps_net.6.weight"], 512, 512, 512), &w.ps_w2t));
+    RET(upload(h, R["ps_net.6.bias"], &w.ps_b2));
+    RET(upload(h, R["ps_net.9.weight"], &w.ps_w3));
+    RET(upload(h, R["ps_net.9.bias"], &w.ps_b3));
+    // Po FCs
+    RET(upload(h, transpose_pad(R["po_net.0.weight"], 256, 10, 12), &w.po_w0t));
+    RET(upload(h, R["po_net.0.bias"], &w.po_b0));
+    RET(upload(h, transpose_pad(R["po_net.3.weight"], 256, 256, 256), &w.po_w1t));
+    RET(upload(h, R["po_net.3.bias"], &w.po_b1));
+    RET(upload(h, transpose_pad(R["po_net.6.weight"], 256, 256, 256), &w.po_w2t));
+    RET(upload(h, R["po_net.6.bias"], &w.po_b2));
+    {   // FC4: reference output index e = c*256 + p (Unflatten (64,16,16)) -> NHWC column n' = p*64 + c
+        const std::vector<float>& W = R["po_net.9.weight"];
+        const std::vector<float>& b = R["po_net.9.bias"];
+        std::vector<float> t((size_t)256 * 16384), bp(16384);
+        for (int c = 0; c < 64; ++c)
+            for (int p = 0; p < 256; ++p) {
+                const int e = c * 256 + p, n = p * 64 + c;
+                bp[n] = b[e];
+                for (int k = 0; k < 256; ++k) t[(size_t)k * 16384 + n] = W[(size_t)e * 256 + k];
+            }
+        RET(upload(h, t, &w.po_w3t));
+        RET(upload(h, bp, &w.po_b3));
+    }
+    RET(upload(h, pack_convT(R["po_net.13.weight"], 64, 64), &w.ct1_w));
+    RET(upload(h, R["po_net.13.bias"], &w.ct1_b));
+    RET(upload(h, pack_convT(R["po_net.15.weight"], 64, 64), &w.ct2_w));
+    RET(upload(h, R["po_net.15.bias"], &w.ct2_b));
+    RET(upload(h, pack_convT(R["po_net.17.weight"], 64, 32), &w.ct3_w));
+    RET(upload(h, R["po_net.17.bias"], &w.ct3_b));
+    RET(upload(h, pack_convT(R["po_net.19.weight"], 32, 1), &w.ct4_w));
+    RET(upload(h, R["po_net.19.bias"], &w.ct4_b));
+    // Qs
+    RET(upload(h, pack_conv(R["qs_net.0.weight"], 32, 1), &w.qc1_w));
+    RET(upload(h, R["qs_net.0.bias"], &w.qc1_b));
+    RET(upload(h, pack_conv(R["qs_net.2.weight"], 32, 32), &w.qc2_w));
+    RET(upload(h, R["qs_net.2.bias"], &w.qc2_b));
+    RET(upload(h, pack_conv(R["qs_net.4.weight"], 64, 32), &w.qc3_w));
+    RET(upload(h, R["qs_net.4.bias"], &w.qc3_b));
+    RET(upload(h, pack_conv(R["qs_net.6.weight"], 64, 64), &w.qc4_w));
+    RET(upload(h, R["qs_net.6.bias"], &w.qc4_b));
+    {   // FC1: reference flatten index f = c*9 + h*3 + w -> NHWC flatten f' = (h*3+w)*64 + c
+        const std::vector<float>& W = R["qs_net.9.weight"];
+        std::vector<float> t((size_t)576 * 256);
+        for (int n = 0; n < 256; ++n)
+            for (int c = 0; c < 64; ++c)
+                for (int p = 0; p < 9; ++p) t[(size_t)(p * 64 + c) * 256 + n] = W[(size_t)n * 576 + c * 9 + p];
+        RET(upload(h, t, &w.qf0_t));
+    }
+    RET(upload(h, R["qs_net.9.bias"], &w.qf0_b));
+    RET(upload(h, transpose_pad(R["qs_net.12.weight"], 256, 256, 256), &w.qf1_t));
+    RET(upload(h, R["qs_net.12.bias"], &w.qf1_b));
+    RET(upload(h, transpose_pad(R["qs_net.15.weight"], 256, 256, 256), &w.qf2_t));
+    RET(upload(h, R["qs_net.15.bias"], &w.qf2_b));
+    RET(upload(h, R["qs_net.18.weight"], &w.qf3));
+    RET(upload(h, R["qs_net.18.bias"], &w.qf3_b));
+    // Qpi
+    RET(upload(h, transpose_pad(R["qpi_net.0.weight"], 128, 10, 12), &w.pi_w0t));
+    RET(upload(h, R["qpi_net.0.bias"], &w.pi_b0));
+    RET(upload(h, transpose_pad(R["qpi_net.2.weight"], 128, 128, 128), &w.pi_w1t));
+    RET(upload(h, R["qpi_net.2.bias"], &w.pi_b1));
+    RET(upload(h, R["qpi_net.4.weight"], &w.pi_w2));
+    RET(upload(h, R["qpi_net.4.bias"], &w.pi_b2));
+    // tensor-core operand planes (bf16 hi/lo, K-major) for the contraction layers
+    {
+        std::vector<void*> extra;
+        std::string terr;
+        const int rc = tc_pack_weights(R, &h->tcw, &extra, &terr);
+        for (void* p : extra) h->wallocs.push_back(p);
+        if (rc != 0) return fail(h, DAI_E_CUDA, "tensor-core weight packing failed: %s", terr.c_str());
+    }
+    h->committed = true;
+    return DAI_OK;
+}
+
+// ---- decoder over row sets -----------------------------------------------------------
+
+// Runs Po on `fc` rows (sets x slots x B): FC1..3 fused, then per chunk FC4 -> ct1 -> ct2 -> ct3 -> pixel
+// terms.  Rows < img_rows write their image into `img`.
+int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float* img, float* hsum, float* reward) {
+    const int rows = fc.map.rows();
+    if (rows <= 0) return DAI_OK;
+    RET(reserve(h, h->h3, (size_t)rows * 256 * sizeof(float)));
+    const int ch = std::min(rows, kDecChunk);
+    const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
+    const size_t esz = sizeof(float);   // fp32 planes, or bf16 hi+lo planes: 4 bytes per element either way
+    RET(reserve(h, h->mask, (size_t)ch * 512 * sizeof(uint32_t)));
+    RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
+    RET(reserve(h, h->act1, (size_t)ch * 16384 * esz));
+    RET(reserve(h, h->act2, (size_t)ch * 65536 * esz));
+    RET(reserve(h, h->act3, (size_t)ch * 131072 * esz));
+    fc.h3 = ptr<float>(h->h3);
+    h->launches += launch_po_fc123(h->w, fc, st);
+    for (int r0 = 0; r0 < rows; r0 += ch) {
+        const int n = std::min(ch, rows - r0);
+        const uint32_t* mask = nullptr;
+        if (fc.nk.training) {
+            h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), st);
+            mask = ptr<uint32_t>(h->mask);
+        }
+        const float* h3c = fc.h3 + (size_t)r0 * 256;
+        Ct4Args c4{};
+        c4.row0 = r0; c4.nrows = n; c4.img_rows = img_rows; c4.img = img; c4.hsum = hsum; c4.reward = reward;
+        if (!tc) {
+            h->launches += launch_fc4_simt(h->w, h3c, mask, n, ptr<float>(h->act0), st);
+            h->launches += launch_ct1_simt(h->w, ptr<float>(h->act0), n, ptr<float>(h->act1), st);
+            h->launches += launch_ct2_simt(h->w, ptr<float>(h->act1), n, ptr<float>(h->act2), st);
+            h->launches += launch_ct3_simt(h->w, ptr<float>(h->act2), n, ptr<float>(h->act3), st);
+            c4.act3 = ptr<float>(h->act3);
+            h->launches += launch_ct4_efe(h->w, c4, st);
+        } else {
+            std::string terr;
+            const int nl = tc_decoder_chunk(h->tcw, h->w, h->cfg.precision, h3c, mask, n, h->act0.p, h->act1.p,
+                                            h->act2.p, h->act3.p, c4, st, &terr);
+            if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core decoder: %s", terr.c_str());
+            h->launches += nl;
+        }
+    }
+    return post_launch(h, "decoder");
+}
+
+// Runs Qs on `rows` images with noise map (B, Sl, sample0, site); outputs [rows][10] each.
+int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl, int sample0, int site,
+                const NoiseKey& nk, float* mean, float* logvar, float* samp) {
+    const int rows = B * Sl;
+    if (rows <= 0) return DAI_OK;
+    const int ch = std::min(rows, kQsChunk);
+    // chunks must hold whole slots so the (slot, b) decode stays valid: round down to a multiple of B
+    int chs = ch;
+    if (rows > ch) {
+        chs = (ch / B) * B;
+        if (chs == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
+    }
+    RET(reserve(h, h->qc1, (size_t)chs * 961 * 32 * sizeof(float)));
+    RET(reserve(h, h->qc2, (size_t)chs * 225 * 32 * sizeof(float)));
+    RET(reserve(h, h->qc3, (size_t)chs * 49 * 64 * sizeof(float)));
+    RET(reserve(h, h->qc4, (size_t)chs * 576 * sizeof(float)));
+    for (int r0 = 0; r0 < rows; r0 += chs) {
+        const int n = std::min(chs, rows - r0);
+        QsArgs a{};
+        a.img = img + (size_t)r0 * IMG; a.rows = n;
+        a.map.B = B; a.map.Sl = (n + B - 1) / B; a.map.sample0 = sample0 + r0 / B; a.map.nsets = 1;
+        a.map.site[0] = site; a.map.site[1] = site; a.map.site[2] = site;
+        a.c1 = ptr<float>(h->qc1); a.c2 = ptr<float>(h->qc2); a.c3 = ptr<float>(h->qc3); a.c4 = ptr<float>(h->qc4);
+        a.mean = mean + (size_t)r0 * S_DIM; a.logvar = logvar + (size_t)r0 * S_DIM;
+        a.samp = samp ? samp + (size_t)r0 * S_DIM : nullptr;
+        a.nk = nk;
+        h->launches += launch_qs(h->w, a, st);
+    }
+    return post_launch(h, "encoder");
+}
+
+// ---- one EFE step (calculate_G / calculate_G_mean) -----------------------------------
+
+struct StepSpec {
+    const float* s0 = nullptr;    // [B][10]
+    const float* pi = nullptr;    // [B][4]
+    int B = 0;
+    int samples = 1, j0 = 0, j1 = 1;
+    int mean_variant = 0;         // 1: calculate_G_mean (src/torchmodel.py:302-327)
+    NoiseKey nk{};
+    double* acc = nullptr;        // [4][B]
+    float* carry_dst = nullptr;   // [B][10] <- ps1 (or ps1_mean when carry_mean) of the last sample
+    int carry_mean = 0;
+    float *out_ps1 = nullptr, *out_mean = nullptr, *out_logvar = nullptr, *out_po1 = nullptr;
+};
+
+int run_step(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
+    const int B = sp.B;
+    const int Sl = sp.mean_variant ? 1 : (sp.j1 - sp.j0);
+    const int S = sp.mean_variant ? 1 : sp.samples;
+    const int j0 = sp.mean_variant ? 0 : sp.j0;
+    const bool own_last = (j0 + Sl == S) && Sl > 0;
+    const int nA = Sl + (own_last ? 0 : 1);
+    const int last_slot = nA - 1;
+    const size_t slab = (size_t)B * S_DIM;          // one [B][10] slab
+    // ps buffer: meanA, logvarA, sampA [nA] ; meanB, sampB [Sl]
+    RET(reserve(h, h->ps, (3 * (size_t)nA + 2 * (size_t)Sl) * slab * sizeof(float)));
+    float* meanA = ptr<float>(h->ps);
+    float* logvarA = meanA + nA * slab;
+    float* sampA = logvarA + nA * slab;
+    float* meanB = sampA + nA * slab;
+    float* sampB = meanB + Sl * slab;
+    PsArgs pa{};
+    pa.pi = sp.pi; pa.s0 = sp.s0; pa.B = B; pa.nA = nA; pa.nB = Sl; pa.sample0 = j0;
+    pa.extra_slot = own_last ? -1 : Sl; pa.extra_sample = S - 1;
+    pa.siteA = SITE_PS_A; pa.siteB = SITE_PS_B;
+    pa.meanA = meanA; pa.logvarA = logvarA; pa.sampA = sampA;
+    pa.meanB = meanB; pa.logvarB = nullptr; pa.sampB = sampB;
+    pa.nk = sp.nk;
+    h->launches += launch_ps(h->w, pa, st);
+    RET(post_launch(h, "transition"));
+
+    const int rows = 3 * Sl * B;
+    RET(reserve(h, h->img, (size_t)std::max(Sl, 1) * B * IMG * sizeof(float)));
+    RET(reserve(h, h->hsum, (size_t)std::max(rows, 1) * sizeof(float)));
+    RET(reserve(h, h->reward, (size_t)std::max(rows, 1) * sizeof(float)));
+    RET(reserve(h, h->qs_out, (size_t)std::max(Sl, 1) * slab * 2 * sizeof(float)));
+    float* qs_mean = ptr<float>(h->qs_out);
+    float* qs_logvar = qs_mean + (size_t)std::max(Sl, 1) * slab;
+    if (Sl > 0) {
+        PoFcArgs fc{};
+        fc.map.B = B; fc.map.Sl = Sl; fc.map.sample0 = j0; fc.map.nsets = 3;
+        fc.map.site[0] = SITE_PO_A; fc.map.site[1] = SITE_PO_B1; fc.map.site[2] = SITE_PO_B2;
+        fc.z[0] = sp.mean_variant ? meanA : sampA;
+        fc.z[1] = sp.mean_variant ? meanB : sampB;
+        fc.z[2] = nullptr;
+        fc.mode[0] = 0; fc.mode[1] = 0; fc.mode[2] = 1;
+        fc.rp_mean = meanA + last_slot * slab; fc.rp_logvar = logvarA + last_slot * slab; fc.rp_site = SITE_RP_B;
+        fc.nk = sp.nk;
+        RET(run_decoder(h, st, fc, Sl * B, ptr<float>(h->img), ptr<float>(h->hsum), ptr<float>(h->reward)));
+        RET(run_encoder(h, st, ptr<float>(h->img), B, Sl, j0, SITE_QS_A, sp.nk, qs_mean, qs_logvar, nullptr));
+    }
+    StepFinalizeArgs fa{};
+    fa.B = B; fa.Sl = Sl; fa.logvarA = logvarA; fa.qs_logvar = qs_logvar;
+    fa.reward = ptr<float>(h->reward); fa.hsum = ptr<float>(h->hsum); fa.acc = sp.acc;
+    fa.carry_src = sp.carry_dst ? ((sp.carry_mean ? meanA : sampA) + last_slot * slab) : nullptr;
+    fa.carry_dst = sp.carry_dst;
+    // outputs of the last sample are read before the carry overwrites anything they alias
+    if (sp.out_ps1) CK(cudaMemcpyAsync(sp.out_ps1, sampA + last_slot * slab, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sp.out_mean) CK(cudaMemcpyAsync(sp.out_mean, meanA + last_slot * slab, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sp.out_logvar) CK(cudaMemcpyAsync(sp.out_logvar, logvarA + last_slot * slab, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sp.out_po1) {
+        if (own_last) {
+            CK(cudaMemcpyAsync(sp.out_po1, ptr<float>(h->img) + (size_t)(Sl - 1) * B * IMG, (size_t)B * IMG * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+        } else {
+            // this rank does not hold the last sample: decode it once more (same noise key => same image on every rank)
+            PoFcArgs fc{};
+            fc.map.B = B; fc.map.Sl = 1; fc.map.sample0 = S - 1; fc.map.nsets = 1;
+            fc.map.site[0] = SITE_PO_A; fc.map.site[1] = SITE_PO_A; fc.map.site[2] = SITE_PO_A;
+            fc.z[0] = sampA + last_slot * slab; fc.mode[0] = 0;
+            fc.nk = sp.nk;
+            RET(reserve(h, h->scratch, (size_t)2 * B * sizeof(float)));
+            RET(run_decoder(h, st, fc, B, sp.out_po1, ptr<float>(h->scratch), ptr<float>(h->scratch) + B));
+        }
+    }
+    h->launches += launch_step_finalize(fa, st);
+    return post_launch(h, "step finalize");
+}
+
+__global__ void k_fill_eye(float* pi, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 4) pi[i] = ((i >> 2) & 3) == (i & 3) ? 1.0f : 0.0f;
+}
+
+int finish_outputs(dai_handle* h, cudaStream_t st, int B, int samples, double* sums, float* G, float* t0, float* t1, float* t2) {
+    double* acc = ptr<double>(h->acc);
+    if (sums) CK(cudaMemcpyAsync(sums, acc, (size_t)4 * B * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (G || t0 || t1 || t2) h->launches += launch_combine(acc, B, samples, G, t0, t1, t2, st);
+    return post_launch(h, "combine");
+}
+
+int rollout_impl(dai_handle* h, cudaStream_t st, const float* o, const float* pi, int B, int steps, int samples,
+                 int calc_mean, int four, int j0, int j1, double* sums, float* G, float* t0, float* t1, float* t2,
+                 float* po1) {
+    if (B <= 0 || steps <= 0 || samples <= 0 || j0 < 0 || j1 > samples || j0 > j1)
+        return fail(h, DAI_E_INVALID, "rollout: bad sizes B=%d steps=%d samples=%d range=[%d,%d)", B, steps, samples, j0, j1);
+    if (!pi && (B % 4) != 0) return fail(h, DAI_E_INVALID, "rollout: pi == NULL needs B %% 4 == 0 (row = root*4 + action)");
+    const uint64_t call = h->call++;
+    ++h->calls;
+    NoiseKey nk = make_key(h, call, 0);
+    const size_t slab = (size_t)B * S_DIM;
+    RET(reserve(h, h->root, 3 * slab * sizeof(float)));
+    RET(reserve(h, h->carry, slab * sizeof(float)));
+    RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
+    float* m0 = ptr<float>(h->root);
+    float* lv0 = m0 + slab;
+    float* smp0 = lv0 + slab;
+    // qs0 = encoder(o) (+ reparameterize), src/torchmodel.py:228-229 / :248-249
+    RET(run_encoder(h, st, o, B, 1, 0, SITE_QS_ROOT, nk, m0, lv0, smp0));
+    CK(cudaMemcpyAsync(h->carry.p, calc_mean ? m0 : smp0, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
+    if (!pi) {
+        RET(reserve(h, h->pi_eye, (size_t)B * 4 * sizeof(float)));
+        k_fill_eye<<<(B * 4 + 255) / 256, 256, 0, st>>>(ptr<float>(h->pi_eye), B);
+        ++h->launches;
+        pi = ptr<float>(h->pi_eye);
+    }
+    const int mean_variant = (four && calc_mean) ? 1 : 0;
+    for (int t = 0; t < steps; ++t) {
+        StepSpec sp;
+        sp.s0 = ptr<float>(h->carry); sp.pi = pi; sp.B = B;
+        sp.samples = samples; sp.j0 = j0; sp.j1 = j1; sp.mean_variant = mean_variant;
+        sp.nk = nk; sp.nk.step = (uint32_t)t;
+        sp.acc = ptr<double>(h->acc);
+        sp.carry_dst = ptr<float>(h->carry); sp.carry_mean = calc_mean;
+        sp.out_po1 = (t == steps - 1) ? po1 : nullptr;
+        RET(run_step(h, st, sp));
+    }
+    return finish_outputs(h, st, B, mean_variant ? 1 : samples, sums, G, t0, t1, t2);
+}
+
+}  // namespace
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+const char* dai_version(void) { return "dai_b200 0.1 (sm_100a)"; }
+
+int dai_create(const dai_config* cfg, int device, dai_handle** out) {
+    if (!cfg || !out) return DAI_E_INVALID;
+    *out = nullptr;
+    if (cfg->s_dim != 10 || cfg->pi_dim != 4 || cfg->resolution != 64 || cfg->colour_channels != 1)
+        return DAI_E_UNSUPPORTED;   // the 32-px / 3-action branch is dead in the reference
+    if (cfg->precision < DAI_PREC_FP32_SIMT || cfg->precision > DAI_PREC_BF16X1) return DAI_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return DAI_E_CUDA;
+    }
+    dai_handle* h = new (std::nothrow) dai_handle();
+    if (!h) return DAI_E_NOMEM;
+    h->cfg = *cfg;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return DAI_E_CUDA; }
+    if (cudaMallocHost(&h->pinned, 4096) != cudaSuccess) { delete h; return DAI_E_NOMEM; }
+    h->pinned_cap = 4096;
+    *out = h;
+    return DAI_OK;
+}
+
+int dai_destroy(dai_handle* h) {
+    if (!h) return DAI_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
+                      &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (void* p : h->wallocs) cudaFree(p);
+    tc_release(&h->tcw);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+    return DAI_OK;
+}
+
+const char* dai_last_error(const dai_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int dai_set_weight(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+    if (!h || !key || !data || !shape) return DAI_E_INVALID;
+    for (int i = 0; i < kNumSpecs; ++i) {
+        if (strcmp(kSpecs[i].key, key) != 0) continue;
+        if (ndim != kSpecs[i].ndim) return fail(h, DAI_E_INVALID, "%s: ndim %d, expected %d", key, ndim, kSpecs[i].ndim);
+        size_t n = 1;
+        for (int d = 0; d < ndim; ++d) {
+            if (shape[d] != kSpecs[i].shape[d])
+                return fail(h, DAI_E_INVALID, "%s: dim %d is %lld, expected %lld", key, d, (long long)shape[d],
+                            (long long)kSpecs[i].shape[d]);
+            n *= (size_t)shape[d];
+        }
+        CK(cudaSetDevice(h->device));
+        std::vector<float>& v = h->raw[key];
+        v.resize(n);
+        CK(cudaMemcpy(v.data(), data, n * sizeof(float), cudaMemcpyDefault));
+        h->committed = false;
+        return DAI_OK;
+    }
+    return fail(h, DAI_E_INVALID, "unknown weight key %s", key);
+}
+
+int dai_commit_weights(dai_handle* h, void* stream) {
+    if (!h) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return commit(h);
+}
+
+int dai_set_rng(dai_handle* h, uint64_t seed, uint64_t call_index) {
+    if (!h) return DAI_E_INVALID;
+    h->seed = seed; h->call = call_index;
+    return DAI_OK;
+}
+
+int dai_get_rng(const dai_handle* h, uint64_t* seed, uint64_t* call_index) {
+    if (!h) return DAI_E_INVALID;
+    if (seed) *seed = h->seed;
+    if (call_index) *call_index = h->call;
+    return DAI_OK;
+}
+
+int dai_set_training(dai_handle* h, int training) {
+    if (!h) return DAI_E_INVALID;
+    h->cfg.training = training ? 1 : 0;
+    return DAI_OK;
+}
+
+int dai_set_precision(dai_handle* h, int precision) {
+    if (!h) return DAI_E_INVALID;
+    if (precision < DAI_PREC_FP32_SIMT || precision > DAI_PREC_BF16X1) return fail(h, DAI_E_INVALID, "unknown precision %d", precision);
+    h->cfg.precision = precision;
+    return DAI_OK;
+}
+
+int dai_get_stats(dai_handle* h, dai_stats* out, int reset) {
+    if (!h || !out) return DAI_E_INVALID;
+    out->kernel_launches = h->launches;
+    out->calls = h->calls;
+    size_t total = 0;
+    DevBuf* bufs[] = {&h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
+                      &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
+    for (DevBuf* b : bufs) total += b->cap;
+    out->workspace_bytes = total;
+    if (reset) { h->launches = 0; h->calls = 0; }
+    return DAI_OK;
+}
+
+int dai_encode(dai_handle* h, const float* o, int B, float* mean, float* logvar, float* sample, void* stream) {
+    RET(check_ready(h));
+    if (!o || !mean || !logvar || B <= 0) return fail(h, DAI_E_INVALID, "encode: bad arguments");
+    const NoiseKey nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    return run_encoder(h, (cudaStream_t)stream, o, B, 1, 0, SITE_QS_ROOT, nk, mean, logvar, sample);
+}
+
+int dai_decode(dai_handle* h, const float* s, int B, float* po, void* stream) {
+    RET(check_ready(h));
+    if (!s || !po || B <= 0) return fail(h, DAI_E_INVALID, "decode: bad arguments");
+    PoFcArgs fc{};
+    fc.map.B = B; fc.map.Sl = 1; fc.map.sample0 = 0; fc.map.nsets = 1;
+    fc.map.site[0] = fc.map.site[1] = fc.map.site[2] = SITE_PO_A;
+    fc.z[0] = s; fc.mode[0] = 0;
+    fc.nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    RET(reserve(h, h->scratch, (size_t)2 * B * sizeof(float)));
+    return run_decoder(h, (cudaStream_t)stream, fc, B, po, ptr<float>(h->scratch), ptr<float>(h->scratch) + B);
+}
+
+int dai_transition(dai_handle* h, const float* pi, const float* s0, int B, float* mean, float* logvar, float* sample,
+                   void* stream) {
+    RET(check_ready(h));
+    if (!pi || !s0 || !mean || !logvar || B <= 0) return fail(h, DAI_E_INVALID, "transition: bad arguments");
+    PsArgs pa{};
+    pa.pi = pi; pa.s0 = s0; pa.B = B; pa.nA = 1; pa.nB = 0; pa.sample0 = 0; pa.extra_slot = -1;
+    pa.siteA = SITE_PS_A; pa.siteB = SITE_PS_B;
+    pa.meanA = mean; pa.logvarA = logvar; pa.sampA = sample;
+    pa.nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    h->launches += launch_ps(h->w, pa, (cudaStream_t)stream);
+    return post_launch(h, "transition");
+}
+
+int dai_habit(dai_handle* h, const float* s, int B, float* logits, float* q, float* logq, void* stream) {
+    RET(check_ready(h));
+    if (!s || B <= 0) return fail(h, DAI_E_INVALID, "habit: bad arguments");
+    ++h->calls;
+    h->launches += launch_qpi(h->w, s, B, logits, q, logq, (cudaStream_t)stream);
+    return post_launch(h, "habit");
+}
+
+int dai_check_reward(dai_handle* h, const float* o, int B, float* r, void* stream) {
+    if (!h) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!o || !r || B <= 0) return fail(h, DAI_E_INVALID, "check_reward: bad arguments");
+    ++h->calls;
+    h->launches += launch_reward_only(o, B, r, (cudaStream_t)stream);
+    return post_launch(h, "check_reward");
+}
+
+int dai_calculate_G(dai_handle* h, const float* s0, const float* pi0, int B, int samples, int sample_begin,
+                    int sample_end, double* sums, float* G, float* t0, float* t1, float* t2, float* ps1,
+                    float* ps1_mean, float* ps1_logvar, float* po1, void* stream) {
+    RET(check_ready(h));
+    if (!s0 || !pi0 || B <= 0 || samples <= 0 || sample_begin < 0 || sample_end > samples || sample_begin > sample_end)
+        return fail(h, DAI_E_INVALID, "calculate_G: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
+    CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
+    StepSpec sp;
+    sp.s0 = s0; sp.pi = pi0; sp.B = B; sp.samples = samples; sp.j0 = sample_begin; sp.j1 = sample_end;
+    sp.nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    sp.acc = ptr<double>(h->acc);
+    sp.out_ps1 = ps1; sp.out_mean = ps1_mean; sp.out_logvar = ps1_logvar; sp.out_po1 = po1;
+    RET(run_step(h, st, sp));
+    return finish_outputs(h, st, B, samples, sums, G, t0, t1, t2);
+}
+
+int dai_calculate_G_mean(dai_handle* h, const float* s0, const float* pi0, int B, float* G, float* t0, float* t1,
+                         float* t2, float* ps1_mean, float* po1, void* stream) {
+    RET(check_ready(h));
+    if (!s0 || !pi0 || B <= 0) return fail(h, DAI_E_INVALID, "calculate_G_mean: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
+    CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
+    StepSpec sp;
+    sp.s0 = s0; sp.pi = pi0; sp.B = B; sp.mean_variant = 1;
+    sp.nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    sp.acc = ptr<double>(h->acc);
+    sp.out_mean = ps1_mean; sp.out_po1 = po1;
+    RET(run_step(h, st, sp));
+    return finish_outputs(h, st, B, 1, nullptr, G, t0, t1, t2);
+}
+
+int dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, const float* ps1_mean,
+                           const float* ps1_logvar, const float* pi0, int D, float* G, void* stream) {
+    RET(check_ready(h));
+    if (!s0 || !ps1 || !ps1_mean || !ps1_logvar || !pi0 || D <= 0 || D > 256)
+        return fail(h, DAI_E_INVALID, "G_given_trajectory: bad arguments (1 <= depth <= 256)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const NoiseKey nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    const size_t slab = (size_t)D * S_DIM;
+    RET(reserve(h, h->ps, slab * sizeof(float)));
+    float* sampB = ptr<float>(h->ps);
+    PsArgs pa{};
+    pa.pi = pi0; pa.s0 = s0; pa.B = D; pa.nA = 0; pa.nB = 1; pa.sample0 = 0; pa.extra_slot = -1;
+    pa.siteA = SITE_PS_A; pa.siteB = SITE_PS_B; pa.sampB = sampB; pa.nk = nk;
+    h->launches += launch_ps(h->w, pa, st);
+    RET(post_launch(h, "transition"));
+    RET(reserve(h, h->img, (size_t)D * IMG * sizeof(float)));
+    RET(reserve(h, h->hsum, (size_t)3 * D * sizeof(float)));
+    RET(reserve(h, h->reward, (size_t)3 * D * sizeof(float)));
+    RET(reserve(h, h->qs_out, 2 * slab * sizeof(float)));
+    PoFcArgs fc{};
+    fc.map.B = D; fc.map.Sl = 1; fc.map.sample0 = 0; fc.map.nsets = 3;
+    fc.map.site[0] = SITE_PO_A; fc.map.site[1] = SITE_PO_B1; fc.map.site[2] = SITE_PO_B2;
+    fc.z[0] = ps1; fc.z[1] = sampB; fc.mode[0] = 0; fc.mode[1] = 0; fc.mode[2] = 1;
+    fc.rp_mean = ps1_mean; fc.rp_logvar = ps1_logvar; fc.rp_site = SITE_RP_B; fc.nk = nk;
+    RET(run_decoder(h, st, fc, D, ptr<float>(h->img), ptr<float>(h->hsum), ptr<float>(h->reward)));
+    float* qs_mean = ptr<float>(h->qs_out);
+    float* qs_logvar = qs_mean + slab;
+    RET(run_encoder(h, st, ptr<float>(h->img), D, 1, 0, SITE_QS_A, nk, qs_mean, qs_logvar, nullptr));
+    RET(reserve(h, h->scratch, 16 * sizeof(float)));
+    h->launches += launch_traj_G(ptr<float>(h->reward), ptr<float>(h->hsum), ps1_logvar, qs_logvar, D, G,
+                                 ptr<float>(h->scratch), st);
+    return post_launch(h, "trajectory G");
+}
+
+int dai_rollout(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples, int calc_mean, int four,
+                int sample_begin, int sample_end, double* sums, float* G, float* t0, float* t1, float* t2, float* po1,
+                void* stream) {
+    RET(check_ready(h));
+    if (!o) return fail(h, DAI_E_INVALID, "rollout: o is NULL");
+    return rollout_impl(h, (cudaStream_t)stream, o, pi, B, steps, samples, calc_mean, four, sample_begin, sample_end,
+                        sums, G, t0, t1, t2, po1);
+}
+
+int dai_combine(dai_handle* h, const double* sums, int B, int samples, float* G, float* t0, float* t1, float* t2,
+                void* stream) {
+    if (!h || !sums || B <= 0 || samples <= 0) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    h->launches += launch_combine(sums, B, samples, G, t0, t1, t2, (cudaStream_t)stream);
+    return post_launch(h, "combine");
+}
+
+int dai_rollout_host(dai_handle* h, const float* o_host, const float* pi_host, int B, int steps, int samples,
+                     int calc_mean, int four, float* G_host, float* t0_host, float* t1_host, float* t2_host,
+                     float* po1_host, void* stream) {
+    RET(check_ready(h));
+    if (!o_host || B <= 0) return fail(h, DAI_E_INVALID, "rollout_host: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t in_bytes = (size_t)B * IMG * sizeof(float) + (size_t)B * 4 * sizeof(float);
+    const size_t out_f = (size_t)4 * B + (po1_host ? (size_t)B * IMG : 0);
+    RET(reserve(h, h->stage_in, in_bytes));
+    RET(reserve(h, h->stage_out, out_f * sizeof(float)));
+    float* o_dev = ptr<float>(h->stage_in);
+    float* pi_dev = o_dev + (size_t)B * IMG;
+    CK(cudaMemcpyAsync(o_dev, o_host, (size_t)B * IMG * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (pi_host) CK(cudaMemcpyAsync(pi_dev, pi_host, (size_t)B * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    float* Gd = ptr<float>(h->stage_out);
+    float* po1d = po1_host ? Gd + 4 * (size_t)B : nullptr;
+    RET(rollout_impl(h, st, o_dev, pi_host ? pi_dev : nullptr, B, steps, samples, calc_mean, four, 0, samples, nullptr,
+                     Gd, Gd + B, Gd + 2 * B, Gd + 3 * B, po1d));
+    if (G_host) CK(cudaMemcpyAsync(G_host, Gd, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (t0_host) CK(cudaMemcpyAsync(t0_host, Gd + B, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (t1_host) CK(cudaMemcpyAsync(t1_host, Gd + 2 * B, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (t2_host) CK(cudaMemcpyAsync(t2_host, Gd + 3 * B, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (po1_host) CK(cudaMemcpyAsync(po1_host, po1d, (size_t)B * IMG * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DAI_OK;
+}
+
+int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means, float* G_host, float* pi0,
+                      float* qpi, void* stream) {
+    RET(check_ready(h));
+    if (!starting_s || !G_host || !pi0 || !qpi || depth <= 0 || depth > 256)
+        return fail(h, DAI_E_INVALID, "mcts_simulate: bad arguments (1 <= depth <= 256)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t slab = (size_t)depth * S_DIM;
+    RET(reserve(h, h->traj, 4 * slab * sizeof(float)));
+    float* s0 = ptr<float>(h->traj);
+    SimArgs sa{};
+    sa.start = starting_s; sa.depth = depth; sa.use_means = use_means;
+    sa.s0 = s0; sa.ps1 = s0 + slab; sa.mean = s0 + 2 * slab; sa.logvar = s0 + 3 * slab;
+    sa.pi0 = pi0; sa.qpi = qpi;
+    sa.nk = make_key(h, h->call++, 0);
+    h->launches += launch_sim_rollout(h->w, sa, st);
+    RET(post_launch(h, "simulate rollout"));
+    // calculate_G_given_trajectory over the depth rows (next call index), mean -> host (src/torchmodel.py:392)
+    RET(dai_G_given_trajectory(h, sa.s0, sa.ps1, sa.mean, sa.logvar, pi0, depth, nullptr, stream));
+    CK(cudaMemcpyAsync(h->pinned, h->scratch.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *G_host = h->pinned[0];
+    return DAI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Shared device helpers: keyed Philox noise, row maps, reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dai {
+
+constexpr int S_DIM = 10;
+constexpr int PI_DIM = 4;
+constexpr int IMG = 4096;            // 64*64*1
+
+// noise sites, one per reference RNG draw inside one MC sample (SURVEY.md §8 a5 order);
+// must match oracle/philox.py SITES.
+constexpr int SITE_PS_A = 0, SITE_PO_A = 4, SITE_QS_A = 8, SITE_PS_B = 12, SITE_PO_B1 = 16,
+              SITE_RP_B = 20, SITE_PO_B2 = 21, SITE_QS_ROOT = 32, SITE_CAT = 40;
+
+struct NoiseKey {
+    uint32_t k0, k1;     // seed + call_index
+    uint32_t step;
+    int32_t training;    // 0: dropout is identity
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += W0; k1 += W1;
+    }
+    return c;
+}
+
+// 128 random bits for (site, block) of (row, sample) at this key/step
+__device__ __forceinline__ uint4 noise_block(const NoiseKey& nk, uint32_t site, uint32_t blk,
+                                             uint32_t row, uint32_t sample) {
+    return philox4x32_10(make_uint4(blk | (site << 16), row, sample, nk.step), nk.k0, nk.k1);
+}
+
+// standard normal for element e: Box-Muller in fp64 on words 0,1 of block e, rounded once
+__device__ __forceinline__ float noise_normal(const NoiseKey& nk, uint32_t site, uint32_t e,
+                                              uint32_t row, uint32_t sample) {
+    const uint4 w = noise_block(nk, site, e, row, sample);
+    const double u1 = ((double)w.x + 0.5) * (1.0 / 4294967296.0);
+    const double u2 = ((double)w.y + 0.5) * (1.0 / 4294967296.0);
+    return (float)(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2));
+}
+
+__device__ __forceinline__ float noise_uniform24(const NoiseKey& nk, uint32_t site, uint32_t row,
+                                                 uint32_t sample) {
+    const uint4 w = noise_block(nk, site, 0, row, sample);
+    return (float)(w.x >> 8) * (1.0f / 16777216.0f);
+}
+
+// reparameterize (src/torchmodel.py:54-56): eps * exp(0.5*logvar) + mean, mul then add like torch
+__device__ __forceinline__ float reparam(float eps, float mean, float logvar) {
+    return __fadd_rn(__fmul_rn(eps, expf(__fmul_rn(logvar, 0.5f))), mean);
+}
+
+// Rows of a batched net launch are ordered (set, local sample, b); set selects the noise
+// site base (which of the reference's decoder/transition calls this row stands for).
+struct RowMap {
+    int32_t B;          // (state, action) rows of the call
+    int32_t Sl;         // sample slots per set held by this rank
+    int32_t sample0;    // global index of local sample slot 0
+    int32_t nsets;
+    int32_t site[3];    // noise site base per set
+    __device__ __forceinline__ void decode(int r, int& set, int& slot, int& b) const {
+        b = r % B;
+        const int q = r / B;
+        slot = q % Sl;
+        set = q / Sl;
+    }
+    __device__ __forceinline__ uint32_t sample_of(int slot) const { return (uint32_t)(sample0 + slot); }
+    __host__ __device__ int rows() const { return nsets * Sl * B; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dai

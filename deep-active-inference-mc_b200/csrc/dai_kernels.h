@@ -1,0 +1,119 @@
+// Host-side launch interface of the kernels (internal; the public boundary is include/dai_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dai_common.cuh"
+
+namespace dai {
+
+// Repacked fp32 weights (built once in dai_commit_weights).
+//   *_t  : hidden FC layers transposed to [Kpad][N] (coalesced over outputs)
+//   tail FCs keep torch's [N][K] (warp-per-output dot products)
+//   convs: [tap = kh*3+kw][Cin][Cout]
+struct DevWeights {
+    // Ps: 14->512->512->512->20 (src/torchmodel.py:41-52)
+    float *ps_w0t, *ps_b0, *ps_w1t, *ps_b1, *ps_w2t, *ps_b2, *ps_w3, *ps_b3;
+    // Po FCs: 10->256->256->256->16384 (:107-118); FC4 columns permuted to NHWC (h,w,c)
+    float *po_w0t, *po_b0, *po_w1t, *po_b1, *po_w2t, *po_b2, *po_w3t, *po_b3;
+    // Po deconvs (:120-126)
+    float *ct1_w, *ct1_b, *ct2_w, *ct2_b, *ct3_w, *ct3_b, *ct4_w, *ct4_b;
+    // Qs convs (:85-92) and FCs (:94-103, FC1 rows permuted to the NHWC flatten)
+    float *qc1_w, *qc1_b, *qc2_w, *qc2_b, *qc3_w, *qc3_b, *qc4_w, *qc4_b;
+    float *qf0_t, *qf0_b, *qf1_t, *qf1_b, *qf2_t, *qf2_b, *qf3, *qf3_b;
+    // Qpi: 10->128->128->4 (:19-25)
+    float *pi_w0t, *pi_b0, *pi_w1t, *pi_b1, *pi_w2, *pi_b2;
+};
+
+// ---- transition net ------------------------------------------------------------------
+struct PsArgs {
+    const float* pi;      // [B][4]
+    const float* s0;      // [B][10]
+    int32_t B;
+    int32_t nA, nB;       // sample slots of the loop-2a set (site siteA) and loop-2b set (siteB)
+    int32_t sample0;      // global sample of slot 0 (both sets)
+    int32_t extra_slot;   // >= 0: loop-2a slot that stands for global sample `extra_sample`
+    int32_t extra_sample;
+    int32_t siteA, siteB;
+    float *meanA, *logvarA, *sampA;   // [nA][B][10]
+    float *meanB, *logvarB, *sampB;   // [nB][B][10] (any may be null)
+    NoiseKey nk;
+};
+int  launch_ps(const DevWeights& w, const PsArgs& a, cudaStream_t st);
+
+// ---- decoder -------------------------------------------------------------------------
+struct PoFcArgs {
+    RowMap map;
+    const float* z[3];     // per set: latent rows [Sl][B][10] (mode 0)
+    int32_t mode[3];       // 0: direct, 1: reparameterize(rp_mean[b], rp_logvar[b]) with site rp_site
+    int32_t zbcast[3];     // 1: z is [B][10] shared by all slots
+    const float *rp_mean, *rp_logvar;   // [B][10]
+    int32_t rp_site;
+    float* h3;             // [rows][256]
+    NoiseKey nk;
+};
+int  launch_po_fc123(const DevWeights& w, const PoFcArgs& a, cudaStream_t st);
+
+// permuted dropout mask bits of the 16384-wide FC4 output, [rows][512] words in NHWC bit order
+int  launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, cudaStream_t st);
+
+// fp32 SIMT layers over a chunk of decoder rows [row0, row0+nrows)
+int  launch_fc4_simt(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, float* act0, cudaStream_t st);
+int  launch_ct1_simt(const DevWeights& w, const float* act0, int nrows, float* act1, cudaStream_t st);
+int  launch_ct2_simt(const DevWeights& w, const float* act1, int nrows, float* act2, cudaStream_t st);
+int  launch_ct3_simt(const DevWeights& w, const float* act2, int nrows, float* act3, cudaStream_t st);
+
+// last deconv + sigmoid + EFE pixel terms.  Per row: hsum = sum_px H_bernoulli(p),
+// reward = check_reward(p).  Rows of set 0 (r < img_rows) also write the image.
+struct Ct4Args {
+    const float* act3;     // [nrows][64][64][32]
+    int32_t row0, nrows;   // global row offset of this chunk
+    int32_t img_rows;      // global rows < img_rows write img[r]
+    float* img;            // [img_rows][4096]
+    float* hsum;           // [rows]
+    float* reward;         // [rows]
+};
+int  launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st);
+
+// ---- encoder -------------------------------------------------------------------------
+struct QsArgs {
+    const float* img;      // [rows][4096]
+    int32_t rows;
+    RowMap map;            // nsets = 1; noise site base map.site[0]
+    float *c1, *c2, *c3, *c4;   // workspaces: [rows][31*31*32], [rows][15*15*32], [rows][7*7*64], [rows][576]
+    float *mean, *logvar, *samp;   // [rows][10]; samp may be null
+    NoiseKey nk;
+};
+int  launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st);
+
+// ---- habit net -----------------------------------------------------------------------
+int  launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float* q, float* logq, cudaStream_t st);
+
+// ---- scalar glue -----------------------------------------------------------------------
+struct StepFinalizeArgs {
+    int32_t B, Sl;
+    const float* logvarA;  // [>=Sl][B][10] transition logvar of the loop-2a slots
+    const float* qs_logvar;// [Sl][B][10]
+    const float* reward;   // [3*Sl*B] (set 0 used)
+    const float* hsum;     // [3*Sl*B] (sets 1,2 used)
+    double* acc;           // [4][B] += sums of term0, term1, term2_1, term2_2
+    const float* carry_src;// [B][10] or null
+    float* carry_dst;      // [B][10]
+};
+int  launch_step_finalize(const StepFinalizeArgs& a, cudaStream_t st);
+int  launch_combine(const double* sums, int B, int samples, float* G, float* t0, float* t1, float* t2, cudaStream_t st);
+int  launch_reward_only(const float* o, int B, float* r, cudaStream_t st);
+int  launch_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
+                   int D, float* G, float* Gmean, cudaStream_t st);
+
+// habit-policy rollout of mcts_step_simulate: `depth` sequential (Qpi -> categorical -> Ps) steps
+struct SimArgs {
+    const float* start;    // [10]
+    int32_t depth, use_means;
+    float *s0, *ps1, *mean, *logvar, *pi0;   // [depth][10|4]
+    float* qpi;            // [4]
+    NoiseKey nk;
+};
+int  launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st);
+
+
+}  // namespace dai

@@ -1,0 +1,852 @@
+// CUDA-core (fp32) kernels of the EFE rollout path: the small fused MLPs (Ps, Po-FC1..3,
+// Qs-FC, Qpi), the pixel-term kernel (last deconv + sigmoid + Bernoulli entropy + reward),
+// the scalar glue, and an fp32 gather-GEMM used for every contraction layer in
+// DAI_PREC_FP32_SIMT mode (the on-device exact reference for the tcgen05 kernels).
+#include "dai_kernels.h"
+
+namespace dai {
+
+// ======================================================================================
+// fused-MLP building blocks: activations of TM rows live in shared memory
+// ======================================================================================
+
+// y[r][n] = relu(bias[n] + sum_k x[r][k] * Wt[k][n]) (* dropout), all NT threads take part
+template <int TM, int NT>
+__device__ __forceinline__ void dense_hidden(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                             int K, int N, const float* xs, int xstride, float* ys, int ystride,
+                                             const uint32_t* mw, int mwstride) {
+    for (int n = threadIdx.x; n < N; n += NT) {
+        float acc[TM];
+        const float bn = __ldg(bias + n);
+#pragma unroll
+        for (int r = 0; r < TM; ++r) acc[r] = bn;
+#pragma unroll 4
+        for (int k = 0; k < K; k += 4) {
+            const float w0 = __ldg(Wt + (size_t)(k + 0) * N + n);
+            const float w1 = __ldg(Wt + (size_t)(k + 1) * N + n);
+            const float w2 = __ldg(Wt + (size_t)(k + 2) * N + n);
+            const float w3 = __ldg(Wt + (size_t)(k + 3) * N + n);
+#pragma unroll
+            for (int r = 0; r < TM; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(xs + r * xstride + k);
+                acc[r] = fmaf(x.x, w0, acc[r]);
+                acc[r] = fmaf(x.y, w1, acc[r]);
+                acc[r] = fmaf(x.z, w2, acc[r]);
+                acc[r] = fmaf(x.w, w3, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TM; ++r) {
+            float v = fmaxf(acc[r], 0.0f);
+            if (mw) v = ((mw[r * mwstride + (n >> 5)] >> (n & 31)) & 1u) ? v * 2.0f : 0.0f;
+            ys[r * ystride + n] = v;
+        }
+    }
+}
+
+// out[r][n] = bias[n] + sum_k x[r][k] * W[n][k]; one warp per output
+template <int TM, int NT>
+__device__ __forceinline__ void dense_tail(const float* __restrict__ W, const float* __restrict__ bias,
+                                           int K, int N, const float* xs, int xstride, float* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < TM * N; o += NT / 32) {
+        const int r = o / N, n = o % N;
+        float p = 0.0f;
+        for (int k = lane; k < K; k += 32) p = fmaf(xs[r * xstride + k], __ldg(W + (size_t)n * K + k), p);
+        p = warp_sum(p);
+        if (lane == 0) out[r * N + n] = p + __ldg(bias + n);
+    }
+}
+
+// dropout mask words for TM rows x N outputs at site (rsite[r] + layer)
+template <int TM, int NT>
+__device__ __forceinline__ void fill_masks(uint32_t* mw, int N, const NoiseKey& nk, int layer,
+                                           const int* rsite, const int* rb, const uint32_t* rsample) {
+    const int nblk = N >> 7;
+    for (int i = threadIdx.x; i < TM * nblk; i += NT) {
+        const int r = i / nblk, blk = i % nblk;
+        const uint4 w = noise_block(nk, (uint32_t)(rsite[r] + layer), (uint32_t)blk, (uint32_t)rb[r], rsample[r]);
+        uint32_t* d = mw + r * (N >> 5) + blk * 4;
+        d[0] = w.x; d[1] = w.y; d[2] = w.z; d[3] = w.w;
+    }
+}
+
+// ======================================================================================
+// Ps: transition net (src/torchmodel.py:41-66)
+// ======================================================================================
+constexpr int PS_TM = 8, PS_NT = 512;
+
+__global__ void __launch_bounds__(PS_NT) k_ps(DevWeights w, PsArgs a) {
+    __shared__ __align__(16) float x0[PS_TM][16];
+    __shared__ __align__(16) float hA[PS_TM][512];
+    __shared__ __align__(16) float hB[PS_TM][512];
+    __shared__ uint32_t mw[PS_TM][16];
+    __shared__ float out[PS_TM][20];
+    __shared__ int rsite[PS_TM], rb[PS_TM], rslot[PS_TM], rset[PS_TM];
+    __shared__ uint32_t rsample[PS_TM];
+
+    const int rows = (a.nA + a.nB) * a.B;
+    const int r0 = blockIdx.x * PS_TM;
+    const int tid = threadIdx.x;
+    if (tid < PS_TM) {
+        int r = r0 + tid;
+        const bool valid = r < rows;
+        if (!valid) r = rows - 1;
+        const int b = r % a.B, q = r / a.B;
+        const int set = q < a.nA ? 0 : 1;
+        const int slot = set == 0 ? q : q - a.nA;
+        rb[tid] = b; rset[tid] = valid ? set : -1; rslot[tid] = slot;
+        rsite[tid] = set == 0 ? a.siteA : a.siteB;
+        rsample[tid] = (set == 0 && slot == a.extra_slot) ? (uint32_t)a.extra_sample : (uint32_t)(a.sample0 + slot);
+    }
+    __syncthreads();
+    if (tid < PS_TM * 16) {
+        const int r = tid >> 4, k = tid & 15, b = rb[r];
+        float v = 0.0f;
+        if (k < 4) v = a.pi[b * 4 + k];
+        else if (k < 14) v = a.s0[b * 10 + (k - 4)];
+        x0[r][k] = v;
+    }
+    const bool drop = a.nk.training != 0;
+    if (drop) fill_masks<PS_TM, PS_NT>(&mw[0][0], 512, a.nk, 0, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PS_TM, PS_NT>(w.ps_w0t, w.ps_b0, 16, 512, &x0[0][0], 16, &hA[0][0], 512, drop ? &mw[0][0] : nullptr, 16);
+    __syncthreads();
+    if (drop) fill_masks<PS_TM, PS_NT>(&mw[0][0], 512, a.nk, 1, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PS_TM, PS_NT>(w.ps_w1t, w.ps_b1, 512, 512, &hA[0][0], 512, &hB[0][0], 512, drop ? &mw[0][0] : nullptr, 16);
+    __syncthreads();
+    if (drop) fill_masks<PS_TM, PS_NT>(&mw[0][0], 512, a.nk, 2, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PS_TM, PS_NT>(w.ps_w2t, w.ps_b2, 512, 512, &hB[0][0], 512, &hA[0][0], 512, drop ? &mw[0][0] : nullptr, 16);
+    __syncthreads();
+    dense_tail<PS_TM, PS_NT>(w.ps_w3, w.ps_b3, 512, 20, &hA[0][0], 512, &out[0][0]);
+    __syncthreads();
+    if (tid < PS_TM * S_DIM) {
+        const int r = tid / S_DIM, d = tid % S_DIM;
+        if (rset[r] >= 0) {
+            const float mean = out[r][d], lv = out[r][S_DIM + d];
+            const float eps = noise_normal(a.nk, (uint32_t)(rsite[r] + 3), (uint32_t)d, (uint32_t)rb[r], rsample[r]);
+            const float s = reparam(eps, mean, lv);
+            const size_t o = ((size_t)rslot[r] * a.B + rb[r]) * S_DIM + d;
+            if (rset[r] == 0) {
+                a.meanA[o] = mean; a.logvarA[o] = lv; if (a.sampA) a.sampA[o] = s;
+            } else {
+                if (a.meanB) a.meanB[o] = mean;
+                if (a.logvarB) a.logvarB[o] = lv;
+                if (a.sampB) a.sampB[o] = s;
+            }
+        }
+    }
+}
+
+int launch_ps(const DevWeights& w, const PsArgs& a, cudaStream_t st) {
+    const int rows = (a.nA + a.nB) * a.B;
+    if (rows <= 0) return 0;
+    k_ps<<<(rows + PS_TM - 1) / PS_TM, PS_NT, 0, st>>>(w, a);
+    return 1;
+}
+
+// ======================================================================================
+// Po FC1..3 (src/torchmodel.py:107-115): latent (10) -> 256 -> 256 -> 256, each ReLU+dropout
+// ======================================================================================
+constexpr int PO_TM = 8, PO_NT = 256;
+
+__global__ void __launch_bounds__(PO_NT) k_po_fc123(DevWeights w, PoFcArgs a) {
+    __shared__ __align__(16) float x0[PO_TM][12];
+    __shared__ __align__(16) float hA[PO_TM][256];
+    __shared__ __align__(16) float hB[PO_TM][256];
+    __shared__ uint32_t mw[PO_TM][8];
+    __shared__ int rsite[PO_TM], rb[PO_TM], rslot[PO_TM], rset[PO_TM];
+    __shared__ uint32_t rsample[PO_TM];
+
+    const int rows = a.map.rows();
+    const int r0 = blockIdx.x * PO_TM;
+    const int tid = threadIdx.x;
+    if (tid < PO_TM) {
+        int r = min(r0 + tid, rows - 1);
+        int set, slot, b;
+        a.map.decode(r, set, slot, b);
+        rb[tid] = b; rset[tid] = set; rslot[tid] = slot;
+        rsite[tid] = a.map.site[set];
+        rsample[tid] = a.map.sample_of(slot);
+    }
+    __syncthreads();
+    if (tid < PO_TM * 12) {
+        const int r = tid / 12, k = tid % 12, set = rset[r], b = rb[r];
+        float v = 0.0f;
+        if (k < S_DIM) {
+            if (a.mode[set] == 0) {
+                const size_t zr = a.zbcast[set] ? (size_t)b : (size_t)rslot[r] * a.map.B + b;
+                v = a.z[set][zr * S_DIM + k];
+            } else {
+                const float eps = noise_normal(a.nk, (uint32_t)a.rp_site, (uint32_t)k, (uint32_t)b, rsample[r]);
+                v = reparam(eps, a.rp_mean[b * S_DIM + k], a.rp_logvar[b * S_DIM + k]);
+            }
+        }
+        x0[r][k] = v;
+    }
+    const bool drop = a.nk.training != 0;
+    if (drop) fill_masks<PO_TM, PO_NT>(&mw[0][0], 256, a.nk, 0, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PO_TM, PO_NT>(w.po_w0t, w.po_b0, 12, 256, &x0[0][0], 12, &hA[0][0], 256, drop ? &mw[0][0] : nullptr, 8);
+    __syncthreads();
+    if (drop) fill_masks<PO_TM, PO_NT>(&mw[0][0], 256, a.nk, 1, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PO_TM, PO_NT>(w.po_w1t, w.po_b1, 256, 256, &hA[0][0], 256, &hB[0][0], 256, drop ? &mw[0][0] : nullptr, 8);
+    __syncthreads();
+    if (drop) fill_masks<PO_TM, PO_NT>(&mw[0][0], 256, a.nk, 2, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<PO_TM, PO_NT>(w.po_w2t, w.po_b2, 256, 256, &hB[0][0], 256, &hA[0][0], 256, drop ? &mw[0][0] : nullptr, 8);
+    __syncthreads();
+    for (int i = tid; i < PO_TM * 256; i += PO_NT) {
+        const int r = i >> 8, n = i & 255;
+        if (r0 + r < rows) a.h3[(size_t)(r0 + r) * 256 + n] = hA[r][n];
+    }
+}
+
+int launch_po_fc123(const DevWeights& w, const PoFcArgs& a, cudaStream_t st) {
+    const int rows = a.map.rows();
+    if (rows <= 0) return 0;
+    k_po_fc123<<<(rows + PO_TM - 1) / PO_TM, PO_NT, 0, st>>>(w, a);
+    return 1;
+}
+
+// ======================================================================================
+// FC4 dropout mask, permuted from the reference's flat index e = c*256 + p (Unflatten
+// (64,16,16), src/torchmodel.py:119) to the NHWC bit order n' = p*64 + c the layers use.
+// One CTA per row; words[512] per row.
+// ======================================================================================
+__global__ void __launch_bounds__(128) k_fc4_mask(RowMap map, NoiseKey nk, int row0, int nrows, uint32_t* mask) {
+    __shared__ uint32_t orig[512];
+    const int r = row0 + blockIdx.x;
+    int set, slot, b;
+    map.decode(r, set, slot, b);
+    const int tid = threadIdx.x;
+    uint32_t* out = mask + (size_t)blockIdx.x * 512;
+    const uint4 w = noise_block(nk, (uint32_t)(map.site[set] + 3), (uint32_t)tid, (uint32_t)b, map.sample_of(slot));
+    orig[tid * 4 + 0] = w.x; orig[tid * 4 + 1] = w.y; orig[tid * 4 + 2] = w.z; orig[tid * 4 + 3] = w.w;
+    __syncthreads();
+    for (int i = tid; i < 512; i += 128) {          // output word i covers n' = i*32 .. i*32+31
+        const int p = i >> 1, c0 = (i & 1) * 32;
+        uint32_t word = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const int e = (c0 + j) * 256 + p;
+            word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
+        }
+        out[i] = word;
+    }
+}
+
+int launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, cudaStream_t st) {
+    if (nrows <= 0) return 0;
+    k_fc4_mask<<<nrows, 128, 0, st>>>(map, nk, row0, nrows, mask);
+    return 1;
+}
+
+// ======================================================================================
+// fp32 gather-GEMM: C[m][n] = sum_tap sum_c A[src(m,tap)][c] * W[tap][c][n]
+// 256 threads as 16x16, micro-tile (BM/16)x(BN/16), BK = 16.
+// ======================================================================================
+struct ConvGeom {
+    int mode;            // 0: dense rows, 1: convT k3 s1 p1, 2: convT k3 s2 p1 op1 (phase = blockIdx.z), 3: conv k3 s2 valid
+    int M;               // GEMM rows (dense: rows; conv: images * Hm * Wm, the m-grid below)
+    int Hm, Wm;          // m-grid per image (mode 1,3: output grid; mode 2: input grid)
+    int Hin, Win, Cin;   // input feature map
+    int Hout, Wout, Cout;// output feature map (N total = Cout)
+    const float* in;
+    const float* W;      // [tap][Cin][Cout]
+    const float* bias;
+    float* out;
+    const uint32_t* mask;// dense only: dropout bits [M][Cout/32]
+};
+
+__device__ __forceinline__ int geom_ntaps(const ConvGeom& g, int phase) {
+    if (g.mode == 0) return 1;
+    if (g.mode == 2) return (1 + (phase >> 1)) * (1 + (phase & 1));
+    return 9;
+}
+
+struct Tap { int wtap, dy, dx; };
+
+// tap t of this phase -> weight tap index kh*3+kw and the input offset (iy = y*scale + dy)
+__device__ __forceinline__ Tap geom_tap(const ConvGeom& g, int t, int phase) {
+    Tap tp{0, 0, 0};
+    if (g.mode == 0) return tp;
+    if (g.mode == 2) {          // oy = 2*iy - 1 + kh; even rows: kh=1 (iy=y); odd rows: kh=0 (iy=y+1), kh=2 (iy=y)
+        const int py = phase >> 1, px = phase & 1;
+        const int nx = 1 + px;
+        const int ty = t / nx, tx = t - ty * nx;
+        int kh, kw;
+        if (py == 0) { kh = 1; tp.dy = 0; } else if (ty == 0) { kh = 0; tp.dy = 1; } else { kh = 2; tp.dy = 0; }
+        if (px == 0) { kw = 1; tp.dx = 0; } else if (tx == 0) { kw = 0; tp.dx = 1; } else { kw = 2; tp.dx = 0; }
+        tp.wtap = kh * 3 + kw;
+        return tp;
+    }
+    const int kh = t / 3, kw = t - kh * 3;
+    tp.wtap = t;
+    if (g.mode == 1) { tp.dy = 1 - kh; tp.dx = 1 - kw; }     // convT s1 p1: oy = iy - 1 + kh
+    else             { tp.dy = kh;     tp.dx = kw; }         // conv s2 valid: iy = 2*oy + kh
+    return tp;
+}
+
+// source row pointer of GEMM row m for this tap (null = zero row)
+__device__ __forceinline__ const float* geom_src(const ConvGeom& g, int m, const Tap& tp) {
+    if (m >= g.M) return nullptr;
+    if (g.mode == 0) return g.in + (size_t)m * g.Cin;
+    const int per = g.Hm * g.Wm;
+    const int img = m / per, rem = m - img * per;
+    const int y = rem / g.Wm, x = rem - y * g.Wm;
+    const int sc = g.mode == 3 ? 2 : 1;
+    const int iy = y * sc + tp.dy, ix = x * sc + tp.dx;
+    if (iy < 0 || iy >= g.Hin || ix < 0 || ix >= g.Win) return nullptr;
+    return g.in + (((size_t)img * g.Hin + iy) * g.Win + ix) * g.Cin;
+}
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) k_gather_gemm(ConvGeom g) {
+    constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
+    constexpr int A_LD = BM * BK / 4 / 256;            // float4 loads per thread for the A tile
+    static_assert(A_LD >= 1, "tile shape");
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, phase = blockIdx.z;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    const int ntaps = geom_ntaps(g, phase);
+    for (int t = 0; t < ntaps; ++t) {
+        const float* ap[A_LD];
+        const Tap tp = geom_tap(g, t, phase);
+#pragma unroll
+        for (int i = 0; i < A_LD; ++i) {
+            const int idx = tid + i * 256;
+            ap[i] = geom_src(g, m0 + (idx >> 2), tp);
+        }
+        const float* wb = g.W + (size_t)tp.wtap * g.Cin * g.Cout + n0;
+        for (int c0 = 0; c0 < g.Cin; c0 += BK) {
+#pragma unroll
+            for (int i = 0; i < A_LD; ++i) {
+                const int idx = tid + i * 256;
+                const int m = idx >> 2, kq = idx & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ap[i]) v = __ldg(reinterpret_cast<const float4*>(ap[i] + c0 + kq * 4));
+                As[kq * 4 + 0][m] = v.x; As[kq * 4 + 1][m] = v.y; As[kq * 4 + 2][m] = v.z; As[kq * 4 + 3][m] = v.w;
+            }
+            for (int idx = tid; idx < BK * BN / 4; idx += 256) {
+                const int k = idx / (BN / 4), nq = idx - k * (BN / 4);
+                *reinterpret_cast<float4*>(&Bs[k][nq * 4]) =
+                    __ldg(reinterpret_cast<const float4*>(wb + (size_t)(c0 + k) * g.Cout + nq * 4));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float av[TM], bv[TN];
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = As[k][ty * TM + i];
+#pragma unroll
+                for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // epilogue: bias + ReLU (+ dropout for the dense FC4) -> NHWC store
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+        size_t obase;
+        if (g.mode == 0) {
+            obase = (size_t)m * g.Cout;
+        } else {
+            const int per = g.Hm * g.Wm;
+            const int img = m / per, rem = m - img * per;
+            const int y = rem / g.Wm, x = rem - y * g.Wm;
+            int oy = y, ox = x;
+            if (g.mode == 2) { oy = 2 * y + (phase >> 1); ox = 2 * x + (phase & 1); }
+            obase = (((size_t)img * g.Hout + oy) * g.Wout + ox) * g.Cout;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            float v = fmaxf(acc[i][j] + __ldg(g.bias + n), 0.0f);
+            if (g.mask) v = ((g.mask[(size_t)m * (g.Cout >> 5) + (n >> 5)] >> (n & 31)) & 1u) ? v * 2.0f : 0.0f;
+            g.out[obase + n] = v;
+        }
+    }
+}
+
+template <int BM, int BN>
+static int launch_gemm(const ConvGeom& g, int nphase, cudaStream_t st) {
+    if (g.M <= 0) return 0;
+    dim3 grid((g.M + BM - 1) / BM, g.Cout / BN, nphase);
+    k_gather_gemm<BM, BN><<<grid, 256, 0, st>>>(g);
+    return 1;
+}
+
+int launch_fc4_simt(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, float* act0, cudaStream_t st) {
+    ConvGeom g{};
+    g.mode = 0; g.M = nrows; g.Cin = 256; g.Cout = 16384;
+    g.in = h3; g.W = w.po_w3t; g.bias = w.po_b3; g.out = act0; g.mask = mask;
+    return launch_gemm<64, 64>(g, 1, st);
+}
+
+int launch_ct1_simt(const DevWeights& w, const float* act0, int nrows, float* act1, cudaStream_t st) {
+    ConvGeom g{};
+    g.mode = 1; g.M = nrows * 256; g.Hm = 16; g.Wm = 16; g.Hin = 16; g.Win = 16; g.Cin = 64;
+    g.Hout = 16; g.Wout = 16; g.Cout = 64;
+    g.in = act0; g.W = w.ct1_w; g.bias = w.ct1_b; g.out = act1;
+    return launch_gemm<128, 64>(g, 1, st);
+}
+
+int launch_ct2_simt(const DevWeights& w, const float* act1, int nrows, float* act2, cudaStream_t st) {
+    ConvGeom g{};
+    g.mode = 2; g.M = nrows * 256; g.Hm = 16; g.Wm = 16; g.Hin = 16; g.Win = 16; g.Cin = 64;
+    g.Hout = 32; g.Wout = 32; g.Cout = 64;
+    g.in = act1; g.W = w.ct2_w; g.bias = w.ct2_b; g.out = act2;
+    return launch_gemm<128, 64>(g, 4, st);
+}
+
+int launch_ct3_simt(const DevWeights& w, const float* act2, int nrows, float* act3, cudaStream_t st) {
+    ConvGeom g{};
+    g.mode = 2; g.M = nrows * 1024; g.Hm = 32; g.Wm = 32; g.Hin = 32; g.Win = 32; g.Cin = 64;
+    g.Hout = 64; g.Wout = 64; g.Cout = 32;
+    g.in = act2; g.W = w.ct3_w; g.bias = w.ct3_b; g.out = act3;
+    return launch_gemm<128, 32>(g, 4, st);
+}
+
+// ======================================================================================
+// Last deconv (32->1, k3 s1 p1) + sigmoid + per-pixel EFE terms, one CTA per decoder row.
+//   H(p)   = -(1-p)*log((d+1)-p) - p*log(d+p)            (src/torchutils.py:22-23)
+//   reward = 10 * mean_px [ p*log(d+t) + (1-p)*log((d+1)-t) ], t = 1[row < 32]
+//            (src/torchmodel.py:210-212 over src/torchutils.py:26-37 with the D12 broadcast)
+// evaluated in fp32 in the reference's operation order.  8 lanes share a pixel (4 channels each).
+// ======================================================================================
+__global__ void __launch_bounds__(256) k_ct4_efe(DevWeights w, Ct4Args a) {
+    __shared__ float ws[9 * 32];
+    __shared__ float red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 288; i += 256) ws[i] = w.ct4_w[i];
+    __syncthreads();
+    const int rl = blockIdx.x;
+    const int r = a.row0 + rl;
+    const float* in = a.act3 + (size_t)rl * 64 * 64 * 32;
+    const float bias = __ldg(w.ct4_b);
+    const int sub = lane >> 3, cq = lane & 7;
+    const bool write_img = r < a.img_rows;
+    const float d = 0.00001f, c1 = 1.00001f;
+    const float la_top = logf(d + 1.0f), lb_top = logf(c1 - 1.0f);
+    const float la_bot = logf(d + 0.0f), lb_bot = logf(c1 - 0.0f);
+    float hacc = 0.0f, racc = 0.0f;
+    for (int g = warp; g < 1024; g += 8) {
+        const int oy = g >> 4, ox = ((g & 15) << 2) + sub;
+        float acc = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int iy = oy + 1 - kh;
+            if (iy < 0 || iy >= 64) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ix = ox + 1 - kw;
+                if (ix < 0 || ix >= 64) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + ((size_t)(iy * 64 + ix)) * 32 + cq * 4));
+                const float* wk = ws + (kh * 3 + kw) * 32 + cq * 4;
+                acc = fmaf(v.x, wk[0], acc); acc = fmaf(v.y, wk[1], acc);
+                acc = fmaf(v.z, wk[2], acc); acc = fmaf(v.w, wk[3], acc);
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (cq == 0) {
+            const float x = acc + bias;
+            const float p = 1.0f / (1.0f + expf(-x));
+            const float q = 1.0f - p;
+            const float h = __fsub_rn(__fmul_rn(-q, logf(c1 - p)), __fmul_rn(p, logf(d + p)));
+            hacc += h;
+            const float lr = oy < 32 ? __fadd_rn(__fmul_rn(p, la_top), __fmul_rn(q, lb_top))
+                                     : __fadd_rn(__fmul_rn(p, la_bot), __fmul_rn(q, lb_bot));
+            racc += lr;
+            if (write_img) a.img[(size_t)r * IMG + oy * 64 + ox] = p;
+        }
+    }
+    hacc = warp_sum(hacc); racc = warp_sum(racc);
+    if (lane == 0) { red[0][warp] = hacc; red[1][warp] = racc; }
+    __syncthreads();
+    if (tid == 0) {
+        float hs = 0.0f, rs = 0.0f;
+        for (int i = 0; i < 8; ++i) { hs += red[0][i]; rs += red[1][i]; }
+        a.hsum[r] = hs;
+        a.reward[r] = rs * (1.0f / 4096.0f) * 10.0f;
+    }
+}
+
+int launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {
+    if (a.nrows <= 0) return 0;
+    k_ct4_efe<<<a.nrows, 256, 0, st>>>(w, a);
+    return 1;
+}
+
+// check_reward on a given image batch
+__global__ void __launch_bounds__(256) k_reward_only(const float* __restrict__ o, int B, float* __restrict__ out) {
+    __shared__ float red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float d = 0.00001f, c1 = 1.00001f;
+    const float la_top = logf(d + 1.0f), lb_top = logf(c1 - 1.0f);
+    const float la_bot = logf(d + 0.0f), lb_bot = logf(c1 - 0.0f);
+    float acc = 0.0f;
+    for (int i = tid; i < IMG; i += 256) {
+        const float p = o[(size_t)b * IMG + i], q = 1.0f - p;
+        acc += (i < 2048) ? __fadd_rn(__fmul_rn(p, la_top), __fmul_rn(q, lb_top))
+                          : __fadd_rn(__fmul_rn(p, la_bot), __fmul_rn(q, lb_bot));
+    }
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) red[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.0f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        out[b] = s * (1.0f / 4096.0f) * 10.0f;
+    }
+}
+
+int launch_reward_only(const float* o, int B, float* r, cudaStream_t st) {
+    if (B <= 0) return 0;
+    k_reward_only<<<B, 256, 0, st>>>(o, B, r);
+    return 1;
+}
+
+// ======================================================================================
+// Qs encoder (src/torchmodel.py:84-104): conv1 on CUDA cores (Cin = 1), conv2..4 through the
+// gather-GEMM, FC stack fused.
+// ======================================================================================
+__global__ void __launch_bounds__(256) k_qs_conv1(const float* __restrict__ img, int rows,
+                                                  const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                  float* __restrict__ out) {
+    __shared__ float ws[9 * 32];
+    __shared__ float bs[32];
+    for (int i = threadIdx.x; i < 288; i += 256) ws[i] = wgt[i];
+    if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= rows * 961) return;
+    const int r = idx / 961, rem = idx - r * 961;
+    const int oy = rem / 31, ox = rem - oy * 31;
+    const float* in = img + (size_t)r * IMG + (2 * oy) * 64 + 2 * ox;
+    float v[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) v[kh * 3 + kw] = __ldg(in + kh * 64 + kw);
+    float* o = out + (size_t)idx * 32;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c4 * 4 + j;
+            float acc = bs[c];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc = fmaf(v[t], ws[t * 32 + c], acc);
+            y[j] = fmaxf(acc, 0.0f);
+        }
+        *reinterpret_cast<float4*>(o + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+}
+
+constexpr int QF_TM = 8, QF_NT = 256;
+
+__global__ void __launch_bounds__(QF_NT) k_qs_fc(DevWeights w, QsArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* x0 = smem;                        // [TM][576]
+    float* hA = x0 + QF_TM * 576;            // [TM][256]
+    float* hB = hA + QF_TM * 256;            // [TM][256]
+    float* out = hB + QF_TM * 256;           // [TM][20]
+    uint32_t* mw = reinterpret_cast<uint32_t*>(out + QF_TM * 20);   // [TM][8]
+    __shared__ int rsite[QF_TM], rb[QF_TM], rvalid[QF_TM];
+    __shared__ uint32_t rsample[QF_TM];
+    const int tid = threadIdx.x, r0 = blockIdx.x * QF_TM;
+    if (tid < QF_TM) {
+        const int r = min(r0 + tid, a.rows - 1);
+        int set, slot, b;
+        a.map.decode(r, set, slot, b);
+        rb[tid] = b; rsite[tid] = a.map.site[0]; rsample[tid] = a.map.sample_of(slot);
+        rvalid[tid] = (r0 + tid) < a.rows;
+    }
+    for (int i = tid; i < QF_TM * 576; i += QF_NT) {
+        const int r = i / 576, k = i - r * 576;
+        const int rr = min(r0 + r, a.rows - 1);
+        x0[i] = a.c4[(size_t)rr * 576 + k];
+    }
+    __syncthreads();
+    const bool drop = a.nk.training != 0;
+    if (drop) fill_masks<QF_TM, QF_NT>(mw, 256, a.nk, 0, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<QF_TM, QF_NT>(w.qf0_t, w.qf0_b, 576, 256, x0, 576, hA, 256, drop ? mw : nullptr, 8);
+    __syncthreads();
+    if (drop) fill_masks<QF_TM, QF_NT>(mw, 256, a.nk, 1, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<QF_TM, QF_NT>(w.qf1_t, w.qf1_b, 256, 256, hA, 256, hB, 256, drop ? mw : nullptr, 8);
+    __syncthreads();
+    if (drop) fill_masks<QF_TM, QF_NT>(mw, 256, a.nk, 2, rsite, rb, rsample);
+    __syncthreads();
+    dense_hidden<QF_TM, QF_NT>(w.qf2_t, w.qf2_b, 256, 256, hB, 256, hA, 256, drop ? mw : nullptr, 8);
+    __syncthreads();
+    dense_tail<QF_TM, QF_NT>(w.qf3, w.qf3_b, 256, 20, hA, 256, out);
+    __syncthreads();
+    if (tid < QF_TM * S_DIM) {
+        const int r = tid / S_DIM, d = tid % S_DIM;
+        if (rvalid[r]) {
+            const float mean = out[r * 20 + d], lv = out[r * 20 + S_DIM + d];
+            const size_t o = (size_t)(r0 + r) * S_DIM + d;
+            a.mean[o] = mean; a.logvar[o] = lv;
+            if (a.samp) {
+                const float eps = noise_normal(a.nk, (uint32_t)(rsite[r] + 3), (uint32_t)d, (uint32_t)rb[r], rsample[r]);
+                a.samp[o] = reparam(eps, mean, lv);
+            }
+        }
+    }
+}
+
+int launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    int n = 0;
+    k_qs_conv1<<<(a.rows * 961 + 255) / 256, 256, 0, st>>>(a.img, a.rows, w.qc1_w, w.qc1_b, a.c1);
+    ++n;
+    ConvGeom g{};
+    g.mode = 3; g.M = a.rows * 225; g.Hm = 15; g.Wm = 15; g.Hin = 31; g.Win = 31; g.Cin = 32;
+    g.Hout = 15; g.Wout = 15; g.Cout = 32; g.in = a.c1; g.W = w.qc2_w; g.bias = w.qc2_b; g.out = a.c2;
+    n += launch_gemm<128, 32>(g, 1, st);
+    g.M = a.rows * 49; g.Hm = 7; g.Wm = 7; g.Hin = 15; g.Win = 15; g.Cin = 32;
+    g.Hout = 7; g.Wout = 7; g.Cout = 64; g.in = a.c2; g.W = w.qc3_w; g.bias = w.qc3_b; g.out = a.c3;
+    n += launch_gemm<64, 64>(g, 1, st);
+    g.M = a.rows * 9; g.Hm = 3; g.Wm = 3; g.Hin = 7; g.Win = 7; g.Cin = 64;
+    g.Hout = 3; g.Wout = 3; g.Cout = 64; g.in = a.c3; g.W = w.qc4_w; g.bias = w.qc4_b; g.out = a.c4;
+    n += launch_gemm<64, 64>(g, 1, st);
+    const size_t smem = (QF_TM * (576 + 256 + 256 + 20)) * sizeof(float) + QF_TM * 8 * sizeof(uint32_t);
+    k_qs_fc<<<(a.rows + QF_TM - 1) / QF_TM, QF_NT, smem, st>>>(w, a);
+    return n + 1;
+}
+
+// ======================================================================================
+// Qpi habit net (src/torchmodel.py:19-31)
+// ======================================================================================
+constexpr int QP_TM = 8, QP_NT = 128;
+
+__global__ void __launch_bounds__(QP_NT) k_qpi(DevWeights w, const float* __restrict__ s, int B,
+                                               float* logits, float* q, float* logq) {
+    __shared__ __align__(16) float x0[QP_TM][12];
+    __shared__ __align__(16) float hA[QP_TM][128];
+    __shared__ __align__(16) float hB[QP_TM][128];
+    __shared__ float out[QP_TM][4];
+    const int tid = threadIdx.x, r0 = blockIdx.x * QP_TM;
+    if (tid < QP_TM * 12) {
+        const int r = tid / 12, k = tid % 12;
+        const int rr = min(r0 + r, B - 1);
+        x0[r][k] = k < S_DIM ? s[(size_t)rr * S_DIM + k] : 0.0f;
+    }
+    __syncthreads();
+    dense_hidden<QP_TM, QP_NT>(w.pi_w0t, w.pi_b0, 12, 128, &x0[0][0], 12, &hA[0][0], 128, nullptr, 0);
+    __syncthreads();
+    dense_hidden<QP_TM, QP_NT>(w.pi_w1t, w.pi_b1, 128, 128, &hA[0][0], 128, &hB[0][0], 128, nullptr, 0);
+    __syncthreads();
+    dense_tail<QP_TM, QP_NT>(w.pi_w2, w.pi_b2, 128, 4, &hB[0][0], 128, &out[0][0]);
+    __syncthreads();
+    if (tid < QP_TM && r0 + tid < B) {
+        const float* l = out[tid];
+        const float mx = fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3]));
+        float e[4], sum = 0.0f;
+        for (int i = 0; i < 4; ++i) { e[i] = expf(l[i] - mx); sum += e[i]; }
+        for (int i = 0; i < 4; ++i) {
+            const float qi = e[i] / sum;
+            const size_t o = (size_t)(r0 + tid) * 4 + i;
+            if (logits) logits[o] = l[i];
+            if (q) q[o] = qi;
+            if (logq) logq[o] = logf(qi + 1e-20f);
+        }
+    }
+}
+
+int launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float* q, float* logq, cudaStream_t st) {
+    if (B <= 0) return 0;
+    k_qpi<<<(B + QP_TM - 1) / QP_TM, QP_NT, 0, st>>>(w, s, B, logits, q, logq);
+    return 1;
+}
+
+// ======================================================================================
+// scalar glue
+// ======================================================================================
+// entropy_normal_from_logvar: 0.5 * (log(2 pi e) + logvar)   (src/torchutils.py:19-20)
+__device__ __forceinline__ float ent_normal(float lv) { return __fmul_rn(0.5f, __fadd_rn(2.8378770664093453f, lv)); }
+
+__global__ void k_step_finalize(StepFinalizeArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int SB = a.Sl * a.B;
+    float t0 = 0.0f, t1 = 0.0f, t21 = 0.0f, t22 = 0.0f;
+    for (int j = 0; j < a.Sl; ++j) {
+        const int r = j * a.B + b;
+        t0 += a.reward[r];
+        float e = 0.0f;
+        for (int d = 0; d < S_DIM; ++d)
+            e += __fadd_rn(ent_normal(a.logvarA[(size_t)r * S_DIM + d]), ent_normal(a.qs_logvar[(size_t)r * S_DIM + d]));
+        t1 += -e;
+        t21 += a.hsum[SB + r];
+        t22 += a.hsum[2 * SB + r];
+    }
+    a.acc[0 * a.B + b] += (double)t0;
+    a.acc[1 * a.B + b] += (double)t1;
+    a.acc[2 * a.B + b] += (double)t21;
+    a.acc[3 * a.B + b] += (double)t22;
+    if (a.carry_src)
+        for (int d = 0; d < S_DIM; ++d) a.carry_dst[b * S_DIM + d] = a.carry_src[b * S_DIM + d];
+}
+
+int launch_step_finalize(const StepFinalizeArgs& a, cudaStream_t st) {
+    k_step_finalize<<<(a.B + 127) / 128, 128, 0, st>>>(a);
+    return 1;
+}
+
+__global__ void k_combine(const double* sums, int B, int samples, float* G, float* t0, float* t1, float* t2) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double inv = 1.0 / (double)samples;
+    const float a0 = (float)(sums[b] * inv), a1 = (float)(sums[B + b] * inv);
+    const float a21 = (float)(sums[2 * B + b] * inv), a22 = (float)(sums[3 * B + b] * inv);
+    const float a2 = a21 - a22;
+    if (t0) t0[b] = a0;
+    if (t1) t1[b] = a1;
+    if (t2) t2[b] = a2;
+    if (G) G[b] = -a0 + a1 + a2;
+}
+
+int launch_combine(const double* sums, int B, int samples, float* G, float* t0, float* t1, float* t2, cudaStream_t st) {
+    k_combine<<<(B + 127) / 128, 128, 0, st>>>(sums, B, samples, G, t0, t1, t2);
+    return 1;
+}
+
+// calculate_G_given_trajectory tail (src/torchmodel.py:335-352): rows = depth
+__global__ void k_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
+                         int D, float* G, float* Gmean) {
+    __shared__ float gs[256];
+    const int t = threadIdx.x;
+    float g = 0.0f;
+    if (t < D) {
+        float e = 0.0f;
+        for (int d = 0; d < S_DIM; ++d)
+            e += __fadd_rn(ent_normal(lv_traj[t * S_DIM + d]), ent_normal(qs_logvar[t * S_DIM + d]));
+        const float term0 = reward[t], term1 = -e, term2 = hsum[D + t] - hsum[2 * D + t];
+        g = -term0 + term1 + term2;
+        if (G) G[t] = g;
+    }
+    gs[t] = g;
+    __syncthreads();
+    if (t == 0 && Gmean) {
+        float s = 0.0f;
+        for (int i = 0; i < D; ++i) s += gs[i];
+        *Gmean = s / (float)D;
+    }
+}
+
+int launch_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
+                  int D, float* G, float* Gmean, cudaStream_t st) {
+    k_traj_G<<<1, 256, 0, st>>>(reward, hsum, lv_traj, qs_logvar, D, G, Gmean);
+    return 1;
+}
+
+// ======================================================================================
+// mcts_step_simulate rollout (src/torchmodel.py:354-388): depth sequential B=1 steps of
+// Qpi -> categorical -> Ps, one CTA, the carry never leaves shared memory.
+// ======================================================================================
+__global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
+    __shared__ __align__(16) float s_cur[12];
+    __shared__ __align__(16) float x0[16];
+    __shared__ __align__(16) float hA[512];
+    __shared__ __align__(16) float hB[512];
+    __shared__ uint32_t mw[16];
+    __shared__ float out[20];
+    __shared__ float lg[4];
+    __shared__ int act;
+    const int tid = threadIdx.x;
+    if (tid < 12) s_cur[tid] = tid < S_DIM ? a.start[tid] : 0.0f;
+    __syncthreads();
+    int rsite[1] = {SITE_PS_A}, rb[1] = {0};
+    uint32_t rsample[1] = {0};
+    for (int t = 0; t < a.depth; ++t) {
+        NoiseKey nk = a.nk;
+        nk.step = (uint32_t)t;
+        // habit prior on the current state
+        dense_hidden<1, 512>(w.pi_w0t, w.pi_b0, 12, 128, s_cur, 12, hA, 128, nullptr, 0);
+        __syncthreads();
+        dense_hidden<1, 512>(w.pi_w1t, w.pi_b1, 128, 128, hA, 128, hB, 128, nullptr, 0);
+        __syncthreads();
+        dense_tail<1, 512>(w.pi_w2, w.pi_b2, 128, 4, hB, 128, lg);
+        __syncthreads();
+        if (tid == 0) {
+            const float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+            float q[4], sum = 0.0f;
+            for (int i = 0; i < 4; ++i) { q[i] = expf(lg[i] - mx); sum += q[i]; }
+            bool ok = true;
+            float cdf[4], c = 0.0f;
+            for (int i = 0; i < 4; ++i) {
+                q[i] = q[i] / sum;
+                ok = ok && isfinite(q[i]) && q[i] >= 0.0f;
+                c = __fadd_rn(c, q[i]);
+                cdf[i] = c;
+            }
+            ok = ok && c > 0.0f;
+            int choice = 0;
+            if (ok) {
+                const float u = noise_uniform24(nk, SITE_CAT, 0, 0);
+                const float thr = __fmul_rn(u, cdf[3]);
+                choice = 3;
+                for (int i = 0; i < 4; ++i) if (thr < cdf[i]) { choice = i; break; }
+            }
+            act = choice;
+            for (int i = 0; i < 4; ++i) a.pi0[t * 4 + i] = (i == choice) ? 1.0f : 0.0f;
+            if (t == 0) for (int i = 0; i < 4; ++i) a.qpi[i] = ok ? q[i] : (i == 0 ? 1.0f : 0.0f);
+            for (int d = 0; d < S_DIM; ++d) a.s0[t * S_DIM + d] = s_cur[d];
+        }
+        __syncthreads();
+        if (tid < 16) x0[tid] = tid < 4 ? (tid == act ? 1.0f : 0.0f) : (tid < 14 ? s_cur[tid - 4] : 0.0f);
+        const bool drop = nk.training != 0;
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 0, rsite, rb, rsample);
+        __syncthreads();
+        dense_hidden<1, 512>(w.ps_w0t, w.ps_b0, 16, 512, x0, 16, hA, 512, drop ? mw : nullptr, 16);
+        __syncthreads();
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 1, rsite, rb, rsample);
+        __syncthreads();
+        dense_hidden<1, 512>(w.ps_w1t, w.ps_b1, 512, 512, hA, 512, hB, 512, drop ? mw : nullptr, 16);
+        __syncthreads();
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 2, rsite, rb, rsample);
+        __syncthreads();
+        dense_hidden<1, 512>(w.ps_w2t, w.ps_b2, 512, 512, hB, 512, hA, 512, drop ? mw : nullptr, 16);
+        __syncthreads();
+        dense_tail<1, 512>(w.ps_w3, w.ps_b3, 512, 20, hA, 512, out);
+        __syncthreads();
+        if (tid < S_DIM) {
+            const float mean = out[tid], lv = out[S_DIM + tid];
+            const float eps = noise_normal(nk, SITE_PS_A + 3, (uint32_t)tid, 0, 0);
+            const float s = reparam(eps, mean, lv);
+            a.ps1[t * S_DIM + tid] = s; a.mean[t * S_DIM + tid] = mean; a.logvar[t * S_DIM + tid] = lv;
+            s_cur[tid] = a.use_means ? mean : s;
+        }
+        __syncthreads();
+    }
+}
+
+int launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st) {
+    k_sim_rollout<<<1, 512, 0, st>>>(w, a);
+    return 1;
+}
+
+}  // namespace dai

@@ -1,0 +1,29 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path of the contraction layers — internal interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dai_kernels.h"
+
+namespace dai {
+
+struct TcWeights {
+    void* impl = nullptr;   // opaque (dai_tc.cu)
+};
+
+// Builds the bf16 hi/lo K-major operand planes + TMA descriptors from the raw state_dict.
+// Device allocations are appended to *allocs (owned by the handle).  Returns 0 or -1 (+ *err).
+int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
+                    std::string* err);
+void tc_release(TcWeights* w);
+
+// FC4 -> ct1 -> ct2 -> ct3 -> pixel terms for one chunk of decoder rows on the tensor cores.
+// Returns the number of kernels launched, or -1 (+ *err).
+int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const float* h3, const uint32_t* mask,
+                     int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4, cudaStream_t st,
+                     std::string* err);
+
+}  // namespace dai

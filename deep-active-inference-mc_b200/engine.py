@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/dai_b200.h.
+
+The library (libdai_b200.so, built in-tree by build.sh / __graft_entry__.build()) is the
+only compute path: there is no CPU or eager-PyTorch fallback, and a missing library is a
+hard error.  torch is used for device memory (tensor.data_ptr()), the current CUDA stream
+and, in torchmodel.py, torch.distributed.
+"""
+import ctypes
+import os
+
+import torch
+
+PREC_FP32_SIMT = 0
+PREC_BF16X3 = 1
+PREC_BF16X1 = 2
+PRECISIONS = {"fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1}
+
+_c_float_p = ctypes.c_void_p
+_vp = ctypes.c_void_p
+
+
+class DaiError(RuntimeError):
+    pass
+
+
+class DaiConfig(ctypes.Structure):
+    _fields_ = [("s_dim", ctypes.c_int32), ("pi_dim", ctypes.c_int32), ("resolution", ctypes.c_int32),
+                ("colour_channels", ctypes.c_int32), ("precision", ctypes.c_int32), ("training", ctypes.c_int32)]
+
+
+class DaiStats(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64)]
+
+
+# name -> (restype, argtypes); every symbol include/dai_b200.h declares
+SIGNATURES = {
+    "dai_create": (ctypes.c_int, [ctypes.POINTER(DaiConfig), ctypes.c_int, ctypes.POINTER(_vp)]),
+    "dai_destroy": (ctypes.c_int, [_vp]),
+    "dai_last_error": (ctypes.c_char_p, [_vp]),
+    "dai_version": (ctypes.c_char_p, []),
+    "dai_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "dai_commit_weights": (ctypes.c_int, [_vp, _vp]),
+    "dai_set_rng": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64]),
+    "dai_get_rng": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "dai_set_training": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dai_set_precision": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "dai_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(DaiStats), ctypes.c_int]),
+    "dai_encode": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "dai_decode": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "dai_transition": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "dai_habit": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp]),
+    "dai_check_reward": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    "dai_calculate_G": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dai_calculate_G_mean": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dai_G_given_trajectory": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "dai_rollout": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dai_combine": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "dai_rollout_host": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dai_mcts_simulate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
+                                         _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdai_b200.so")
+
+
+def load_library():
+    """Load libdai_b200.so and bind every declared entry point (fails loudly if absent)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise DaiError("%s not found: build it first (./build.sh or __graft_entry__.build()); "
+                       "there is no CPU fallback for this path" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One handle on one CUDA device.  All tensor arguments are contiguous float32 CUDA tensors on
+    that device unless a method says `host`."""
+
+    def __init__(self, device=None, precision="bf16x3", training=True):
+        if not torch.cuda.is_available():
+            raise DaiError("no CUDA device: the EFE rollout path is CUDA-only (sm_100a), there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        cfg = DaiConfig(10, 4, 64, 1, PRECISIONS[precision] if isinstance(precision, str) else int(precision),
+                        1 if training else 0)
+        h = _vp()
+        rc = self.lib.dai_create(ctypes.byref(cfg), self.device.index, ctypes.byref(h))
+        if rc != 0:
+            raise DaiError("dai_create failed with code %d" % rc)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dai_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _ck(self, rc):
+        if rc != 0:
+            raise DaiError("dai error %d: %s" % (rc, self.lib.dai_last_error(self.h).decode()))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, t, shape=None):
+        """contiguous float32 tensor on the engine's device (host inputs are copied)."""
+        t = torch.as_tensor(t)
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if shape is not None:
+            t = t.reshape(shape)
+        return t
+
+    def new(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    # ------------------------------------------------------------------ state
+    def set_weights(self, state):
+        """state: {key: tensor / ndarray} with the 46 state_dict keys."""
+        for key, val in state.items():
+            t = torch.as_tensor(val).detach().to(torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            with torch.cuda.device(self.device):
+                if t.is_cuda:
+                    torch.cuda.current_stream(self.device).synchronize()
+                self._ck(self.lib.dai_set_weight(self.h, key.encode(), _p(t), shape, t.dim()))
+        self._ck(self.lib.dai_commit_weights(self.h, self._stream()))
+
+    def set_rng(self, seed, call=0):
+        self._ck(self.lib.dai_set_rng(self.h, int(seed), int(call)))
+
+    def get_rng(self):
+        s, c = ctypes.c_uint64(), ctypes.c_uint64()
+        self._ck(self.lib.dai_get_rng(self.h, ctypes.byref(s), ctypes.byref(c)))
+        return s.value, c.value
+
+    def set_training(self, flag):
+        self._ck(self.lib.dai_set_training(self.h, 1 if flag else 0))
+
+    def set_precision(self, precision):
+        self._ck(self.lib.dai_set_precision(self.h, PRECISIONS[precision] if isinstance(precision, str) else int(precision)))
+
+    def stats(self, reset=False):
+        s = DaiStats()
+        self._ck(self.lib.dai_get_stats(self.h, ctypes.byref(s), 1 if reset else 0))
+        return {"kernel_launches": s.kernel_launches, "calls": s.calls, "workspace_bytes": s.workspace_bytes}
+
+    # ------------------------------------------------------------------ nets
+    def encode(self, o, sample=False):
+        o = self.dev(o).reshape(-1, 4096)
+        B = o.shape[0]
+        mean, logvar = self.new(B, 10), self.new(B, 10)
+        s = self.new(B, 10) if sample else None
+        self._ck(self.lib.dai_encode(self.h, _p(o), B, _p(mean), _p(logvar), _p(s), self._stream()))
+        return mean, logvar, s
+
+    def decode(self, s):
+        s = self.dev(s).reshape(-1, 10)
+        B = s.shape[0]
+        po = self.new(B, 1, 64, 64)
+        self._ck(self.lib.dai_decode(self.h, _p(s), B, _p(po), self._stream()))
+        return po
+
+    def transition(self, pi, s0, sample=False):
+        pi, s0 = self.dev(pi).reshape(-1, 4), self.dev(s0).reshape(-1, 10)
+        B = s0.shape[0]
+        if pi.shape[0] != B:
+            raise DaiError("transition: pi has %d rows, s0 has %d" % (pi.shape[0], B))
+        mean, logvar = self.new(B, 10), self.new(B, 10)
+        s = self.new(B, 10) if sample else None
+        self._ck(self.lib.dai_transition(self.h, _p(pi), _p(s0), B, _p(mean), _p(logvar), _p(s), self._stream()))
+        return mean, logvar, s
+
+    def habit(self, s):
+        s = self.dev(s).reshape(-1, 10)
+        B = s.shape[0]
+        logits, q, logq = self.new(B, 4), self.new(B, 4), self.new(B, 4)
+        self._ck(self.lib.dai_habit(self.h, _p(s), B, _p(logits), _p(q), _p(logq), self._stream()))
+        return logits, q, logq
+
+    def check_reward(self, o):
+        o = self.dev(o).reshape(-1, 4096)
+        r = self.new(o.shape[0])
+        self._ck(self.lib.dai_check_reward(self.h, _p(o), o.shape[0], _p(r), self._stream()))
+        return r
+
+    # ------------------------------------------------------------------ EFE
+    def calculate_G(self, s0, pi0, samples, shard=None, want_po1=True):
+        """Returns dict(sums (4,B) f64, G, t0, t1, t2, ps1, ps1_mean, ps1_logvar, po1)."""
+        s0, pi0 = self.dev(s0).reshape(-1, 10), self.dev(pi0).reshape(-1, 4)
+        B = s0.shape[0]
+        j0, j1 = (0, samples) if shard is None else shard
+        out = dict(sums=self.new(4, B, dtype=torch.float64), G=self.new(B), t0=self.new(B), t1=self.new(B),
+                   t2=self.new(B), ps1=self.new(B, 10), ps1_mean=self.new(B, 10), ps1_logvar=self.new(B, 10),
+                   po1=self.new(B, 1, 64, 64) if want_po1 else None)
+        self._ck(self.lib.dai_calculate_G(self.h, _p(s0), _p(pi0), B, samples, j0, j1, _p(out["sums"]), _p(out["G"]),
+                                          _p(out["t0"]), _p(out["t1"]), _p(out["t2"]), _p(out["ps1"]),
+                                          _p(out["ps1_mean"]), _p(out["ps1_logvar"]), _p(out["po1"]), self._stream()))
+        return out
+
+    def calculate_G_mean(self, s0, pi0):
+        s0, pi0 = self.dev(s0).reshape(-1, 10), self.dev(pi0).reshape(-1, 4)
+        B = s0.shape[0]
+        out = dict(G=self.new(B), t0=self.new(B), t1=self.new(B), t2=self.new(B), ps1_mean=self.new(B, 10),
+                   po1=self.new(B, 1, 64, 64))
+        self._ck(self.lib.dai_calculate_G_mean(self.h, _p(s0), _p(pi0), B, _p(out["G"]), _p(out["t0"]), _p(out["t1"]),
+                                               _p(out["t2"]), _p(out["ps1_mean"]), _p(out["po1"]), self._stream()))
+        return out
+
+    def G_given_trajectory(self, s0, ps1, ps1_mean, ps1_logvar, pi0):
+        s0, ps1, mu, lv = (self.dev(x).reshape(-1, 10) for x in (s0, ps1, ps1_mean, ps1_logvar))
+        pi0 = self.dev(pi0).reshape(-1, 4)
+        D = s0.shape[0]
+        G = self.new(D)
+        self._ck(self.lib.dai_G_given_trajectory(self.h, _p(s0), _p(ps1), _p(mu), _p(lv), _p(pi0), D, _p(G), self._stream()))
+        return G
+
+    def rollout(self, o, pi, steps, samples, calc_mean=False, four=False, shard=None, want_po1=True):
+        o = self.dev(o).reshape(-1, 4096)
+        B = o.shape[0]
+        pi = None if pi is None else self.dev(pi).reshape(B, 4)
+        j0, j1 = (0, samples) if shard is None else shard
+        out = dict(sums=self.new(4, B, dtype=torch.float64), G=self.new(B), t0=self.new(B), t1=self.new(B),
+                   t2=self.new(B), po1=self.new(B, 1, 64, 64) if want_po1 else None)
+        self._ck(self.lib.dai_rollout(self.h, _p(o), _p(pi), B, steps, samples, 1 if calc_mean else 0, 1 if four else 0,
+                                      j0, j1, _p(out["sums"]), _p(out["G"]), _p(out["t0"]), _p(out["t1"]),
+                                      _p(out["t2"]), _p(out["po1"]), self._stream()))
+        return out
+
+    def combine(self, sums, samples):
+        B = sums.shape[1]
+        G, t0, t1, t2 = self.new(B), self.new(B), self.new(B), self.new(B)
+        self._ck(self.lib.dai_combine(self.h, _p(sums), B, samples, _p(G), _p(t0), _p(t1), _p(t2), self._stream()))
+        return G, t0, t1, t2
+
+    def rollout_host(self, o_host, pi_host, steps, samples, calc_mean, four, out_host, po1_host=None):
+        """o_host (B,4096) and out_host (4,B) are HOST float32 tensors (pinned for async copies);
+        copies in, runs, copies G,t0,t1,t2 back and waits (the bench's end-to-end call)."""
+        B = o_host.shape[0]
+        self._ck(self.lib.dai_rollout_host(self.h, _p(o_host), _p(pi_host), B, steps, samples, 1 if calc_mean else 0,
+                                           1 if four else 0, _p(out_host[0]), _p(out_host[1]), _p(out_host[2]),
+                                           _p(out_host[3]), _p(po1_host), self._stream()))
+
+    def mcts_simulate(self, starting_s, depth, use_means=False):
+        s = self.dev(starting_s).reshape(10)
+        pi0, qpi = self.new(depth, 4), self.new(4)
+        G = ctypes.c_float()
+        self._ck(self.lib.dai_mcts_simulate(self.h, _p(s), depth, 1 if use_means else 0, ctypes.byref(G), _p(pi0),
+                                            _p(qpi), self._stream()))
+        return float(G.value), pi0, qpi

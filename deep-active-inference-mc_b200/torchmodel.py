@@ -1,0 +1,286 @@
+"""Drop-in for the reference's src/torchmodel.py on the EFE-rollout path.
+
+Same class names, constructor, attributes, method names, argument order and return arity
+as src/torchmodel.py:10-393 (zfountas/deep-active-inference-mc @ d7e76d8), so that the
+reference's planner (src/mcts.py:71-85,158-164,188), batch maker (src/util.py:62) and demo
+(test_demo.py:56-57,136-137,150) resolve against it unchanged.  The three sub-modules stay
+real nn.Modules holding the canonical fp32 parameters (state_dict keys and checkpoint files
+are the reference's); every forward on the path is served by the CUDA library through
+engine.Engine — there is no eager-PyTorch or CPU fallback.
+
+Differences a caller can observe, all forced by reference defects:
+  D1  the encoder's first FC is 576->256 (the shipped 256->256 cannot run on 64x64 input);
+  D2  `precision` exists;  D3 `.to()` exists and returns self;  D7 outputs are detached;
+  G / terms / Qpi / pi0 / rewards come back as CPU tensors because src/mcts.py combines them
+  in place with CPU tensors (:27-29,82,93); latents and images stay on the GPU.
+Noise is keyed Philox (seed + call index), not torch's global generator: `set_rng`.
+"""
+import pickle
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, DaiError  # noqa: F401
+
+
+class _Served(nn.Module):
+    """nn.Module whose forwards are served by the owning ActiveInferenceModel's engine."""
+
+    def _eng(self):
+        owner = self.__dict__.get("_owner")
+        if owner is None:
+            raise DaiError("%s is not attached to an ActiveInferenceModel" % type(self).__name__)
+        owner._sync()
+        return owner._engine
+
+    def reparameterize(self, mean, logvar):
+        # src/torchmodel.py:54-56,130-132 (host-visible helper; the hot path samples in-kernel)
+        eps = torch.randn_like(mean)
+        return eps * torch.exp(logvar * 0.5) + mean
+
+
+class ModelTop(_Served):
+    """Habit net Qpi — src/torchmodel.py:10-31."""
+
+    def __init__(self, s_dim, pi_dim):
+        super().__init__()
+        self.s_dim, self.pi_dim = s_dim, pi_dim
+        self.qpi_net = nn.Sequential(nn.Linear(s_dim, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(),
+                                     nn.Linear(128, pi_dim))
+
+    def encode_s(self, s0):
+        logits, q, logq = self._eng().habit(s0)
+        owner = self.__dict__["_owner"]
+        return owner._host(logits), owner._host(q), owner._host(logq)
+
+
+class ModelMid(_Served):
+    """Transition net Ps — src/torchmodel.py:34-66."""
+
+    def __init__(self, s_dim, pi_dim):
+        super().__init__()
+        self.s_dim, self.pi_dim = s_dim, pi_dim
+        self.ps_net = nn.Sequential(nn.Linear(pi_dim + s_dim, 512), nn.ReLU(), nn.Dropout(0.5),
+                                    nn.Linear(512, 512), nn.ReLU(), nn.Dropout(0.5),
+                                    nn.Linear(512, 512), nn.ReLU(), nn.Dropout(0.5),
+                                    nn.Linear(512, s_dim * 2))
+
+    def transition(self, pi, s0):
+        mean, logvar, _ = self._eng().transition(pi, s0, sample=False)
+        return mean, logvar
+
+    def transition_with_sample(self, pi, s0):
+        mean, logvar, s = self._eng().transition(pi, s0, sample=True)
+        return s, mean, logvar
+
+
+class ModelDown(_Served):
+    """Encoder Qs and decoder Po — src/torchmodel.py:69-146 (FC1 = 576->256, D1)."""
+
+    def __init__(self, s_dim, pi_dim, colour_channels, resolution):
+        super().__init__()
+        if resolution != 64 or colour_channels != 1:
+            raise ValueError("Unknown resolution")   # the 32-px branch is dead in the reference (D11)
+        self.s_dim, self.pi_dim = s_dim, pi_dim
+        self.colour_channels, self.resolution = colour_channels, resolution
+        self.qs_net = nn.Sequential(
+            nn.Conv2d(colour_channels, 32, kernel_size=3, stride=2), nn.ReLU(),
+            nn.Conv2d(32, 32, kernel_size=3, stride=2), nn.ReLU(),
+            nn.Conv2d(32, 64, kernel_size=3, stride=2), nn.ReLU(),
+            nn.Conv2d(64, 64, kernel_size=3, stride=2), nn.ReLU(),
+            nn.Flatten(),
+            nn.Linear(64 * 3 * 3, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, s_dim * 2))
+        self.po_net = nn.Sequential(
+            nn.Linear(s_dim, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, 256), nn.ReLU(), nn.Dropout(0.5),
+            nn.Linear(256, 16 * 16 * 64), nn.ReLU(), nn.Dropout(0.5),
+            nn.Unflatten(1, (64, 16, 16)),
+            nn.ConvTranspose2d(64, 64, kernel_size=3, stride=1, padding=1), nn.ReLU(),
+            nn.ConvTranspose2d(64, 64, kernel_size=3, stride=2, padding=1, output_padding=1), nn.ReLU(),
+            nn.ConvTranspose2d(64, 32, kernel_size=3, stride=2, padding=1, output_padding=1), nn.ReLU(),
+            nn.ConvTranspose2d(32, colour_channels, kernel_size=3, stride=1, padding=1), nn.Sigmoid())
+
+    def encoder(self, o):
+        mean, logvar, _ = self._eng().encode(o, sample=False)
+        return mean, logvar
+
+    def decoder(self, s):
+        return self._eng().decode(s)
+
+    def encoder_with_sample(self, o):
+        mean, logvar, s = self._eng().encode(o, sample=True)
+        return s, mean, logvar
+
+
+class ActiveInferenceModel:
+    """src/torchmodel.py:149-393."""
+
+    def __init__(self, s_dim, pi_dim, gamma, beta_s, beta_o, colour_channels=1, resolution=64,
+                 precision="bf16x3", device=None, seed=1234):
+        if s_dim != 10 or pi_dim != 4:
+            raise ValueError("the B200 path is built for s_dim=10, pi_dim=4 (BASELINE.json configs)")
+        self._engine = Engine(device=device, precision=precision)
+        self.device = self._engine.device
+        self.precision = torch.float32                      # D2
+        self.s_dim, self.pi_dim = s_dim, pi_dim
+        self.model_top = ModelTop(s_dim, pi_dim).to(self.device)
+        self.model_mid = ModelMid(s_dim, pi_dim).to(self.device)
+        self.model_down = ModelDown(s_dim, pi_dim, colour_channels, resolution).to(self.device)
+        for m in (self.model_top, self.model_mid, self.model_down):
+            m.__dict__["_owner"] = self
+        self.beta_s = torch.tensor(beta_s, device=self.device)
+        self.gamma = torch.tensor(gamma, device=self.device)
+        self.beta_o = torch.tensor(beta_o, device=self.device)
+        self.pi_one_hot = torch.eye(4, device=self.device)
+        self.pi_one_hot_3 = torch.eye(3, device=self.device)
+        self.host_results = True
+        self._versions = None
+        self._plist = None
+        self._group = None          # torch.distributed group for MC-sample sharding
+        self._engine.set_rng(seed, 0)
+
+    # ------------------------------------------------------------------ plumbing
+    def to(self, device=None, *a, **k):     # D3: train.py:97 / test_demo.py:48 call .to(device)
+        return self
+
+    def _params(self):
+        if self._plist is None:
+            self._plist = [(name, p) for m in (self.model_top, self.model_mid, self.model_down)
+                           for name, p in m.state_dict(keep_vars=True).items()]
+        return self._plist
+
+    def _sync(self):
+        """Re-pack the engine's weights when any parameter changed (optimizer step, load_state_dict)."""
+        v = tuple((p.data_ptr(), p._version) for _, p in self._params())
+        train = (self.model_mid.training, self.model_down.training)
+        if v != self._versions:
+            self._engine.set_weights({name: p.detach() for name, p in self._params()})
+            self._versions = v
+        # nn.Dropout follows module.training: the reference never leaves train mode
+        self._engine.set_training(all(train))
+
+    def load_numpy_weights(self, weights):
+        """Load {state_dict key: ndarray} (synthetic.make_weights) into the three modules."""
+        for m in (self.model_top, self.model_mid, self.model_down):
+            m.load_state_dict({k: torch.as_tensor(weights[k]) for k in m.state_dict()})
+        self._versions = None
+        return self
+
+    def set_rng(self, seed, call=0):
+        self._engine.set_rng(seed, call)
+
+    def set_precision(self, precision):
+        self._engine.set_precision(precision)
+
+    def enable_sample_sharding(self, group=None):
+        """Shard the MC samples of calculate_G / calculate_G_repeated over the ranks of a
+        torch.distributed group (NCCL): one all-reduce of the (4,B) float64 term sums per call."""
+        import torch.distributed as dist
+        self._group = group if group is not None else dist.group.WORLD
+        return self
+
+    def _host(self, t):
+        return t.cpu() if self.host_results else t
+
+    def _shard(self, samples):
+        if self._group is None:
+            return None, 1
+        import torch.distributed as dist
+        from .sharding import shard_range
+        world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        return shard_range(samples, rank, world), world
+
+    def _finish(self, out, samples, world):
+        """all-reduce the raw term sums over the sample shards and finish G / terms."""
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out["sums"], op=dist.ReduceOp.SUM, group=self._group)
+            out["G"], out["t0"], out["t1"], out["t2"] = self._engine.combine(out["sums"], samples)
+        return self._host(out["G"]), [self._host(out["t0"]), self._host(out["t1"]), self._host(out["t2"])]
+
+    # ------------------------------------------------------------------ checkpoints (src/torchmodel.py:167-208)
+    def save_weights(self, folder_chp):
+        torch.save(self.model_down.state_dict(), f"{folder_chp}/checkpoint_down.pth")
+        torch.save(self.model_top.state_dict(), f"{folder_chp}/checkpoint_top.pth")
+        torch.save(self.model_mid.state_dict(), f"{folder_chp}/checkpoint_mid.pth")
+
+    def load_weights(self, folder_chp):
+        self.model_down.load_state_dict(torch.load(f"{folder_chp}/checkpoint_down.pth", map_location=self.device))
+        self.model_top.load_state_dict(torch.load(f"{folder_chp}/checkpoint_top.pth", map_location=self.device))
+        self.model_mid.load_state_dict(torch.load(f"{folder_chp}/checkpoint_mid.pth", map_location=self.device))
+        self._versions = None
+
+    def save_all(self, folder_chp, stats, script_file="", optimizers={}):
+        self.save_weights(folder_chp)
+        with open(f"{folder_chp}/stats.pkl", "wb") as ff:
+            pickle.dump(stats, ff)
+        with open(f"{folder_chp}/optimizers.pkl", "wb") as ff:
+            pickle.dump({k: v.state_dict() for k, v in optimizers.items()}, ff)
+
+    def load_all(self, folder_chp):
+        self.load_weights(folder_chp)
+        with open(f"{folder_chp}/stats.pkl", "rb") as ff:
+            stats = pickle.load(ff)
+        for name, key in (("beta_s", "var_beta_s"), ("gamma", "var_gamma"), ("beta_o", "var_beta_o")):
+            if stats.get(key):
+                setattr(self, name, torch.tensor(stats[key][-1], device=self.device))
+        return stats, {}      # the reference always ends up with optimizers = {} (D4)
+
+    # ------------------------------------------------------------------ small evaluators
+    def check_reward(self, o):
+        self._sync()
+        return self._host(self._engine.check_reward(o))
+
+    def imagine_future_from_o(self, o0, pi):
+        s0, _, _ = self.model_down.encoder_with_sample(o0)
+        ps1, _, _ = self.model_mid.transition_with_sample(pi, s0)
+        return self.model_down.decoder(ps1)
+
+    def habitual_net(self, o):
+        qs_mean, _ = self.model_down.encoder(o)
+        _, Qpi, _ = self.model_top.encode_s(qs_mean)
+        return Qpi
+
+    # ------------------------------------------------------------------ EFE evaluators
+    def calculate_G_repeated(self, o, pi, steps=1, calc_mean=False, samples=10):
+        self._sync()
+        shard, world = self._shard(samples)
+        out = self._engine.rollout(o, pi, steps, samples, calc_mean=calc_mean, four=False, shard=shard)
+        G, terms = self._finish(out, samples, world)
+        return G, terms, out["po1"]
+
+    def calculate_G_4_repeated(self, o, steps=1, calc_mean=False, samples=10):
+        self._sync()
+        if calc_mean:       # calculate_G_mean steps have a single sample: nothing to shard
+            shard, world = None, 1
+        else:
+            shard, world = self._shard(samples)
+        out = self._engine.rollout(o, None, steps, samples, calc_mean=calc_mean, four=True, shard=shard)
+        G, terms = self._finish(out, samples, world)
+        return G, terms, out["po1"]
+
+    def calculate_G(self, s0, pi0, samples=10):
+        self._sync()
+        shard, world = self._shard(samples)
+        out = self._engine.calculate_G(s0, pi0, samples, shard=shard)
+        G, terms = self._finish(out, samples, world)
+        return G, terms, out["ps1"], out["ps1_mean"], out["po1"]
+
+    def calculate_G_mean(self, s0, pi0):
+        self._sync()
+        out = self._engine.calculate_G_mean(s0, pi0)
+        return (self._host(out["G"]), [self._host(out["t0"]), self._host(out["t1"]), self._host(out["t2"])],
+                out["ps1_mean"], out["po1"])
+
+    def calculate_G_given_trajectory(self, s0_traj, ps1_traj, ps1_mean_traj, ps1_logvar_traj, pi0_traj):
+        self._sync()
+        return self._host(self._engine.G_given_trajectory(s0_traj, ps1_traj, ps1_mean_traj, ps1_logvar_traj, pi0_traj))
+
+    def mcts_step_simulate(self, starting_s, depth, use_means=False):
+        self._sync()
+        G, pi0, qpi = self._engine.mcts_simulate(starting_s, depth, use_means)
+        return G, self._host(pi0), self._host(qpi)

@@ -1,0 +1,163 @@
+/*
+ * dai_b200.h — C ABI of the B200-native Monte-Carlo EFE rollout path.
+ *
+ * The reference (zfountas/deep-active-inference-mc @ d7e76d8) has no FFI: its boundary
+ * is the Python attribute surface of ActiveInferenceModel and its three sub-modules
+ * (src/torchmodel.py:149-393), used from src/mcts.py:71-85,158-164,188, src/util.py:62,
+ * test_demo.py:56-57,136-137,150.  Each entry point below names the reference method it
+ * replaces.  The Python mirror of that surface (deep-active-inference-mc_b200/
+ * torchmodel.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative DAI_E_* code; nothing throws or
+ *     aborts; dai_last_error() gives the message of the last failure on that handle;
+ *   - all tensors are contiguous float32; images are NCHW (B,1,64,64) == (B,4096);
+ *     unless a function says "host", pointers are device pointers on the handle's GPU and
+ *     the work is enqueued on `stream` (a cudaStream_t passed as void*) and not waited for;
+ *   - the caller owns every buffer it passes; the handle owns repacked weights and
+ *     workspaces (freed in dai_destroy).  One handle per (process, device); a handle is
+ *     not thread-safe; distinct handles are independent; no global mutable state;
+ *   - noise: every compute call draws its MC-dropout masks and reparameterisation normals
+ *     from Philox4x32-10 keyed by (seed + call_index) and addressed by
+ *     (step, sample, site, row, element) — DESIGN.md "Noise".  Each entry point states
+ *     how many call indices it consumes.
+ */
+#ifndef DAI_B200_H
+#define DAI_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DAI_API __attribute__((visibility("default")))
+#else
+#define DAI_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAI_OK              0
+#define DAI_E_INVALID      -1   /* bad argument / shape / state            */
+#define DAI_E_CUDA         -2   /* CUDA runtime or driver error            */
+#define DAI_E_NOMEM        -3   /* device allocation failed                */
+#define DAI_E_WEIGHTS      -4   /* weights missing or not committed        */
+#define DAI_E_UNSUPPORTED  -5   /* configuration outside the built path    */
+
+/* arithmetic of the contraction layers (dai_set_precision) */
+#define DAI_PREC_FP32_SIMT   0  /* fp32 FMA on CUDA cores (debug / exact reference on device) */
+#define DAI_PREC_BF16X3      1  /* tcgen05 kind::f16, hi/lo split, 3 products, fp32 accumulate (parity mode) */
+#define DAI_PREC_BF16X1      2  /* tcgen05 single bf16 pass (fast mode, statistical validation only)        */
+
+typedef struct dai_handle dai_handle;
+
+typedef struct dai_config {
+    int32_t s_dim;            /* 10  (ActiveInferenceModel.__init__, src/torchmodel.py:150) */
+    int32_t pi_dim;           /* 4                                                        */
+    int32_t resolution;       /* 64                                                       */
+    int32_t colour_channels;  /* 1                                                        */
+    int32_t precision;        /* DAI_PREC_*                                               */
+    int32_t training;         /* 1: MC-dropout on (the reference's only mode), 0: identity */
+} dai_config;
+
+/* per-call counters filled by dai_get_stats */
+typedef struct dai_stats {
+    uint64_t kernel_launches; /* kernels of this library launched since the last reset */
+    uint64_t calls;           /* compute entry points served                           */
+    uint64_t workspace_bytes; /* device bytes currently held by the handle             */
+} dai_stats;
+
+DAI_API int  dai_create(const dai_config* cfg, int device, dai_handle** out);
+DAI_API int  dai_destroy(dai_handle* h);
+DAI_API const char* dai_last_error(const dai_handle* h);
+DAI_API const char* dai_version(void);
+
+/* ---- weights: the 46 state_dict tensors of model_top / model_mid / model_down
+ *      (src/torchmodel.py:167-177 checkpoint keys, e.g. "po_net.9.weight"); torch layouts
+ *      (Linear (out,in); Conv2d (Cout,Cin,3,3); ConvTranspose2d (Cin,Cout,3,3)).
+ *      `data` may be a host or a device pointer.  dai_commit_weights repacks (transposes,
+ *      NHWC permutations, bf16 hi/lo split) and must be called before any compute call. */
+DAI_API int  dai_set_weight(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+DAI_API int  dai_commit_weights(dai_handle* h, void* stream);
+
+DAI_API int  dai_set_rng(dai_handle* h, uint64_t seed, uint64_t call_index);
+DAI_API int  dai_get_rng(const dai_handle* h, uint64_t* seed, uint64_t* call_index);
+DAI_API int  dai_set_training(dai_handle* h, int training);      /* nn.Module.train()/eval() on the three nets */
+DAI_API int  dai_set_precision(dai_handle* h, int precision);
+DAI_API int  dai_get_stats(dai_handle* h, dai_stats* out, int reset);
+
+/* ---- single-net forwards (1 call index each, dai_habit 0) -------------------------- */
+
+/* ModelDown.encoder / encoder_with_sample (src/torchmodel.py:134-137,143-146).
+ * o (B,4096) -> mean (B,10), logvar (B,10); sample (B,10) may be NULL. */
+DAI_API int  dai_encode(dai_handle* h, const float* o, int B, float* mean, float* logvar, float* sample, void* stream);
+
+/* ModelDown.decoder (src/torchmodel.py:139-141).  s (B,10) -> po (B,4096). */
+DAI_API int  dai_decode(dai_handle* h, const float* s, int B, float* po, void* stream);
+
+/* ModelMid.transition / transition_with_sample (src/torchmodel.py:58-66).
+ * pi (B,4), s0 (B,10) -> mean, logvar (B,10); sample may be NULL. */
+DAI_API int  dai_transition(dai_handle* h, const float* pi, const float* s0, int B,
+                    float* mean, float* logvar, float* sample, void* stream);
+
+/* ModelTop.encode_s (src/torchmodel.py:27-31).  s (B,10) -> logits, q, logq (B,4); any may be NULL. */
+DAI_API int  dai_habit(dai_handle* h, const float* s, int B, float* logits, float* q, float* logq, void* stream);
+
+/* ActiveInferenceModel.check_reward (src/torchmodel.py:210-212).  o (B,4096) -> r (B). */
+DAI_API int  dai_check_reward(dai_handle* h, const float* o, int B, float* r, void* stream);
+
+/* ---- EFE evaluators ---------------------------------------------------------------- */
+
+/* calculate_G (src/torchmodel.py:270-300) for B (state, action) rows and `samples` MC
+ * samples; 1 call index.  This rank evaluates samples [sample_begin, sample_end) (pass
+ * 0, samples for everything).  Outputs, each may be NULL:
+ *   sums (4,B) float64: sum over the local samples of term0, term1, term2_1, term2_2 (NOT
+ *   divided) — the payload of the one all-reduce when samples are sharded over GPUs;
+ *   G, t0, t1, t2 (B): the finished values — only meaningful when the rank holds all samples;
+ *   ps1, ps1_mean, ps1_logvar (B,10), po1 (B,4096): from the globally LAST loop-2a sample
+ *   (every rank recomputes that sample under the same noise key, so these agree on all ranks). */
+DAI_API int  dai_calculate_G(dai_handle* h, const float* s0, const float* pi0, int B, int samples,
+                     int sample_begin, int sample_end,
+                     double* sums, float* G, float* t0, float* t1, float* t2,
+                     float* ps1, float* ps1_mean, float* ps1_logvar, float* po1, void* stream);
+
+/* calculate_G_mean (src/torchmodel.py:302-327); 1 call index. */
+DAI_API int  dai_calculate_G_mean(dai_handle* h, const float* s0, const float* pi0, int B,
+                          float* G, float* t0, float* t1, float* t2,
+                          float* ps1_mean, float* po1, void* stream);
+
+/* calculate_G_given_trajectory (src/torchmodel.py:329-352); 1 call index.  D rows. */
+DAI_API int  dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, const float* ps1_mean,
+                            const float* ps1_logvar, const float* pi0, int D, float* G, void* stream);
+
+/* calculate_G_repeated (src/torchmodel.py:227-245) and calculate_G_4_repeated (:247-268);
+ * 1 call index.  o (B,4096); pi (B,4) or NULL for eye(4) tiled over B/4 roots (row =
+ * root*4 + action, src/util.py:57-60).  `four` selects the _4_ semantics (calculate_G_mean
+ * when calc_mean).  T = steps sequential calculate_G evaluations with the s0 carry kept on
+ * the device.  Sample sharding and outputs as in dai_calculate_G; sums accumulate over steps. */
+DAI_API int  dai_rollout(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples,
+                 int calc_mean, int four, int sample_begin, int sample_end,
+                 double* sums, float* G, float* t0, float* t1, float* t2, float* po1, void* stream);
+
+/* Finish sharded sums after the all-reduce: sums (4,B) -> G, t0, t1, t2 (B). */
+DAI_API int  dai_combine(dai_handle* h, const double* sums, int B, int samples,
+                 float* G, float* t0, float* t1, float* t2, void* stream);
+
+/* Same as dai_rollout with HOST buffers: copies o (and pi) host->device, runs, copies
+ * G,t0,t1,t2 (and po1 if not NULL) device->host and waits.  This is the end-to-end call
+ * bench.py times as `e2e`. */
+DAI_API int  dai_rollout_host(dai_handle* h, const float* o_host, const float* pi_host, int B, int steps,
+                      int samples, int calc_mean, int four,
+                      float* G_host, float* t0_host, float* t1_host, float* t2_host, float* po1_host,
+                      void* stream);
+
+/* mcts_step_simulate (src/torchmodel.py:354-393); 2 call indices (rollout, trajectory).
+ * starting_s (10) device; writes pi0 (depth,4), qpi (4) on the device and the mean G to
+ * *G_host (waits for the stream). */
+DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means,
+                       float* G_host, float* pi0, float* qpi, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAI_B200_H */

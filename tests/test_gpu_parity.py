@@ -1,0 +1,98 @@
+"""Parity of the CUDA path (through the drop-in model -> ctypes -> C ABI) against the oracle
+and against the fixtures written from the real reference.  Tolerances: cases.compare
+(1e-4 relative on G/term0/term1, term2 against |G|, images/latents rtol 1e-4 + atol 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+_models, _oracles = {}, {}
+
+
+def _model(kind, precision):
+    from dai_b200.torchmodel import ActiveInferenceModel
+    key = (kind, precision)
+    if key not in _models:
+        m = ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, precision=precision, device="cuda:0")
+        _models[key] = m.load_numpy_weights(cases.weights_for(kind))
+    return _models[key]
+
+
+def _oracle(kind):
+    from oracle import efe_oracle as O
+    if kind not in _oracles:
+        _oracles[kind] = O.OracleModel(cases.weights_for(kind), seed=cases.SEED)
+    return _oracles[kind]
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "bf16x3"])
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_case_matches_reference_fixture_and_oracle(name, precision, golden):
+    kind = cases.CASES[name][0]
+    got = cases.run_case(name, _model(kind, precision), dev="cuda:0")
+    assert cases.compare(name, got, golden[name]) == []
+    ref = cases.run_case(name, _oracle(kind))
+    assert cases.compare(name, got, ref) == []
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "bf16x3"])
+def test_sample_shards_sum_to_the_full_evaluation(precision):
+    """Single-process emulation of W ranks: partial sums over sample shards add up to the
+    unsharded call, and the last-sample outputs agree on every shard (SURVEY.md §8 e)."""
+    from dai_b200.sharding import shard_range
+    m = _model("w0", precision)
+    eng = m._engine
+    m._sync()
+    s0 = torch.from_numpy(np.random.default_rng(3).standard_normal((8, 10)).astype(np.float32)).cuda()
+    pi = torch.eye(4, device="cuda").repeat(2, 1)
+    N = 7
+    eng.set_rng(77, 0)
+    full = eng.calculate_G(s0, pi, N)
+    for W in (2, 3):
+        sums = torch.zeros_like(full["sums"])
+        for r in range(W):
+            eng.set_rng(77, 0)
+            part = eng.calculate_G(s0, pi, N, shard=shard_range(N, r, W))
+            sums += part["sums"]
+            for k in ("ps1", "ps1_mean", "ps1_logvar", "po1"):
+                assert torch.equal(part[k], full[k]), (k, W, r)
+        assert torch.allclose(sums, full["sums"], rtol=1e-6, atol=1e-6)
+        G, t0, t1, t2 = eng.combine(sums, N)
+        assert torch.allclose(G, full["G"], rtol=1e-5, atol=1e-4)
+
+
+def test_eval_mode_disables_dropout():
+    m = _model("w0", "fp32_simt")
+    s = torch.zeros(3, 10, device="cuda")
+    try:
+        m.model_down.eval(); m.model_mid.eval()
+        m.set_rng(1, 0)
+        a = m.model_down.decoder(s)
+        m.set_rng(2, 9)
+        b = m.model_down.decoder(s)
+        assert torch.equal(a, b)
+        from oracle import efe_oracle as O
+        ora = O.OracleModel(cases.weights_for("w0"), seed=1, training=False)
+        ref = ora.model_down.decoder(torch.zeros(3, 10))
+        assert torch.allclose(a.cpu(), ref, rtol=1e-4, atol=1e-5)
+    finally:
+        m.model_down.train(); m.model_mid.train()
+
+
+def test_weight_updates_are_picked_up():
+    m = _model("w0", "fp32_simt")
+    s = torch.zeros(2, 10, device="cuda")
+    m.set_rng(5, 0)
+    a = m.model_down.decoder(s)
+    with torch.no_grad():
+        m.model_down.po_net[19].bias.add_(0.5)
+    m.set_rng(5, 0)
+    b = m.model_down.decoder(s)
+    with torch.no_grad():
+        m.model_down.po_net[19].bias.sub_(0.5)
+    m.set_rng(5, 0)
+    c = m.model_down.decoder(s)
+    assert not torch.equal(a, b) and torch.allclose(a, c, atol=1e-6)
