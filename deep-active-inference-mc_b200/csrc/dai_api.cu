@@ -799,4 +799,27 @@ int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use
     return DAI_OK;
 }
 
+int dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, int nrows, float* out, void* stream) {
+    RET(check_ready(h));
+    if (!in || !out || nrows <= 0 || layer < 1 || layer > 3) return fail(h, DAI_E_INVALID, "debug_layer: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == DAI_PREC_FP32_SIMT) {
+        if (layer == 1) h->launches += launch_ct1_simt(h->w, in, nrows, out, st);
+        if (layer == 2) h->launches += launch_ct2_simt(h->w, in, nrows, out, st);
+        if (layer == 3) h->launches += launch_ct3_simt(h->w, in, nrows, out, st);
+        return post_launch(h, "debug layer (simt)");
+    }
+    const int hw_in = layer == 3 ? 1024 : 256, hw_out = layer == 1 ? 256 : (layer == 2 ? 1024 : 4096);
+    RET(reserve(h, h->act0, (size_t)nrows * hw_in * 64 * 4));
+    RET(reserve(h, h->act1, (size_t)nrows * hw_out * 64 * 4));
+    h->launches += tc_to_blocked(in, nrows, hw_in, 64, h->act0.p, st);
+    std::string terr;
+    void* dst = layer == 3 ? (void*)out : h->act1.p;
+    const int nl = tc_layer(h->tcw, h->w, precision, layer, h->act0.p, dst, nrows, st, &terr);
+    if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core layer: %s", terr.c_str());
+    h->launches += nl;
+    if (layer != 3) h->launches += tc_from_blocked(h->act1.p, nrows, hw_out, 64, out, st);
+    return post_launch(h, "debug layer (tc)");
+}
+
 }  // extern "C"

@@ -58,6 +58,7 @@ int  launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows,
 
 // fp32 SIMT layers over a chunk of decoder rows [row0, row0+nrows)
 int  launch_fc4_simt(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, float* act0, cudaStream_t st);
+int  launch_fc4_simt_blocked(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, void* act0, cudaStream_t st);
 int  launch_ct1_simt(const DevWeights& w, const float* act0, int nrows, float* act1, cudaStream_t st);
 int  launch_ct2_simt(const DevWeights& w, const float* act1, int nrows, float* act2, cudaStream_t st);
 int  launch_ct3_simt(const DevWeights& w, const float* act2, int nrows, float* act3, cudaStream_t st);

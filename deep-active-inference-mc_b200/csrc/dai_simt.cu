@@ -4,6 +4,8 @@
 // DAI_PREC_FP32_SIMT mode (the on-device exact reference for the tcgen05 kernels).
 #include "dai_kernels.h"
 
+#include <cuda_bf16.h>
+
 namespace dai {
 
 // ======================================================================================
@@ -260,6 +262,8 @@ struct ConvGeom {
     const float* bias;
     float* out;
     const uint32_t* mask;// dense only: dropout bits [M][Cout/32]
+    unsigned short* out_blocked;   // dense FC4 only: write blocked bf16 [plane hi|lo][row][kc 8][16][16][8] instead of `out`
+    size_t plane;                  // elements per bf16 plane
 };
 
 __device__ __forceinline__ int geom_ntaps(const ConvGeom& g, int phase) {
@@ -380,7 +384,17 @@ __global__ void __launch_bounds__(256) k_gather_gemm(ConvGeom g) {
             const int n = n0 + tx * TN + j;
             float v = fmaxf(acc[i][j] + __ldg(g.bias + n), 0.0f);
             if (g.mask) v = ((g.mask[(size_t)m * (g.Cout >> 5) + (n >> 5)] >> (n & 31)) & 1u) ? v * 2.0f : 0.0f;
-            g.out[obase + n] = v;
+            if (g.out_blocked) {
+                // n = pixel * 64 + c of the (16,16,64) NHWC map -> channel-blocked bf16 hi/lo planes
+                const int px = n >> 6, c = n & 63;
+                const size_t o = (((size_t)m * 8 + (c >> 3)) * 256 + px) * 8 + (c & 7);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                g.out_blocked[o] = __bfloat16_as_ushort(hi);
+                g.out_blocked[g.plane + o] = __bfloat16_as_ushort(lo);
+            } else {
+                g.out[obase + n] = v;
+            }
         }
     }
 }
@@ -397,6 +411,14 @@ int launch_fc4_simt(const DevWeights& w, const float* h3, const uint32_t* mask, 
     ConvGeom g{};
     g.mode = 0; g.M = nrows; g.Cin = 256; g.Cout = 16384;
     g.in = h3; g.W = w.po_w3t; g.bias = w.po_b3; g.out = act0; g.mask = mask;
+    return launch_gemm<64, 64>(g, 1, st);
+}
+
+int launch_fc4_simt_blocked(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, void* act0, cudaStream_t st) {
+    ConvGeom g{};
+    g.mode = 0; g.M = nrows; g.Cin = 256; g.Cout = 16384;
+    g.in = h3; g.W = w.po_w3t; g.bias = w.po_b3; g.out = nullptr; g.mask = mask;
+    g.out_blocked = static_cast<unsigned short*>(act0); g.plane = (size_t)nrows * 16384;
     return launch_gemm<64, 64>(g, 1, st);
 }
 

@@ -1,21 +1,639 @@
-// Tensor-core path (tcgen05 / TMEM / TMA) of the contraction layers.
+// Tensor-core path of the decoder's contraction layers: tcgen05.mma (kind::f16, bf16 operands,
+// fp32 accumulators in TMEM) fed by TMA, warp-specialised, persistent.
+//
+// Transposed convolutions are implicit GEMMs over a halo tile that is loaded ONCE per
+// 128-pixel output tile and re-read by every tap through shifted shared-memory descriptors:
+//   activations in HBM are channel-blocked   [plane hi|lo][row][kc = C/8][H][W][8] bf16
+//   a TMA box (W' x H' x 8 kc x 2 planes) lands as [plane][kc][y][x][8] = the UMMA
+//   no-swizzle K-major canonical layout (8 pixels x 16 B core matrices, LBO = kc plane,
+//   SBO = halo row pitch), so a tap shift is just a start-address offset of 16 B per pixel.
+// Precision: x = hi + lo (bf16 each); D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (DAI_PREC_BF16X3)
+// or the first product only (DAI_PREC_BF16X1).
 #include "dai_tc.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "../../include/dai_b200.h"
 
 namespace dai {
 
-int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
-                    std::string* err) {
-    (void)raw; (void)allocs; (void)err;
-    out->impl = nullptr;
+namespace {
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must fail the launch (trap -> CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, K = 16, bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8-row x 16-byte core matrices;
+// LBO = bytes between the two 16-byte K chunks of one MMA, SBO = bytes between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---------------------------------------------------------------------------------------
+// layer geometry
+// ---------------------------------------------------------------------------------------
+struct Unit {            // one MMA group of a tile: a tap shift of the halo x a block of weights
+    int16_t oy, ox;      // halo-local pixel offset of the A window
+    int16_t col;         // TMEM column offset inside the tile's accumulator block
+    int16_t n;           // N of the MMA
+    int16_t init;        // 1: its first MMA overwrites the accumulator
+    int32_t woff;        // byte offset of its weight block (resident layout) / index * slot (streamed)
+};
+
+constexpr int MAX_UNITS = 9;
+
+struct ConvParams {
+    Unit units[MAX_UNITS];
+    int32_t nunits;
+    int32_t nrows;           // images in this launch
+    int32_t nprod;           // 3: bf16x3, 1: bf16x1
+    const uint8_t* wpack;    // packed weights (see pack_layer)
+    const float* bias;       // [Cout]
+    void* out;               // blocked bf16 planes (ct1, ct2) or fp32 NHWC (ct3)
+};
+
+template <int MODE_, int NPH_, int HIN_, int WIN_, bool WRES_, int NA_>
+struct Cfg {
+    static constexpr int MODE = MODE_;       // 0: convT k3 s1 p1; 1: convT k3 s2 p1 op1 (4 sub-pixel phases)
+    static constexpr int NPH = NPH_;         // Cout
+    static constexpr int HIN = HIN_, WIN = WIN_;
+    static constexpr bool WRES = WRES_;      // weights resident in shared memory
+    static constexpr int NA = NA_;           // A (halo) stages
+    static constexpr int TH = 16, TW = 8;    // tile of the m-grid: 128 pixels
+    static constexpr int HY = MODE == 0 ? TH + 2 : TH + 1;
+    static constexpr int HX = MODE == 0 ? TW + 2 : TW + 1;
+    static constexpr int KC_STRIDE = HY * HX * 16;             // bytes of one 8-channel plane of the halo
+    static constexpr int PLANE_A = 8 * KC_STRIDE;              // one bf16 plane (64 channels)
+    static constexpr int A_BYTES = 2 * PLANE_A;
+    static constexpr int TILES_X = WIN / TW, TILES_Y = HIN / TH;
+    static constexpr int TILES = TILES_X * TILES_Y;
+    static constexpr int ACC_COLS = MODE == 0 ? NPH : 4 * NPH;
+    static constexpr int NACC = 2;
+    static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
+    static constexpr int W_BYTES = 9 * NPH * 256;              // all taps, hi + lo
+    static constexpr int NB = 4;                               // weight ring slots (streamed)
+    static constexpr int B_SLOT = NPH * 256;                   // one (tap) block, hi + lo
+    static constexpr int SMEM_W = WRES ? W_BYTES : NB * B_SLOT;
+    static constexpr int SMEM_A = NA * A_BYTES;
+    static constexpr int SMEM_BYTES = SMEM_W + SMEM_A + 1024;  // + barriers, tmem slot, bias
+};
+
+// ---------------------------------------------------------------------------------------
+// the kernel: warp 0 = halo TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warp 3 = weight producer, warps 4..7 = epilogue (TMEM -> registers -> HBM)
+// ---------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUtensorMap tmapA, const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smW = smem;
+    uint8_t* smA = smem + C::SMEM_W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_W + C::SMEM_A);
+    uint64_t* a_full = bars;                  // [NA]
+    uint64_t* a_empty = a_full + C::NA;       // [NA]
+    uint64_t* b_full = a_empty + C::NA;       // [NB]
+    uint64_t* b_empty = b_full + C::NB;       // [NB]
+    uint64_t* acc_full = b_empty + C::NB;     // [NACC]
+    uint64_t* acc_empty = acc_full + C::NACC; // [NACC]
+    uint64_t* w_full = acc_empty + C::NACC;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [NPH]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + C::NPH) sbias[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ntiles = p.nrows * C::TILES;
+
+    if (warp == 0) {
+        // ===== halo producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it % C::NA;
+                const uint32_t ph = (uint32_t)(it / C::NA) & 1u;
+                mbar_wait(&a_empty[s], ph ^ 1u);
+                const int row = tile / C::TILES, t = tile % C::TILES;
+                const int y0 = (t / C::TILES_X) * C::TH, x0 = (t % C::TILES_X) * C::TW;
+                const int hy0 = C::MODE == 0 ? y0 - 1 : y0, hx0 = C::MODE == 0 ? x0 - 1 : x0;
+                mbar_expect_tx(&a_full[s], C::A_BYTES);
+                tma_load_5d(smA + (size_t)s * C::A_BYTES, &tmapA, &a_full[s], hx0 * 8, hy0, 0, row, 0);
+            }
+        }
+    } else if (warp == 3) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            if (C::WRES) {
+                mbar_expect_tx(w_full, C::W_BYTES);
+                for (int off = 0; off < C::W_BYTES; off += 8192)
+                    bulk_load(smW + off, p.wpack + off, 8192, w_full);
+            } else {
+                int cnt = 0;
+                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                    for (int u = 0; u < p.nunits; ++u, ++cnt) {
+                        const int s = cnt % C::NB;
+                        const uint32_t ph = (uint32_t)(cnt / C::NB) & 1u;
+                        mbar_wait(&b_empty[s], ph ^ 1u);
+                        mbar_expect_tx(&b_full[s], C::B_SLOT);
+                        bulk_load(smW + (size_t)s * C::B_SLOT, p.wpack + p.units[u].woff, C::B_SLOT, &b_full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            if (C::WRES) { mbar_wait(w_full, 0); tc_fence_after(); }
+            int it = 0, cnt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int buf = it % C::NACC;
+                const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
+                mbar_wait(&acc_empty[buf], aph ^ 1u);
+                const int s = it % C::NA;
+                const uint32_t ph = (uint32_t)(it / C::NA) & 1u;
+                mbar_wait(&a_full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smA + (size_t)s * C::A_BYTES);
+                for (int u = 0; u < p.nunits; ++u, ++cnt) {
+                    const Unit un = p.units[u];
+                    uint32_t w_base;
+                    int bs = 0;
+                    if (C::WRES) {
+                        w_base = smem_u32(smW + un.woff);
+                    } else {
+                        bs = cnt % C::NB;
+                        const uint32_t bph = (uint32_t)(cnt / C::NB) & 1u;
+                        mbar_wait(&b_full[bs], bph);
+                        tc_fence_after();
+                        w_base = smem_u32(smW + (size_t)bs * C::B_SLOT);
+                    }
+                    const uint32_t n = (uint32_t)un.n;
+                    const uint32_t idesc = umma_idesc(un.n);
+                    const uint32_t b_plane = 8u * n * 16u;            // one bf16 plane of this block
+                    const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+                    const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a_hi = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                        const uint64_t a_lo = umma_desc(a_base + C::PLANE_A + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                        const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                        const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                        umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
+                        if (p.nprod == 3) {
+                            umma_bf16(d, a_lo, b_hi, idesc, 1u);
+                            umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                        }
+                    }
+                    if (!C::WRES) umma_commit(&b_empty[bs]);
+                }
+                umma_commit(&a_empty[s]);
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: lane = pixel of the tile =====
+        const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may read
+        const int m = ew * 32 + lane;
+        const int ty = m >> 3, tx = m & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int buf = it % C::NACC;
+            const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
+            const int row = tile / C::TILES, t = tile % C::TILES;
+            const int y = (t / C::TILES_X) * C::TH + ty, x = (t % C::TILES_X) * C::TW + tx;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
+            if (C::MODE == 0) {
+                // -> blocked bf16 hi/lo [plane][row][kc][H][W][8]
+                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                const size_t plane = (size_t)p.nrows * C::NPH * C::HIN * C::WIN;
+#pragma unroll
+                for (int c0 = 0; c0 < C::NPH; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tbase + c0, r);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + sbias[c0 + q * 8 + 2 * e], 0.0f), h0, l0);
+                            split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + sbias[c0 + q * 8 + 2 * e + 1], 0.0f), h1, l1);
+                            hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
+                        }
+                        const int kc = (c0 >> 3) + q;
+                        const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * C::HIN + y) * C::WIN + x) * 8;
+                        *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            } else {
+                constexpr int HO = 2 * C::HIN, WO = 2 * C::WIN;
+#pragma unroll
+                for (int slot = 0; slot < 4; ++slot) {
+                    // TMEM column block `slot` holds phase (py,px); the map is fixed by the host unit table:
+                    // streamed layers use slot = py*2+px, resident grouped layers use [00,01,11,10]
+                    const int phase = C::WRES ? ((slot == 2) ? 3 : (slot == 3) ? 2 : slot) : slot;
+                    const int oy = 2 * y + (phase >> 1), ox = 2 * x + (phase & 1);
+#pragma unroll
+                    for (int c0 = 0; c0 < C::NPH; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tbase + slot * C::NPH + c0, r);
+                        if (C::NPH == 32) {
+                            // last tensor-core layer: fp32 NHWC [row][HO][WO][32] for the pixel-term kernel
+                            float* out = reinterpret_cast<float*>(p.out) + (((size_t)row * HO + oy) * WO + ox) * 32;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 v;
+                                v.x = fmaxf(__uint_as_float(r[q * 4 + 0]) + sbias[q * 4 + 0], 0.0f);
+                                v.y = fmaxf(__uint_as_float(r[q * 4 + 1]) + sbias[q * 4 + 1], 0.0f);
+                                v.z = fmaxf(__uint_as_float(r[q * 4 + 2]) + sbias[q * 4 + 2], 0.0f);
+                                v.w = fmaxf(__uint_as_float(r[q * 4 + 3]) + sbias[q * 4 + 3], 0.0f);
+                                *reinterpret_cast<float4*>(out + q * 4) = v;
+                            }
+                        } else {
+                            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                            const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    __nv_bfloat16 h0, l0, h1, l1;
+                                    split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + sbias[c0 + q * 8 + 2 * e], 0.0f), h0, l0);
+                                    split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + sbias[c0 + q * 8 + 2 * e + 1], 0.0f), h1, l1);
+                                    hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
+                                }
+                                const int kc = (c0 >> 3) + q;
+                                const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * HO + oy) * WO + ox) * 8;
+                                *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+using CfgCt1 = Cfg<0, 64, 16, 16, false, 3>;
+using CfgCt2 = Cfg<1, 64, 16, 16, false, 3>;
+using CfgCt3 = Cfg<1, 32, 32, 32, true, 3>;
+
+// ---------------------------------------------------------------------------------------
+// host: weight packing, tensor maps, launches
+// ---------------------------------------------------------------------------------------
+struct LayerPack {
+    uint8_t* wpack = nullptr;    // device
+    Unit units[MAX_UNITS];
+    int nunits = 0;
+};
+
+struct TcImpl {
+    LayerPack ct1, ct2, ct3;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+    bool attrs_set = false;
+};
+
+inline uint16_t f2bf(float v) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);          // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float v;
+    memcpy(&v, &u, 4);
+    return v;
+}
+
+struct Sub { int kh, kw; };
+
+// One weight block = [plane hi|lo][kc 8][n][8] bf16 with n = sub * Cout + co, K = Cin = 64:
+// the UMMA no-swizzle K-major layout of a (n x 64) operand.  ConvTranspose2d weight is (Cin,Cout,3,3).
+void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst) {
+    const int n = nsub * Cout;
+    for (int s = 0; s < nsub; ++s)
+        for (int co = 0; co < Cout; ++co)
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float v = W[(((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw];
+                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                const int nn = s * Cout + co, kc = ci >> 3, e = ci & 7;
+                const size_t o = ((size_t)kc * n + nn) * 8 + e;
+                dst[o] = hi;
+                dst[(size_t)8 * n * 8 + o] = lo;
+            }
+}
+
+// sub-pixel decomposition of ConvTranspose2d(k3, s2, p1, op1): output (2y+py, 2x+px) reads input
+// (y+dy, x+dx) with kh = 1 (py = 0); kh = 0 for dy = 1 and kh = 2 for dy = 0 (py = 1); same in x.
+inline int k_of(int parity, int d) { return parity == 0 ? 1 : (d == 1 ? 0 : 2); }
+
+int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool grouped, LayerPack* lp,
+                std::vector<void*>* allocs, std::string* err) {
+    std::vector<uint16_t> host((size_t)9 * Cout * 128);       // 9 taps * Cout * 64 k * 2 planes
+    int nu = 0;
+    size_t off = 0;                                            // in uint16 elements
+    auto add = [&](int oy, int ox, int col, const Sub* subs, int nsub, int init) {
+        Unit& u = lp->units[nu++];
+        u.oy = (int16_t)oy; u.ox = (int16_t)ox; u.col = (int16_t)col; u.n = (int16_t)(nsub * Cout); u.init = (int16_t)init;
+        u.woff = (int32_t)(off * 2);
+        pack_block(W, Cin, Cout, subs, nsub, host.data() + off);
+        off += (size_t)nsub * Cout * 128;
+    };
+    if (mode == 0) {
+        // convT s1 p1: oy = iy - 1 + kh; halo origin (y0-1, x0-1) => local row = ty + 2 - kh
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                Sub s{kh, kw};
+                add(2 - kh, 2 - kw, 0, &s, 1, nu == 0);
+            }
+    } else if (!grouped) {
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                bool first = true;
+                for (int dy = 0; dy <= py; ++dy)
+                    for (int dx = 0; dx <= px; ++dx) {
+                        Sub s{k_of(py, dy), k_of(px, dx)};
+                        add(dy, dx, (py * 2 + px) * Cout, &s, 1, first);
+                        first = false;
+                    }
+            }
+    } else {
+        // column slots [00, 01, 11, 10]; every shift of the halo feeds all phases that read it in one MMA
+        const Sub g00[4] = {{k_of(0, 0), k_of(0, 0)}, {k_of(0, 0), k_of(1, 0)}, {k_of(1, 0), k_of(1, 0)}, {k_of(1, 0), k_of(0, 0)}};
+        add(0, 0, 0, g00, 4, 1);
+        const Sub g01[2] = {{k_of(0, 0), k_of(1, 1)}, {k_of(1, 0), k_of(1, 1)}};        // phases 01, 11
+        add(0, 1, 1 * Cout, g01, 2, 0);
+        const Sub g10[2] = {{k_of(1, 1), k_of(1, 0)}, {k_of(1, 1), k_of(0, 0)}};        // phases 11, 10
+        add(1, 0, 2 * Cout, g10, 2, 0);
+        const Sub g11[1] = {{k_of(1, 1), k_of(1, 1)}};                                  // phase 11
+        add(1, 1, 2 * Cout, g11, 1, 0);
+    }
+    lp->nunits = nu;
+    void* d = nullptr;
+    if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(tc weights)"; return -1; }
+    allocs->push_back(d);
+    if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(tc weights)"; return -1; }
+    lp->wpack = static_cast<uint8_t*>(d);
     return 0;
 }
 
-void tc_release(TcWeights* w) { w->impl = nullptr; }
+// blocked bf16 activation tensor [plane 2][rows][kc 8][H][W][8] -> 5-D map (W*8, H, kc, rows, plane), box = halo
+int make_map(TcImpl* im, const void* base, int rows, int H, int W, int HX, int HY, CUtensorMap* map, std::string* err) {
+    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, 8, (cuuint64_t)rows, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)8 * H * W * 16,
+                             (cuuint64_t)rows * 8 * H * W * 16};
+    cuuint32_t box[5] = {(cuuint32_t)HX * 8, (cuuint32_t)HY, 8, 1, 2};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = im->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        *err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+        return -1;
+    }
+    return 0;
+}
 
-int tc_decoder_chunk(const TcWeights&, const DevWeights&, int, const float*, const uint32_t*, int, void*, void*, void*,
-                     void*, const Ct4Args&, cudaStream_t, std::string* err) {
-    if (err) *err = "tensor-core decoder not built yet";
+template <class C>
+int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precision, const void* in, void* out, int nrows,
+                cudaStream_t st, std::string* err) {
+    CUtensorMap map;
+    if (make_map(im, in, nrows, C::HIN, C::WIN, C::HX, C::HY, &map, err) != 0) return -1;
+    ConvParams p{};
+    for (int i = 0; i < lp.nunits; ++i) p.units[i] = lp.units[i];
+    p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
+    p.wpack = lp.wpack; p.bias = bias; p.out = out;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = nrows * C::TILES;
+    const int grid = ntiles < sms ? ntiles : sms;
+    k_tc_conv<C><<<grid, 256, C::SMEM_BYTES, st>>>(map, p);
+    return 1;
+}
+
+__global__ void k_to_blocked(const float* __restrict__ in, int rows, int hw, int C, __nv_bfloat16* __restrict__ out) {
+    const size_t n = (size_t)rows * hw * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t px = (i / C) % hw, row = i / ((size_t)C * hw);
+        __nv_bfloat16 hi, lo;
+        split_bf16(in[i], hi, lo);
+        const size_t o = ((row * (C / 8) + (c >> 3)) * hw + px) * 8 + (c & 7);
+        out[o] = hi;
+        out[n + o] = lo;
+    }
+}
+
+__global__ void k_from_blocked(const __nv_bfloat16* __restrict__ in, int rows, int hw, int C, float* __restrict__ out) {
+    const size_t n = (size_t)rows * hw * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t px = (i / C) % hw, row = i / ((size_t)C * hw);
+        const size_t o = ((row * (C / 8) + (c >> 3)) * hw + px) * 8 + (c & 7);
+        out[i] = __bfloat162float(in[o]) + __bfloat162float(in[n + o]);
+    }
+}
+
+}  // namespace
+
+int tc_to_blocked(const float* nhwc, int rows, int hw, int C, void* blocked, cudaStream_t st) {
+    k_to_blocked<<<1024, 256, 0, st>>>(nhwc, rows, hw, C, static_cast<__nv_bfloat16*>(blocked));
+    return 1;
+}
+
+int tc_from_blocked(const void* blocked, int rows, int hw, int C, float* nhwc, cudaStream_t st) {
+    k_from_blocked<<<1024, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(blocked), rows, hw, C, nhwc);
+    return 1;
+}
+
+int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
+                    std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(out->impl);
+    if (!im) { im = new TcImpl(); out->impl = im; }
+    if (!im->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            *err = "cuTensorMapEncodeTiled not available from the driver";
+            return -1;
+        }
+        im->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    if (!im->attrs_set) {
+        if (cudaFuncSetAttribute(k_tc_conv<CfgCt1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt1::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgCt2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt2::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess) {
+            *err = std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(cudaGetLastError());
+            return -1;
+        }
+        im->attrs_set = true;
+    }
+    if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, &im->ct1, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, false, &im->ct2, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, &im->ct3, allocs, err) != 0) return -1;
+    return 0;
+}
+
+void tc_release(TcWeights* w) {
+    delete static_cast<TcImpl*>(w->impl);
+    w->impl = nullptr;
+}
+
+int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer, const void* in, void* out, int nrows,
+             cudaStream_t st, std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(tw.impl);
+    if (!im) { *err = "tensor-core weights not packed"; return -1; }
+    switch (layer) {
+        case 1: return launch_conv<CfgCt1>(im, im->ct1, w.ct1_b, precision, in, out, nrows, st, err);
+        case 2: return launch_conv<CfgCt2>(im, im->ct2, w.ct2_b, precision, in, out, nrows, st, err);
+        case 3: return launch_conv<CfgCt3>(im, im->ct3, w.ct3_b, precision, in, out, nrows, st, err);
+    }
+    *err = "unknown tensor-core layer";
     return -1;
+}
+
+int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const float* h3, const uint32_t* mask,
+                     int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4in, cudaStream_t st,
+                     std::string* err) {
+    int n = 0, rc;
+    n += launch_fc4_simt_blocked(w, h3, mask, nrows, act0, st);
+    if ((rc = tc_layer(tw, w, precision, 1, act0, act1, nrows, st, err)) < 0) return -1;
+    n += rc;
+    if ((rc = tc_layer(tw, w, precision, 2, act1, act2, nrows, st, err)) < 0) return -1;
+    n += rc;
+    if ((rc = tc_layer(tw, w, precision, 3, act2, act3, nrows, st, err)) < 0) return -1;
+    n += rc;
+    Ct4Args c4 = c4in;
+    c4.act3 = static_cast<const float*>(act3);
+    n += launch_ct4_efe(w, c4, st);
+    return n;
 }
 
 }  // namespace dai

@@ -26,4 +26,12 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
                      int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4, cudaStream_t st,
                      std::string* err);
 
+// One tensor-core layer (1: ct1, 2: ct2, 3: ct3) on channel-blocked bf16 hi/lo input planes.
+int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer, const void* in, void* out, int nrows,
+             cudaStream_t st, std::string* err);
+
+// fp32 NHWC [rows][HW][C] <-> channel-blocked bf16 planes [hi|lo][rows][C/8][HW][8] (test / debug converters)
+int tc_to_blocked(const float* nhwc, int rows, int hw, int C, void* blocked, cudaStream_t st);
+int tc_from_blocked(const void* blocked, int rows, int hw, int C, float* nhwc, cudaStream_t st);
+
 }  // namespace dai

@@ -61,6 +61,7 @@ SIGNATURES = {
                                         ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dai_mcts_simulate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                          _vp, _vp, _vp]),
+    "dai_debug_layer": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
 }
 
 _LIB = None
@@ -264,6 +265,16 @@ class Engine:
         self._ck(self.lib.dai_rollout_host(self.h, _p(o_host), _p(pi_host), B, steps, samples, 1 if calc_mean else 0,
                                            1 if four else 0, _p(out_host[0]), _p(out_host[1]), _p(out_host[2]),
                                            _p(out_host[3]), _p(po1_host), self._stream()))
+
+    def debug_layer(self, layer, precision, x):
+        """test hook: one decoder contraction layer, fp32 NHWC in/out (include/dai_b200.h)."""
+        x = self.dev(x)
+        n = x.shape[0]
+        hw_out, c_out = {1: (256, 64), 2: (1024, 64), 3: (4096, 32)}[layer]
+        out = self.new(n, hw_out, c_out)
+        prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        self._ck(self.lib.dai_debug_layer(self.h, layer, prec, _p(x), n, _p(out), self._stream()))
+        return out
 
     def mcts_simulate(self, starting_s, depth, use_means=False):
         s = self.dev(starting_s).reshape(10)

@@ -157,6 +157,13 @@ DAI_API int  dai_rollout_host(dai_handle* h, const float* o_host, const float* p
 DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means,
                        float* G_host, float* pi0, float* qpi, void* stream);
 
+/* ---- test hook ------------------------------------------------------------------------
+ * One decoder contraction layer in isolation (layer 1: ConvT 64->64 s1 16x16; 2: ConvT 64->64 s2
+ * 16x16->32x32; 3: ConvT 64->32 s2 32x32->64x64; src/torchmodel.py:120-124), bias + ReLU included,
+ * fp32 NHWC in and out, in the given DAI_PREC_* arithmetic.  Used by tests to compare the tcgen05
+ * kernels with the fp32 CUDA-core kernels layer by layer. */
+DAI_API int  dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, int nrows, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
