@@ -714,7 +714,9 @@ __global__ void k_step_finalize(StepFinalizeArgs a) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const int SB = a.Sl * a.B;
-    float t0 = 0.0f, t1 = 0.0f, t21 = 0.0f, t22 = 0.0f;
+    // per-sample terms are fp32 (as in the reference); their sums over samples / steps / shards are
+    // kept in fp64 so that any sample partition adds up to the same value
+    double t0 = 0.0, t1 = 0.0, t21 = 0.0, t22 = 0.0;
     for (int j = 0; j < a.Sl; ++j) {
         const int r = j * a.B + b;
         t0 += a.reward[r];
@@ -725,10 +727,10 @@ __global__ void k_step_finalize(StepFinalizeArgs a) {
         t21 += a.hsum[SB + r];
         t22 += a.hsum[2 * SB + r];
     }
-    a.acc[0 * a.B + b] += (double)t0;
-    a.acc[1 * a.B + b] += (double)t1;
-    a.acc[2 * a.B + b] += (double)t21;
-    a.acc[3 * a.B + b] += (double)t22;
+    a.acc[0 * a.B + b] += t0;
+    a.acc[1 * a.B + b] += t1;
+    a.acc[2 * a.B + b] += t21;
+    a.acc[3 * a.B + b] += t22;
     if (a.carry_src)
         for (int d = 0; d < S_DIM; ++d) a.carry_dst[b * S_DIM + d] = a.carry_src[b * S_DIM + d];
 }
