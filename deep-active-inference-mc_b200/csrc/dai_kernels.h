@@ -74,6 +74,8 @@ struct Ct4Args {
     float* reward;         // [rows]
 };
 int  launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st);
+// same, from the 9 tap projections [nrows][9][64][64] the tensor-core ct3 epilogue writes into act3
+int  launch_ct4_gather(const DevWeights& w, const Ct4Args& a, cudaStream_t st);
 
 // ---- encoder -------------------------------------------------------------------------
 struct QsArgs {

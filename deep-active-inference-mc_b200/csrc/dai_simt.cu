@@ -518,6 +518,60 @@ int launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {
     return 1;
 }
 
+// Same pixel terms from the tap projections the tensor-core ct3 epilogue leaves behind:
+// act3 = D[row][t = kh*3+kw][64][64] with D_t = <relu(ct3 out), w4[:, t]>, so the last deconv is
+//   x[oy][ox] = b + sum_t D_t[oy + 1 - kh][ox + 1 - kw]   (every D element is read exactly once).
+__global__ void __launch_bounds__(256) k_ct4_gather(DevWeights w, Ct4Args a) {
+    __shared__ float red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rl = blockIdx.x;
+    const int r = a.row0 + rl;
+    const float* D = a.act3 + (size_t)rl * 9 * IMG;
+    const float bias = __ldg(w.ct4_b);
+    const bool write_img = r < a.img_rows;
+    const float d = 0.00001f, c1 = 1.00001f;
+    const float la_top = logf(d + 1.0f), lb_top = logf(c1 - 1.0f);
+    const float la_bot = logf(d + 0.0f), lb_bot = logf(c1 - 0.0f);
+    float hacc = 0.0f, racc = 0.0f;
+    for (int i = tid; i < IMG; i += 256) {
+        const int oy = i >> 6, ox = i & 63;
+        float acc = 0.0f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int iy = oy + 1 - kh;
+            if (iy < 0 || iy >= 64) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ix = ox + 1 - kw;
+                if (ix < 0 || ix >= 64) continue;
+                acc += __ldg(D + (size_t)(kh * 3 + kw) * IMG + iy * 64 + ix);
+            }
+        }
+        const float x = acc + bias;
+        const float p = 1.0f / (1.0f + expf(-x));
+        const float q = 1.0f - p;
+        hacc += __fsub_rn(__fmul_rn(-q, logf(c1 - p)), __fmul_rn(p, logf(d + p)));
+        racc += oy < 32 ? __fadd_rn(__fmul_rn(p, la_top), __fmul_rn(q, lb_top))
+                        : __fadd_rn(__fmul_rn(p, la_bot), __fmul_rn(q, lb_bot));
+        if (write_img) a.img[(size_t)r * IMG + i] = p;
+    }
+    hacc = warp_sum(hacc); racc = warp_sum(racc);
+    if (lane == 0) { red[0][warp] = hacc; red[1][warp] = racc; }
+    __syncthreads();
+    if (tid == 0) {
+        float hs = 0.0f, rs = 0.0f;
+        for (int i = 0; i < 8; ++i) { hs += red[0][i]; rs += red[1][i]; }
+        a.hsum[r] = hs;
+        a.reward[r] = rs * (1.0f / 4096.0f) * 10.0f;
+    }
+}
+
+int launch_ct4_gather(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {
+    if (a.nrows <= 0) return 0;
+    k_ct4_gather<<<a.nrows, 256, 0, st>>>(w, a);
+    return 1;
+}
+
 // check_reward on a given image batch
 __global__ void __launch_bounds__(256) k_reward_only(const float* __restrict__ o, int B, float* __restrict__ out) {
     __shared__ float red[8];

@@ -154,11 +154,14 @@ struct ConvParams {
     int32_t nprod;           // 3: bf16x3, 1: bf16x1
     const uint8_t* wpack;    // packed weights (see pack_layer)
     const float* bias;       // [Cout]
-    void* out;               // blocked bf16 planes (ct1, ct2) or fp32 NHWC (ct3)
+    void* out;               // blocked bf16 planes (ct1, ct2) or projected fp32 planes [row][9][HO][WO] (ct3)
+    float w4[288];           // ct3 only: last deconv's weights [c 32][tap 9] (kernel params = constant bank)
 };
 
-template <int MODE_, int NPH_, int HIN_, int WIN_, bool WRES_, int NA_>
+template <int MODE_, int NPH_, int HIN_, int WIN_, bool WRES_, int NA_, int EPI_WARPS_ = 4>
 struct Cfg {
+    static constexpr int EPI_WARPS = EPI_WARPS_;            // 4, or 8 (two warps per TMEM lane quarter)
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS_;
     static constexpr int MODE = MODE_;       // 0: convT k3 s1 p1; 1: convT k3 s2 p1 op1 (4 sub-pixel phases)
     static constexpr int NPH = NPH_;         // Cout
     static constexpr int HIN = HIN_, WIN = WIN_;
@@ -188,7 +191,7 @@ struct Cfg {
 // warp 3 = weight producer, warps 4..7 = epilogue (TMEM -> registers -> HBM)
 // ---------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUtensorMap tmapA, const ConvParams p) {
+__global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant__ CUtensorMap tmapA, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smW = smem;
     uint8_t* smA = smem + C::SMEM_W;
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUte
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], C::EPI_WARPS); }
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
@@ -306,7 +309,8 @@ __global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUte
         }
     } else if (warp >= 4) {
         // ===== epilogue: lane = pixel of the tile =====
-        const int ew = warp - 4;                  // == warp % 4: the TMEM lane quarter this warp may read
+        const int ew = warp & 3;                  // the TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;         // with 8 epilogue warps: which output row parity this warp owns
         const int m = ew * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
         int it = 0;
@@ -344,31 +348,55 @@ __global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUte
                 }
             } else {
                 constexpr int HO = 2 * C::HIN, WO = 2 * C::WIN;
-#pragma unroll
-                for (int slot = 0; slot < 4; ++slot) {
-                    // TMEM column block `slot` holds phase (py,px); the map is fixed by the host unit table:
-                    // streamed layers use slot = py*2+px, resident grouped layers use [00,01,11,10]
-                    const int phase = C::WRES ? ((slot == 2) ? 3 : (slot == 3) ? 2 : slot) : slot;
-                    const int oy = 2 * y + (phase >> 1), ox = 2 * x + (phase & 1);
-#pragma unroll
-                    for (int c0 = 0; c0 < C::NPH; c0 += 32) {
+                if (C::NPH == 32) {
+                    // Last tensor-core layer.  The next layer (ConvT 32->1, k3 s1 p1) is linear in this output,
+                    // so its channel contraction is done here, in registers, per output pixel:
+                    //   d[t] = sum_c relu(acc[c] + b[c]) * w4[c][t],  t = kh*3+kw
+                    // and only the 9 projections leave the SM ([row][t][HO][WO] fp32, 36 B/pixel instead of 128).
+                    // Column slots are [00, 01, 11, 10]: this warp takes output row parity `half`, both columns.
+                    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * 9 * HO * WO;
+                    const int py = half;
+                    const int slot_l = py == 0 ? 0 : 3, slot_r = py == 0 ? 1 : 2;   // px = 0, px = 1
+                    float dl[9], dr[9];
+                    {
                         uint32_t r[32];
-                        tmem_ld32(tbase + slot * C::NPH + c0, r);
-                        if (C::NPH == 32) {
-                            // last tensor-core layer: fp32 NHWC [row][HO][WO][32] for the pixel-term kernel
-                            float* out = reinterpret_cast<float*>(p.out) + (((size_t)row * HO + oy) * WO + ox) * 32;
+                        tmem_ld32(tbase + slot_l * 32, r);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float4 v;
-                                v.x = fmaxf(__uint_as_float(r[q * 4 + 0]) + sbias[q * 4 + 0], 0.0f);
-                                v.y = fmaxf(__uint_as_float(r[q * 4 + 1]) + sbias[q * 4 + 1], 0.0f);
-                                v.z = fmaxf(__uint_as_float(r[q * 4 + 2]) + sbias[q * 4 + 2], 0.0f);
-                                v.w = fmaxf(__uint_as_float(r[q * 4 + 3]) + sbias[q * 4 + 3], 0.0f);
-                                *reinterpret_cast<float4*>(out + q * 4) = v;
-                            }
-                        } else {
-                            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-                            const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
+                        for (int t9 = 0; t9 < 9; ++t9) dl[t9] = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float v = fmaxf(__uint_as_float(r[c]) + sbias[c], 0.0f);
+#pragma unroll
+                            for (int t9 = 0; t9 < 9; ++t9) dl[t9] = fmaf(v, p.w4[c * 9 + t9], dl[t9]);
+                        }
+                    }
+                    {
+                        uint32_t r[32];
+                        tmem_ld32(tbase + slot_r * 32, r);
+#pragma unroll
+                        for (int t9 = 0; t9 < 9; ++t9) dr[t9] = 0.0f;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float v = fmaxf(__uint_as_float(r[c]) + sbias[c], 0.0f);
+#pragma unroll
+                            for (int t9 = 0; t9 < 9; ++t9) dr[t9] = fmaf(v, p.w4[c * 9 + t9], dr[t9]);
+                        }
+                    }
+                    const size_t o = (size_t)(2 * y + py) * WO + 2 * x;
+#pragma unroll
+                    for (int t9 = 0; t9 < 9; ++t9)
+                        *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                } else {
+#pragma unroll
+                    for (int slot = 0; slot < 4; ++slot) {
+                        // streamed layers: TMEM column block `slot` holds phase (py,px) = (slot >> 1, slot & 1)
+                        const int oy = 2 * y + (slot >> 1), ox = 2 * x + (slot & 1);
+                        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                        const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
+#pragma unroll
+                        for (int c0 = 0; c0 < C::NPH; c0 += 32) {
+                            uint32_t r[32];
+                            tmem_ld32(tbase + slot * C::NPH + c0, r);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 uint32_t hi[4], lo[4];
@@ -400,7 +428,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_conv(const __grid_constant__ CUte
 
 using CfgCt1 = Cfg<0, 64, 16, 16, false, 3>;
 using CfgCt2 = Cfg<1, 64, 16, 16, false, 3>;
-using CfgCt3 = Cfg<1, 32, 32, 32, true, 3>;
+using CfgCt3 = Cfg<1, 32, 32, 32, true, 3, 8>;
 
 // ---------------------------------------------------------------------------------------
 // host: weight packing, tensor maps, launches
@@ -413,6 +441,7 @@ struct LayerPack {
 
 struct TcImpl {
     LayerPack ct1, ct2, ct3;
+    float w4[288];               // po_net.19.weight as [c][tap]
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool attrs_set = false;
 };
@@ -522,19 +551,20 @@ int make_map(TcImpl* im, const void* base, int rows, int H, int W, int HX, int H
 
 template <class C>
 int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precision, const void* in, void* out, int nrows,
-                cudaStream_t st, std::string* err) {
+                cudaStream_t st, std::string* err, const float* w4 = nullptr) {
     CUtensorMap map;
     if (make_map(im, in, nrows, C::HIN, C::WIN, C::HX, C::HY, &map, err) != 0) return -1;
     ConvParams p{};
     for (int i = 0; i < lp.nunits; ++i) p.units[i] = lp.units[i];
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     p.wpack = lp.wpack; p.bias = bias; p.out = out;
+    if (w4) memcpy(p.w4, w4, sizeof(p.w4));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = nrows * C::TILES;
     const int grid = ntiles < sms ? ntiles : sms;
-    k_tc_conv<C><<<grid, 256, C::SMEM_BYTES, st>>>(map, p);
+    k_tc_conv<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return 1;
 }
 
@@ -598,6 +628,9 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
     if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, &im->ct1, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, false, &im->ct2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, &im->ct3, allocs, err) != 0) return -1;
+    const std::vector<float>& w19 = raw.at("po_net.19.weight");     // (Cin 32, Cout 1, 3, 3)
+    for (int c = 0; c < 32; ++c)
+        for (int t = 0; t < 9; ++t) im->w4[c * 9 + t] = w19[(size_t)c * 9 + t];
     return 0;
 }
 
@@ -613,7 +646,7 @@ int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer,
     switch (layer) {
         case 1: return launch_conv<CfgCt1>(im, im->ct1, w.ct1_b, precision, in, out, nrows, st, err);
         case 2: return launch_conv<CfgCt2>(im, im->ct2, w.ct2_b, precision, in, out, nrows, st, err);
-        case 3: return launch_conv<CfgCt3>(im, im->ct3, w.ct3_b, precision, in, out, nrows, st, err);
+        case 3: return launch_conv<CfgCt3>(im, im->ct3, w.ct3_b, precision, in, out, nrows, st, err, im->w4);
     }
     *err = "unknown tensor-core layer";
     return -1;
@@ -631,8 +664,8 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
     if ((rc = tc_layer(tw, w, precision, 3, act2, act3, nrows, st, err)) < 0) return -1;
     n += rc;
     Ct4Args c4 = c4in;
-    c4.act3 = static_cast<const float*>(act3);
-    n += launch_ct4_efe(w, c4, st);
+    c4.act3 = static_cast<const float*>(act3);     // projected planes [row][9][64][64]
+    n += launch_ct4_gather(w, c4, st);
     return n;
 }
 
