@@ -280,16 +280,19 @@ int commit(dai_handle* h) {
 int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float* img, float* hsum, float* reward) {
     const int rows = fc.map.rows();
     if (rows <= 0) return DAI_OK;
-    RET(reserve(h, h->h3, (size_t)rows * 256 * sizeof(float)));
-    const int ch = std::min(rows, kDecChunk);
     const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
+    const size_t rows_pad = ((size_t)rows + 127) / 128 * 128 + 128;      // the tensor-core FC4 reads whole 128-row tiles
+    RET(reserve(h, h->h3, tc ? rows_pad * 256 * 2 * sizeof(unsigned short) : (size_t)rows * 256 * sizeof(float)));
+    const int ch = std::min(rows, kDecChunk);
     const size_t esz = sizeof(float);   // fp32 planes, or bf16 hi+lo planes: 4 bytes per element either way
     RET(reserve(h, h->mask, (size_t)ch * 512 * sizeof(uint32_t)));
     RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act1, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act2, (size_t)ch * 65536 * esz));
     RET(reserve(h, h->act3, (size_t)ch * 131072 * esz));
-    fc.h3 = ptr<float>(h->h3);
+    fc.h3 = tc ? nullptr : ptr<float>(h->h3);
+    fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
+    fc.rows_pad = rows_pad;
     h->launches += launch_po_fc123(h->w, fc, st);
     for (int r0 = 0; r0 < rows; r0 += ch) {
         const int n = std::min(ch, rows - r0);
@@ -298,7 +301,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
             h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), st);
             mask = ptr<uint32_t>(h->mask);
         }
-        const float* h3c = fc.h3 + (size_t)r0 * 256;
+        const float* h3c = tc ? nullptr : fc.h3 + (size_t)r0 * 256;
         Ct4Args c4{};
         c4.row0 = r0; c4.nrows = n; c4.img_rows = img_rows; c4.img = img; c4.hsum = hsum; c4.reward = reward;
         if (!tc) {
@@ -310,8 +313,8 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
             h->launches += launch_ct4_efe(h->w, c4, st);
         } else {
             std::string terr;
-            const int nl = tc_decoder_chunk(h->tcw, h->w, h->cfg.precision, h3c, mask, n, h->act0.p, h->act1.p,
-                                            h->act2.p, h->act3.p, c4, st, &terr);
+            const int nl = tc_decoder_chunk(h->tcw, h->w, h->cfg.precision, fc.h3b, rows_pad, r0, mask, n, h->act0.p,
+                                            h->act1.p, h->act2.p, h->act3.p, c4, st, &terr);
             if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core decoder: %s", terr.c_str());
             h->launches += nl;
         }

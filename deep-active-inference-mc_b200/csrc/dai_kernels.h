@@ -48,7 +48,9 @@ struct PoFcArgs {
     int32_t zbcast[3];     // 1: z is [B][10] shared by all slots
     const float *rp_mean, *rp_logvar;   // [B][10]
     int32_t rp_site;
-    float* h3;             // [rows][256]
+    float* h3;             // [rows][256] fp32 (CUDA-core FC4), or null
+    unsigned short* h3b;   // [plane hi|lo][kc 32][rows_pad][8] bf16 (tensor-core FC4), or null
+    size_t rows_pad;
     NoiseKey nk;
 };
 int  launch_po_fc123(const DevWeights& w, const PoFcArgs& a, cudaStream_t st);

@@ -203,7 +203,16 @@ __global__ void __launch_bounds__(PO_NT) k_po_fc123(DevWeights w, PoFcArgs a) {
     __syncthreads();
     for (int i = tid; i < PO_TM * 256; i += PO_NT) {
         const int r = i >> 8, n = i & 255;
-        if (r0 + r < rows) a.h3[(size_t)(r0 + r) * 256 + n] = hA[r][n];
+        if (r0 + r >= rows) continue;
+        if (a.h3) a.h3[(size_t)(r0 + r) * 256 + n] = hA[r][n];
+        if (a.h3b) {     // K-blocked bf16 hi/lo operand planes for the tensor-core FC4
+            const float v = hA[r][n];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const size_t o = ((size_t)(n >> 3) * a.rows_pad + (r0 + r)) * 8 + (n & 7);
+            a.h3b[o] = __bfloat16_as_ushort(hi);
+            a.h3b[(size_t)32 * a.rows_pad * 8 + o] = __bfloat16_as_ushort(lo);
+        }
     }
 }
 

@@ -426,6 +426,163 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------
+// FC4 (256 -> 16384, the decoder's widest layer) as a tcgen05 GEMM: tile 128 rows x 256 columns,
+// K = 256 in 4 chunks of 64.  A = h3 in K-blocked bf16 hi/lo [plane][kc 32][rows_pad][8] (written by
+// k_po_fc123), B = weights pre-packed per (n-tile, k-chunk) in the UMMA no-swizzle layout; both
+// arrive by plain bulk copies (UBLKCP).  Epilogue: bias + ReLU + MC-dropout bit + hi/lo split ->
+// channel-blocked activation planes for ct1.
+// ---------------------------------------------------------------------------------------
+struct Fc4Params {
+    const __nv_bfloat16* a;      // h3 blocked, already offset to the chunk's first row
+    size_t a_kc_stride;          // elements between kc planes  (rows_pad * 8)
+    size_t a_plane;              // elements between hi and lo  (32 * rows_pad * 8)
+    const uint8_t* wpack;        // [n_tile 64][k_chunk 4] blocks of FC4_B_BYTES
+    const float* bias;           // [16384] NHWC-permuted
+    const uint32_t* mask;        // [nrows][512] dropout bits in NHWC order, or null (eval mode)
+    __nv_bfloat16* out;          // blocked [plane][nrows][kc 8][256 px][8]
+    int32_t nrows, nprod;
+};
+
+constexpr int FC4_NS = 2;                          // pipeline stages
+constexpr int FC4_A_BYTES = 2 * 8 * 128 * 16;      // 32 KB: hi+lo, 8 kc, 128 rows
+constexpr int FC4_B_BYTES = 2 * 8 * 256 * 16;      // 64 KB: hi+lo, 8 kc, 256 columns
+constexpr int FC4_STAGE = FC4_A_BYTES + FC4_B_BYTES;
+constexpr int FC4_SMEM = FC4_NS * FC4_STAGE + 2048;
+constexpr int FC4_THREADS = 128 + 256;             // 8 epilogue warps
+
+__global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FC4_NS * FC4_STAGE);
+    uint64_t* full = bars;                 // [NS]
+    uint64_t* empty = full + FC4_NS;       // [NS]
+    uint64_t* acc_full = empty + FC4_NS;   // [2]
+    uint64_t* acc_empty = acc_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 2);      // [256] of the current n-tile (per accumulator buffer: [2][256])
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < FC4_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int mtiles = (p.nrows + 127) / 128;
+    const int ntiles = mtiles * 64;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int cnt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int nt = tile / mtiles, mt = tile % mtiles;
+                for (int kch = 0; kch < 4; ++kch, ++cnt) {
+                    const int s = cnt % FC4_NS;
+                    const uint32_t ph = (uint32_t)(cnt / FC4_NS) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t* sa = smem + (size_t)s * FC4_STAGE;
+                    uint8_t* sb = sa + FC4_A_BYTES;
+                    mbar_expect_tx(&full[s], FC4_STAGE);
+                    for (int pl = 0; pl < 2; ++pl)
+                        for (int kc = 0; kc < 8; ++kc)
+                            bulk_load(sa + (pl * 8 + kc) * 2048,
+                                      p.a + pl * p.a_plane + (size_t)(kch * 8 + kc) * p.a_kc_stride + (size_t)mt * 128 * 8, 2048, &full[s]);
+                    const uint8_t* wsrc = p.wpack + ((size_t)nt * 4 + kch) * FC4_B_BYTES;
+                    for (int off = 0; off < FC4_B_BYTES; off += 8192) bulk_load(sb + off, wsrc + off, 8192, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(256);
+            int it = 0, cnt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&acc_empty[buf], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(buf * 256);
+                for (int kch = 0; kch < 4; ++kch, ++cnt) {
+                    const int s = cnt % FC4_NS;
+                    const uint32_t ph = (uint32_t)(cnt / FC4_NS) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + (size_t)s * FC4_STAGE);
+                    const uint32_t b_base = a_base + FC4_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a_hi = umma_desc(a_base + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                        const uint64_t a_lo = umma_desc(a_base + 16384u + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                        const uint64_t b_hi = umma_desc(b_base + (uint32_t)(2 * k) * 4096u, 4096, 128);
+                        const uint64_t b_lo = umma_desc(b_base + 32768u + (uint32_t)(2 * k) * 4096u, 4096, 128);
+                        umma_bf16(d, a_hi, b_hi, idesc, (kch == 0 && k == 0) ? 0u : 1u);
+                        if (p.nprod == 3) {
+                            umma_bf16(d, a_lo, b_hi, idesc, 1u);
+                            umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3, half = (warp - 4) >> 2;       // lane quarter; column half of the tile
+        const int m = ew * 32 + lane;
+        const size_t plane = (size_t)p.nrows * 16384;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            const int nt = tile / mtiles, mt = tile % mtiles;
+            const int row = mt * 128 + m;
+            mbar_wait(&acc_full[buf], aph);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tbase + c0, r);
+                if (row < p.nrows) {
+                    const int n0 = nt * 256 + half * 128 + c0;           // NHWC column = px * 64 + c
+                    const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
+                    const float sc = p.mask ? 2.0f : 1.0f;
+                    const int px = n0 >> 6, kc0 = (n0 & 63) >> 3;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j0 = q * 8 + 2 * e, j1 = j0 + 1;
+                            float v0 = fmaxf(__uint_as_float(r[j0]) + __ldg(p.bias + n0 + j0), 0.0f);
+                            float v1 = fmaxf(__uint_as_float(r[j1]) + __ldg(p.bias + n0 + j1), 0.0f);
+                            v0 = ((mw >> j0) & 1u) ? v0 * sc : 0.0f;
+                            v1 = ((mw >> j1) & 1u) ? v1 * sc : 0.0f;
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(v0, h0, l0);
+                            split_bf16(v1, h1, l1);
+                            hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
+                        }
+                        const size_t o = (((size_t)row * 8 + kc0 + q) * 256 + px) * 8;
+                        *reinterpret_cast<uint4*>(p.out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(p.out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 using CfgCt1 = Cfg<0, 64, 16, 16, false, 3>;
 using CfgCt2 = Cfg<1, 64, 16, 16, false, 3>;
 using CfgCt3 = Cfg<1, 32, 32, 32, true, 3, 8>;
@@ -442,6 +599,7 @@ struct LayerPack {
 struct TcImpl {
     LayerPack ct1, ct2, ct3;
     float w4[288];               // po_net.19.weight as [c][tap]
+    uint8_t* fc4_wpack = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool attrs_set = false;
 };
@@ -619,7 +777,8 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
     if (!im->attrs_set) {
         if (cudaFuncSetAttribute(k_tc_conv<CfgCt1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt1::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgCt2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt2::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess) {
+            cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_fc4, cudaFuncAttributeMaxDynamicSharedMemorySize, FC4_SMEM) != cudaSuccess) {
             *err = std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(cudaGetLastError());
             return -1;
         }
@@ -628,6 +787,29 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
     if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, &im->ct1, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, false, &im->ct2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, &im->ct3, allocs, err) != 0) return -1;
+    {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
+        // of [plane][kc 8][256 n][8]
+        const std::vector<float>& W = raw.at("po_net.9.weight");
+        std::vector<uint16_t> host((size_t)16384 * 256 * 2);
+        for (int n = 0; n < 16384; ++n) {
+            const int px = n >> 6, c = n & 63, e = c * 256 + px;
+            const int nt = n >> 8, nl = n & 255;
+            for (int k = 0; k < 256; ++k) {
+                const float v = W[(size_t)e * 256 + k];
+                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                const int kch = k >> 6, kc = (k >> 3) & 7, ke = k & 7;
+                const size_t blk = ((size_t)nt * 4 + kch) * (FC4_B_BYTES / 2);
+                const size_t o = blk + ((size_t)kc * 256 + nl) * 8 + ke;
+                host[o] = hi;
+                host[o + (size_t)8 * 256 * 8] = lo;
+            }
+        }
+        void* d = nullptr;
+        if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(fc4 weights)"; return -1; }
+        allocs->push_back(d);
+        if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(fc4 weights)"; return -1; }
+        im->fc4_wpack = static_cast<uint8_t*>(d);
+    }
     const std::vector<float>& w19 = raw.at("po_net.19.weight");     // (Cin 32, Cout 1, 3, 3)
     for (int c = 0; c < 32; ++c)
         for (int t = 0; t < 9; ++t) im->w4[c * 9 + t] = w19[(size_t)c * 9 + t];
@@ -652,11 +834,29 @@ int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer,
     return -1;
 }
 
-int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const float* h3, const uint32_t* mask,
-                     int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4in, cudaStream_t st,
-                     std::string* err) {
+int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* h3b, size_t rows_pad, int row0,
+           const uint32_t* mask, int nrows, void* act0, cudaStream_t st, std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(tw.impl);
+    if (!im) { *err = "tensor-core weights not packed"; return -1; }
+    Fc4Params p{};
+    p.a = static_cast<const __nv_bfloat16*>(h3b) + (size_t)row0 * 8;
+    p.a_kc_stride = rows_pad * 8; p.a_plane = 32 * rows_pad * 8;
+    p.wpack = im->fc4_wpack; p.bias = w.po_b3; p.mask = mask; p.out = static_cast<__nv_bfloat16*>(act0);
+    p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = ((nrows + 127) / 128) * 64;
+    k_tc_fc4<<<ntiles < sms ? ntiles : sms, FC4_THREADS, FC4_SMEM, st>>>(p);
+    return 1;
+}
+
+int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const void* h3b, size_t rows_pad, int row0,
+                     const uint32_t* mask, int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4in,
+                     cudaStream_t st, std::string* err) {
     int n = 0, rc;
-    n += launch_fc4_simt_blocked(w, h3, mask, nrows, act0, st);
+    if ((rc = tc_fc4(tw, w, precision, h3b, rows_pad, row0, mask, nrows, act0, st, err)) < 0) return -1;
+    n += rc;
     if ((rc = tc_layer(tw, w, precision, 1, act0, act1, nrows, st, err)) < 0) return -1;
     n += rc;
     if ((rc = tc_layer(tw, w, precision, 2, act1, act2, nrows, st, err)) < 0) return -1;
