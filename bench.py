@@ -107,6 +107,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--shard", default="samples", choices=["samples", "roots"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,10 +207,10 @@ def main():
     eng.stats(reset=True)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, args.steps, max(3, args.warmup))
+    ms_dev = timed(step_device, args.steps, 1 if args.quick else max(3, args.warmup))
     launches = eng.stats()["kernel_launches"]
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, 1)
+    ms_e2e = ms_dev if args.quick else timed(step_e2e, args.steps, 1)
     value = total_roots / (ms_dev * 1e-3)
     e2e = total_roots / (ms_e2e * 1e-3)
 
@@ -237,10 +238,31 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    # roofline of the dominant kernel (ct3 implicit GEMM), per-launch CUDA-event timing in a separate profiled pass
-    line["roofline"] = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None,
-                        "traffic": None, "peak_source": peak_src, "kernel": "ct3 (ConvT 64->32, 32x32->64x64)"}
-    if not args.no_cpu_baseline and world == 1:
+    # roofline of the dominant kernel (ct3: ConvT 64->32 as tcgen05 implicit GEMM): every launch of the same
+    # steps bracketed by CUDA events on the launch stream, in a separate pass so the events do not perturb `value`
+    layers = {}
+    if args.precision != "fp32_simt":
+        eng.profile_begin()
+        for _ in range(min(args.steps, 3)):
+            step_device()
+        layers = eng.profile_end()
+    roof = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None,
+            "peak_source": peak_src, "kernel": "k_tc_conv<ct3> (ConvT 64->32, 32x32->64x64, + last-deconv projection)"}
+    if layers and layers["ct3"][1] > 0:
+        ms3, n3, rows3 = layers["ct3"]
+        alg = 2.0 * MAC_CT3 * rows3 / (ms3 * 1e-3) / 1e12           # algorithmic flops of ct3: 18,874,368 MAC per decoder row
+        issued = alg * (3 if args.precision == "bf16x3" else 1)     # bf16x3 issues 3 MMAs per algorithmic MAC
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ct3_dram_traffic.json")))["bytes_per_launch"]
+        except Exception:
+            pass
+        roof.update({"achieved": alg, "frac": alg / peak_tf, "issued_mma_tflops": issued, "issued_frac": issued / peak_tf,
+                     "avg_launch_ms": ms3 / n3, "launches_timed": int(n3), "rows_per_launch": rows3 / n3,
+                     "traffic": traffic,
+                     "step_share_ms": {k: v[0] / min(args.steps, 3) for k, v in layers.items()}})
+    line["roofline"] = roof
+    if not args.no_cpu_baseline and not args.quick and world == 1:
         cv, per_call, cores = cpu_reference_run(N, T, 3, 1)
         line["cpu_baseline"] = {"value": cv, "unit": "rollouts/s", "cores": cores, "kind": "port",
                                 "sample": "calculate_G_4_repeated(steps=1, samples=%d), 1 root, 3 timed calls "

@@ -76,6 +76,7 @@ struct dai_handle {
     // workspaces (grow-only)
     DevBuf ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
         pi_eye, traj, root, stage_in, stage_out, scratch;
+    LayerTimer timer;
     float* pinned = nullptr;   // small host result buffer
     size_t pinned_cap = 0;
 };
@@ -314,7 +315,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
         } else {
             std::string terr;
             const int nl = tc_decoder_chunk(h->tcw, h->w, h->cfg.precision, fc.h3b, rows_pad, r0, mask, n, h->act0.p,
-                                            h->act1.p, h->act2.p, h->act3.p, c4, st, &terr);
+                                            h->act1.p, h->act2.p, h->act3.p, c4, st, &terr, &h->timer);
             if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core decoder: %s", terr.c_str());
             h->launches += nl;
         }
@@ -799,6 +800,32 @@ int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use
     CK(cudaMemcpyAsync(h->pinned, h->scratch.p, sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *G_host = h->pinned[0];
+    return DAI_OK;
+}
+
+int dai_profile_begin(dai_handle* h) {
+    if (!h) return DAI_E_INVALID;
+    for (auto& r : h->timer.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    h->timer.recs.clear();
+    h->timer.on = true;
+    return DAI_OK;
+}
+
+int dai_profile_end(dai_handle* h, float ms[5], int64_t launches[5], int64_t rows[5], void* stream) {
+    if (!h || !ms || !launches || !rows) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    h->timer.on = false;
+    for (int i = 0; i < 5; ++i) { ms[i] = 0.0f; launches[i] = 0; rows[i] = 0; }
+    for (auto& r : h->timer.recs) {
+        float t = 0.0f;
+        if (r.b && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.layer >= 0 && r.layer < 5) {
+            ms[r.layer] += t; launches[r.layer] += 1; rows[r.layer] += r.rows;
+        }
+        cudaEventDestroy(r.a);
+        if (r.b) cudaEventDestroy(r.b);
+    }
+    h->timer.recs.clear();
     return DAI_OK;
 }
 

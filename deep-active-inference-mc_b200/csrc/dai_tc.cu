@@ -142,7 +142,7 @@ struct Unit {            // one MMA group of a tile: a tap shift of the halo x a
     int16_t col;         // TMEM column offset inside the tile's accumulator block
     int16_t n;           // N of the MMA
     int16_t init;        // 1: its first MMA overwrites the accumulator
-    int32_t woff;        // byte offset of its weight block (resident layout) / index * slot (streamed)
+    int32_t woff;        // byte offset of its weight block in the resident weight image
 };
 
 constexpr int MAX_UNITS = 9;
@@ -158,58 +158,76 @@ struct ConvParams {
     float w4[288];           // ct3 only: last deconv's weights [c 32][tap 9] (kernel params = constant bank)
 };
 
-template <int MODE_, int NPH_, int HIN_, int WIN_, bool WRES_, int NA_, int EPI_WARPS_ = 4>
+template <int MODE_, int NPH_, int HIN_, int WIN_, int NA_, bool TWO_PASS_>
 struct Cfg {
-    static constexpr int EPI_WARPS = EPI_WARPS_;            // 4, or 8 (two warps per TMEM lane quarter)
-    static constexpr int THREADS = 128 + 32 * EPI_WARPS_;
+    // TWO_PASS: per tile, all MMAs on the hi plane of the halo first, then all on the lo plane (the planes can
+    // then share a 3-slot ring); otherwise both planes are waited for and the three products of one (tap, k)
+    // step are issued back to back.
+    static constexpr bool TWO_PASS = TWO_PASS_;
     static constexpr int MODE = MODE_;       // 0: convT k3 s1 p1; 1: convT k3 s2 p1 op1 (4 sub-pixel phases)
     static constexpr int NPH = NPH_;         // Cout
     static constexpr int HIN = HIN_, WIN = WIN_;
-    static constexpr bool WRES = WRES_;      // weights resident in shared memory
-    static constexpr int NA = NA_;           // A (halo) stages
+    static constexpr int NA = NA_;           // halo ring slots; one slot = one bf16 plane (hi or lo) of one tile
+    static constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int TH = 16, TW = 8;    // tile of the m-grid: 128 pixels
     static constexpr int HY = MODE == 0 ? TH + 2 : TH + 1;
     static constexpr int HX = MODE == 0 ? TW + 2 : TW + 1;
     static constexpr int KC_STRIDE = HY * HX * 16;             // bytes of one 8-channel plane of the halo
-    static constexpr int PLANE_A = 8 * KC_STRIDE;              // one bf16 plane (64 channels)
-    static constexpr int A_BYTES = 2 * PLANE_A;
+    static constexpr int PLANE_A = 8 * KC_STRIDE;              // one bf16 plane (64 channels) = one ring slot
     static constexpr int TILES_X = WIN / TW, TILES_Y = HIN / TH;
     static constexpr int TILES = TILES_X * TILES_Y;
     static constexpr int ACC_COLS = MODE == 0 ? NPH : 4 * NPH;
     static constexpr int NACC = 2;
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
-    static constexpr int W_BYTES = 9 * NPH * 256;              // all taps, hi + lo
-    static constexpr int NB = 4;                               // weight ring slots (streamed)
-    static constexpr int B_SLOT = NPH * 256;                   // one (tap) block, hi + lo
-    static constexpr int SMEM_W = WRES ? W_BYTES : NB * B_SLOT;
-    static constexpr int SMEM_A = NA * A_BYTES;
-    static constexpr int SMEM_BYTES = SMEM_W + SMEM_A + 1024;  // + barriers, tmem slot, bias
+    static constexpr int W_BYTES = 9 * NPH * 256;              // all 9 taps, hi + lo, resident
+    static constexpr int SMEM_A = NA * PLANE_A;
+    static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + 1024; // + barriers, tmem slot, bias
 };
+
+// relu(acc + bias) for two neighbouring channels -> packed bf16 hi pair and lo pair (x = hi + lo)
+__device__ __forceinline__ void split2(uint32_t r0, uint32_t r1, float b0, float b1, float scale0, float scale1,
+                                       uint32_t& hi, uint32_t& lo) {
+    const float v0 = fmaxf(__uint_as_float(r0) + b0, 0.0f) * scale0;
+    const float v1 = fmaxf(__uint_as_float(r1) + b1, 0.0f) * scale1;
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float f0 = __uint_as_float(hi << 16), f1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - f0, v1 - f1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+                 "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+                 : "memory");
+}
 
 // ---------------------------------------------------------------------------------------
 // the kernel: warp 0 = halo TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = weight producer, warps 4..7 = epilogue (TMEM -> registers -> HBM)
+// warp 3 = weight loader (once), warps 4..11 = epilogue (TMEM -> registers -> HBM).
+// Per tile the issuer makes two passes over the tap units: pass 1 on the hi plane of the halo
+// (A_hi*B_hi, A_hi*B_lo), pass 2 on the lo plane (A_lo*B_hi); the planes travel through the ring
+// separately so three 20 KB slots are enough to keep the next tile's data in flight.
 // ---------------------------------------------------------------------------------------
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant__ CUtensorMap tmapA, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smW = smem;
-    uint8_t* smA = smem + C::SMEM_W;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SMEM_W + C::SMEM_A);
+    uint8_t* smA = smem + C::W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::W_BYTES + C::SMEM_A);
     uint64_t* a_full = bars;                  // [NA]
     uint64_t* a_empty = a_full + C::NA;       // [NA]
-    uint64_t* b_full = a_empty + C::NA;       // [NB]
-    uint64_t* b_empty = b_full + C::NB;       // [NB]
-    uint64_t* acc_full = b_empty + C::NB;     // [NACC]
+    uint64_t* acc_full = a_empty + C::NA;     // [NACC]
     uint64_t* acc_empty = acc_full + C::NACC; // [NACC]
     uint64_t* w_full = acc_empty + C::NACC;   // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [NPH]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nplanes = p.nprod == 3 ? 2 : 1;
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < C::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], C::EPI_WARPS); }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -223,94 +241,114 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     const int ntiles = p.nrows * C::TILES;
 
     if (warp == 0) {
-        // ===== halo producer =====
+        // ===== halo producer: one TMA box per (tile, plane) =====
         if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int s = it % C::NA;
-                const uint32_t ph = (uint32_t)(it / C::NA) & 1u;
-                mbar_wait(&a_empty[s], ph ^ 1u);
+            int cnt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row = tile / C::TILES, t = tile % C::TILES;
                 const int y0 = (t / C::TILES_X) * C::TH, x0 = (t % C::TILES_X) * C::TW;
                 const int hy0 = C::MODE == 0 ? y0 - 1 : y0, hx0 = C::MODE == 0 ? x0 - 1 : x0;
-                mbar_expect_tx(&a_full[s], C::A_BYTES);
-                tma_load_5d(smA + (size_t)s * C::A_BYTES, &tmapA, &a_full[s], hx0 * 8, hy0, 0, row, 0);
+                for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
+                    const int s = cnt % C::NA;
+                    const uint32_t ph = (uint32_t)(cnt / C::NA) & 1u;
+                    mbar_wait(&a_empty[s], ph ^ 1u);
+                    mbar_expect_tx(&a_full[s], C::PLANE_A);
+                    tma_load_5d(smA + (size_t)s * C::PLANE_A, &tmapA, &a_full[s], hx0 * 8, hy0, 0, row, pl);
+                }
             }
         }
     } else if (warp == 3) {
-        // ===== weight producer =====
+        // ===== weights: all taps, once =====
         if (lane == 0) {
-            if (C::WRES) {
-                mbar_expect_tx(w_full, C::W_BYTES);
-                for (int off = 0; off < C::W_BYTES; off += 8192)
-                    bulk_load(smW + off, p.wpack + off, 8192, w_full);
-            } else {
-                int cnt = 0;
-                for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                    for (int u = 0; u < p.nunits; ++u, ++cnt) {
-                        const int s = cnt % C::NB;
-                        const uint32_t ph = (uint32_t)(cnt / C::NB) & 1u;
-                        mbar_wait(&b_empty[s], ph ^ 1u);
-                        mbar_expect_tx(&b_full[s], C::B_SLOT);
-                        bulk_load(smW + (size_t)s * C::B_SLOT, p.wpack + p.units[u].woff, C::B_SLOT, &b_full[s]);
-                    }
-                }
-            }
+            mbar_expect_tx(w_full, C::W_BYTES);
+            for (int off = 0; off < C::W_BYTES; off += 8192) bulk_load(smW + off, p.wpack + off, 8192, w_full);
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            if (C::WRES) { mbar_wait(w_full, 0); tc_fence_after(); }
+            mbar_wait(w_full, 0);
+            tc_fence_after();
             int it = 0, cnt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it % C::NACC;
                 const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
                 mbar_wait(&acc_empty[buf], aph ^ 1u);
-                const int s = it % C::NA;
-                const uint32_t ph = (uint32_t)(it / C::NA) & 1u;
-                mbar_wait(&a_full[s], ph);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smA + (size_t)s * C::A_BYTES);
-                for (int u = 0; u < p.nunits; ++u, ++cnt) {
-                    const Unit un = p.units[u];
-                    uint32_t w_base;
-                    int bs = 0;
-                    if (C::WRES) {
-                        w_base = smem_u32(smW + un.woff);
-                    } else {
-                        bs = cnt % C::NB;
-                        const uint32_t bph = (uint32_t)(cnt / C::NB) & 1u;
-                        mbar_wait(&b_full[bs], bph);
+                if (C::TWO_PASS) {
+                    for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
+                        const int s = cnt % C::NA;
+                        const uint32_t ph = (uint32_t)(cnt / C::NA) & 1u;
+                        mbar_wait(&a_full[s], ph);
                         tc_fence_after();
-                        w_base = smem_u32(smW + (size_t)bs * C::B_SLOT);
-                    }
-                    const uint32_t n = (uint32_t)un.n;
-                    const uint32_t idesc = umma_idesc(un.n);
-                    const uint32_t b_plane = 8u * n * 16u;            // one bf16 plane of this block
-                    const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
-                    const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
+                        const uint32_t a_base = smem_u32(smA + (size_t)s * C::PLANE_A);
+                        for (int u = 0; u < p.nunits; ++u) {
+                            const Unit un = p.units[u];
+                            const uint32_t n = (uint32_t)un.n;
+                            const uint32_t idesc = umma_idesc(un.n);
+                            const uint32_t w_base = smem_u32(smW + un.woff);
+                            const uint32_t b_plane = 8u * n * 16u;            // hi -> lo plane of this weight block
+                            const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+                            const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t a_hi = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                        const uint64_t a_lo = umma_desc(a_base + C::PLANE_A + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                        const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                        const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                        umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
-                        if (p.nprod == 3) {
-                            umma_bf16(d, a_lo, b_hi, idesc, 1u);
-                            umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_d = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                if (pl == 0) {
+                                    umma_bf16(d, a_d, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);      // A_hi * B_hi
+                                    if (nplanes == 2) {
+                                        const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                        umma_bf16(d, a_d, b_lo, idesc, 1u);                             // A_hi * B_lo
+                                    }
+                                } else {
+                                    umma_bf16(d, a_d, b_hi, idesc, 1u);                                 // A_lo * B_hi
+                                }
+                            }
+                        }
+                        umma_commit(&a_empty[s]);
+                    }
+                } else {
+                    const int s0 = cnt % C::NA;
+                    mbar_wait(&a_full[s0], (uint32_t)(cnt / C::NA) & 1u);
+                    ++cnt;
+                    int s1 = s0;
+                    if (nplanes == 2) {
+                        s1 = cnt % C::NA;
+                        mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
+                        ++cnt;
+                    }
+                    tc_fence_after();
+                    const uint32_t a_hi_base = smem_u32(smA + (size_t)s0 * C::PLANE_A);
+                    const uint32_t a_lo_base = smem_u32(smA + (size_t)s1 * C::PLANE_A);
+                    for (int u = 0; u < p.nunits; ++u) {
+                        const Unit un = p.units[u];
+                        const uint32_t n = (uint32_t)un.n;
+                        const uint32_t idesc = umma_idesc(un.n);
+                        const uint32_t w_base = smem_u32(smW + un.woff);
+                        const uint32_t b_plane = 8u * n * 16u;
+                        const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+                        const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_hi = umma_desc(a_hi_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                            const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                            umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
+                            if (nplanes == 2) {
+                                const uint64_t a_lo = umma_desc(a_lo_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                                const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                umma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                            }
                         }
                     }
-                    if (!C::WRES) umma_commit(&b_empty[bs]);
+                    umma_commit(&a_empty[s0]);
+                    if (nplanes == 2) umma_commit(&a_empty[s1]);
                 }
-                umma_commit(&a_empty[s]);
                 umma_commit(&acc_full[buf]);
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: lane = pixel of the tile =====
+        // ===== epilogue: lane = pixel of the tile; `half` = which half of the tile's outputs this warp owns =====
         const int ew = warp & 3;                  // the TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;         // with 8 epilogue warps: which output row parity this warp owns
+        const int half = (warp - 4) >> 2;
         const int m = ew * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
         int it = 0;
@@ -323,40 +361,37 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
             if (C::MODE == 0) {
-                // -> blocked bf16 hi/lo [plane][row][kc][H][W][8]
+                // 32 of the 64 output channels -> blocked bf16 hi/lo [plane][row][kc][H][W][8]
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
                 const size_t plane = (size_t)p.nrows * C::NPH * C::HIN * C::WIN;
+                const int c0 = half * 32;
+                uint32_t r[32];
+                tmem_ld32(tbase + c0, r);
 #pragma unroll
-                for (int c0 = 0; c0 < C::NPH; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tbase + c0, r);
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + sbias[c0 + q * 8 + 2 * e], 0.0f), h0, l0);
-                            split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + sbias[c0 + q * 8 + 2 * e + 1], 0.0f), h1, l1);
-                            hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
-                        }
-                        const int kc = (c0 >> 3) + q;
-                        const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * C::HIN + y) * C::WIN + x) * 8;
-                        *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                    for (int e = 0; e < 4; ++e)
+                        split2(r[q * 8 + 2 * e], r[q * 8 + 2 * e + 1], sbias[c0 + q * 8 + 2 * e], sbias[c0 + q * 8 + 2 * e + 1],
+                               1.0f, 1.0f, hi[e], lo[e]);
+                    const int kc = (c0 >> 3) + q;
+                    const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * C::HIN + y) * C::WIN + x) * 8;
+                    *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             } else {
+                // TMEM column slots are [00, 01, 11, 10] (host unit table): this warp takes output row parity
+                // py = half and both column parities, so every store covers two neighbouring output pixels.
                 constexpr int HO = 2 * C::HIN, WO = 2 * C::WIN;
+                const int py = half;
+                const int slot_l = py == 0 ? 0 : 3, slot_r = py == 0 ? 1 : 2;   // px = 0, px = 1
+                const int oy = 2 * y + py, ox = 2 * x;
                 if (C::NPH == 32) {
                     // Last tensor-core layer.  The next layer (ConvT 32->1, k3 s1 p1) is linear in this output,
                     // so its channel contraction is done here, in registers, per output pixel:
                     //   d[t] = sum_c relu(acc[c] + b[c]) * w4[c][t],  t = kh*3+kw
                     // and only the 9 projections leave the SM ([row][t][HO][WO] fp32, 36 B/pixel instead of 128).
-                    // Column slots are [00, 01, 11, 10]: this warp takes output row parity `half`, both columns.
                     float* out = reinterpret_cast<float*>(p.out) + (size_t)row * 9 * HO * WO;
-                    const int py = half;
-                    const int slot_l = py == 0 ? 0 : 3, slot_r = py == 0 ? 1 : 2;   // px = 0, px = 1
                     float dl[9], dr[9];
                     {
                         uint32_t r[32];
@@ -382,36 +417,31 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                             for (int t9 = 0; t9 < 9; ++t9) dr[t9] = fmaf(v, p.w4[c * 9 + t9], dr[t9]);
                         }
                     }
-                    const size_t o = (size_t)(2 * y + py) * WO + 2 * x;
+                    const size_t o = (size_t)oy * WO + ox;
 #pragma unroll
                     for (int t9 = 0; t9 < 9; ++t9)
                         *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
                 } else {
+                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                    const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C::NPH; c0 += 32) {
+                        uint32_t rl[32], rr[32];
+                        tmem_ld32(tbase + slot_l * C::NPH + c0, rl);
+                        tmem_ld32(tbase + slot_r * C::NPH + c0, rr);
 #pragma unroll
-                    for (int slot = 0; slot < 4; ++slot) {
-                        // streamed layers: TMEM column block `slot` holds phase (py,px) = (slot >> 1, slot & 1)
-                        const int oy = 2 * y + (slot >> 1), ox = 2 * x + (slot & 1);
-                        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-                        const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t hl[4], ll[4], hr[4], lr[4];
 #pragma unroll
-                        for (int c0 = 0; c0 < C::NPH; c0 += 32) {
-                            uint32_t r[32];
-                            tmem_ld32(tbase + slot * C::NPH + c0, r);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t hi[4], lo[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    __nv_bfloat16 h0, l0, h1, l1;
-                                    split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e]) + sbias[c0 + q * 8 + 2 * e], 0.0f), h0, l0);
-                                    split_bf16(fmaxf(__uint_as_float(r[q * 8 + 2 * e + 1]) + sbias[c0 + q * 8 + 2 * e + 1], 0.0f), h1, l1);
-                                    hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
-                                }
-                                const int kc = (c0 >> 3) + q;
-                                const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * HO + oy) * WO + ox) * 8;
-                                *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                                *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            for (int e = 0; e < 4; ++e) {
+                                const float b0 = sbias[c0 + q * 8 + 2 * e], b1 = sbias[c0 + q * 8 + 2 * e + 1];
+                                split2(rl[q * 8 + 2 * e], rl[q * 8 + 2 * e + 1], b0, b1, 1.0f, 1.0f, hl[e], ll[e]);
+                                split2(rr[q * 8 + 2 * e], rr[q * 8 + 2 * e + 1], b0, b1, 1.0f, 1.0f, hr[e], lr[e]);
                             }
+                            const int kc = (c0 >> 3) + q;
+                            const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * HO + oy) * WO + ox) * 8;
+                            st_global_256(out + o, hl, hr);               // pixels (oy, 2x) and (oy, 2x+1): 32 B
+                            st_global_256(out + plane + o, ll, lr);
                         }
                     }
                 }
@@ -558,14 +588,8 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int j0 = q * 8 + 2 * e, j1 = j0 + 1;
-                            float v0 = fmaxf(__uint_as_float(r[j0]) + __ldg(p.bias + n0 + j0), 0.0f);
-                            float v1 = fmaxf(__uint_as_float(r[j1]) + __ldg(p.bias + n0 + j1), 0.0f);
-                            v0 = ((mw >> j0) & 1u) ? v0 * sc : 0.0f;
-                            v1 = ((mw >> j1) & 1u) ? v1 * sc : 0.0f;
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(v0, h0, l0);
-                            split_bf16(v1, h1, l1);
-                            hi[e] = pack_bf16(h0, h1); lo[e] = pack_bf16(l0, l1);
+                            split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
+                                   ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[e], lo[e]);
                         }
                         const size_t o = (((size_t)row * 8 + kc0 + q) * 256 + px) * 8;
                         *reinterpret_cast<uint4*>(p.out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -583,9 +607,9 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-using CfgCt1 = Cfg<0, 64, 16, 16, false, 3>;
-using CfgCt2 = Cfg<1, 64, 16, 16, false, 3>;
-using CfgCt3 = Cfg<1, 32, 32, 32, true, 3, 8>;
+using CfgCt1 = Cfg<0, 64, 16, 16, 3, false>;     // 144 KB of weights + 3 x 22.5 KB halo planes
+using CfgCt2 = Cfg<1, 64, 16, 16, 4, false>;     // 144 KB of weights + 4 x 19.1 KB halo planes (2 tiles in flight)
+using CfgCt3 = Cfg<1, 32, 32, 32, 6, false>;     //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
 
 // ---------------------------------------------------------------------------------------
 // host: weight packing, tensor maps, launches
@@ -695,7 +719,7 @@ int make_map(TcImpl* im, const void* base, int rows, int H, int W, int HX, int H
     cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, 8, (cuuint64_t)rows, 2};
     cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)8 * H * W * 16,
                              (cuuint64_t)rows * 8 * H * W * 16};
-    cuuint32_t box[5] = {(cuuint32_t)HX * 8, (cuuint32_t)HY, 8, 1, 2};
+    cuuint32_t box[5] = {(cuuint32_t)HX * 8, (cuuint32_t)HY, 8, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = im->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -785,7 +809,7 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         im->attrs_set = true;
     }
     if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, &im->ct1, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, false, &im->ct2, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, &im->ct2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, &im->ct3, allocs, err) != 0) return -1;
     {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
         // of [plane][kc 8][256 n][8]
@@ -853,19 +877,27 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
 
 int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const void* h3b, size_t rows_pad, int row0,
                      const uint32_t* mask, int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4in,
-                     cudaStream_t st, std::string* err) {
+                     cudaStream_t st, std::string* err, LayerTimer* timer) {
+    LayerTimer none;
+    LayerTimer& T = timer ? *timer : none;
     int n = 0, rc;
+    T.begin(0, nrows, st);
     if ((rc = tc_fc4(tw, w, precision, h3b, rows_pad, row0, mask, nrows, act0, st, err)) < 0) return -1;
+    T.end(st);
     n += rc;
-    if ((rc = tc_layer(tw, w, precision, 1, act0, act1, nrows, st, err)) < 0) return -1;
-    n += rc;
-    if ((rc = tc_layer(tw, w, precision, 2, act1, act2, nrows, st, err)) < 0) return -1;
-    n += rc;
-    if ((rc = tc_layer(tw, w, precision, 3, act2, act3, nrows, st, err)) < 0) return -1;
-    n += rc;
+    const void* in[3] = {act0, act1, act2};
+    void* out[3] = {act1, act2, act3};
+    for (int layer = 1; layer <= 3; ++layer) {
+        T.begin(layer, nrows, st);
+        if ((rc = tc_layer(tw, w, precision, layer, in[layer - 1], out[layer - 1], nrows, st, err)) < 0) return -1;
+        T.end(st);
+        n += rc;
+    }
     Ct4Args c4 = c4in;
     c4.act3 = static_cast<const float*>(act3);     // projected planes [row][9][64][64]
+    T.begin(4, nrows, st);
     n += launch_ct4_gather(w, c4, st);
+    T.end(st);
     return n;
 }
 

@@ -22,10 +22,25 @@ void tc_release(TcWeights* w);
 
 // FC4 -> ct1 -> ct2 -> ct3 -> pixel terms for one chunk of decoder rows on the tensor cores.
 // Returns the number of kernels launched, or -1 (+ *err).
+// optional per-kernel event recorder (dai_profile_begin / dai_profile_end)
+struct LayerTimer {
+    struct Rec { int layer; int rows; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    bool on = false;
+    void begin(int layer, int rows, cudaStream_t st) {
+        if (!on) return;
+        Rec r{layer, rows, nullptr, nullptr};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st) { if (on) cudaEventRecord(recs.back().b, st); }
+};
+
 // h3b = FC3 output in K-blocked bf16 hi/lo [plane][kc 32][rows_pad][8]; the chunk starts at row0.
 int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, const void* h3b, size_t rows_pad, int row0,
                      const uint32_t* mask, int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4,
-                     cudaStream_t st, std::string* err);
+                     cudaStream_t st, std::string* err, LayerTimer* timer = nullptr);
 
 // One tensor-core layer (1: ct1, 2: ct2, 3: ct3) on channel-blocked bf16 hi/lo input planes.
 int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer, const void* in, void* out, int nrows,

@@ -61,6 +61,9 @@ SIGNATURES = {
                                         ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dai_mcts_simulate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                          _vp, _vp, _vp]),
+    "dai_profile_begin": (ctypes.c_int, [_vp]),
+    "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
+                                       ctypes.POINTER(ctypes.c_int64), _vp]),
     "dai_debug_layer": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp]),
 }
 
@@ -265,6 +268,15 @@ class Engine:
         self._ck(self.lib.dai_rollout_host(self.h, _p(o_host), _p(pi_host), B, steps, samples, 1 if calc_mean else 0,
                                            1 if four else 0, _p(out_host[0]), _p(out_host[1]), _p(out_host[2]),
                                            _p(out_host[3]), _p(po1_host), self._stream()))
+
+    def profile_begin(self):
+        self._ck(self.lib.dai_profile_begin(self.h))
+
+    def profile_end(self):
+        """{layer: (ms, launches, rows)} for layers fc4, ct1, ct2, ct3, pixel."""
+        ms, n, rows = (ctypes.c_float * 5)(), (ctypes.c_int64 * 5)(), (ctypes.c_int64 * 5)()
+        self._ck(self.lib.dai_profile_end(self.h, ms, n, rows, self._stream()))
+        return {name: (ms[i], n[i], rows[i]) for i, name in enumerate(("fc4", "ct1", "ct2", "ct3", "pixel"))}
 
     def debug_layer(self, layer, precision, x):
         """test hook: one decoder contraction layer, fp32 NHWC in/out (include/dai_b200.h)."""

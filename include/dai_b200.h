@@ -157,6 +157,14 @@ DAI_API int  dai_rollout_host(dai_handle* h, const float* o_host, const float* p
 DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means,
                        float* G_host, float* pi0, float* qpi, void* stream);
 
+/* ---- per-kernel timing (bench.py's roofline leg) -----------------------------------------
+ * Between dai_profile_begin and dai_profile_end every decoder contraction kernel is bracketed by
+ * CUDA events on its launch stream.  dai_profile_end waits for the stream and returns, per layer
+ * (0: FC4, 1: ct1, 2: ct2, 3: ct3, 4: pixel terms), the summed device time in ms, the number of
+ * launches and the decoder rows processed. */
+DAI_API int  dai_profile_begin(dai_handle* h);
+DAI_API int  dai_profile_end(dai_handle* h, float ms[5], int64_t launches[5], int64_t rows[5], void* stream);
+
 /* ---- test hook ------------------------------------------------------------------------
  * One decoder contraction layer in isolation (layer 1: ConvT 64->64 s1 16x16; 2: ConvT 64->64 s2
  * 16x16->32x32; 3: ConvT 64->32 s2 32x32->64x64; src/torchmodel.py:120-124), bias + ReLU included,
