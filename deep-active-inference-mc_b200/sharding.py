@@ -18,3 +18,20 @@ def shard_range(samples, rank, world):
     base, rem = divmod(samples, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allreduce_term_sums(sums, group=None):
+    """The one collective of a sharded rollout: in-place sum of the (4,B) float64 partial term sums."""
+    import torch.distributed as dist
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def combine_sums(sums, samples):
+    """(4,B) float64 sums of term0, term1, term2_1, term2_2 -> (G, term0, term1, term2) float32, as
+    src/torchmodel.py:282-298 finishes them.  Host-side twin of dai_combine (which the model uses for device
+    tensors); used where the sums live on the CPU (gloo tests)."""
+    import torch
+    t = (sums / float(samples)).to(torch.float32)
+    t2 = t[2] - t[3]
+    return -t[0] + t[1] + t2, t[0], t[1], t2

@@ -247,6 +247,32 @@ def calculate_G(W, s0, pi0, samples, nz, step=0, extras=None):
     return G, [term0, term1, term2], ps1, ps1_mean, po1
 
 
+def calculate_G_shard(W, s0, pi0, samples, j0, j1, nz, step=0):
+    """The sample-sharded form of calculate_G (SURVEY.md §8 e): this "rank" evaluates samples [j0, j1) and
+    returns the raw float64 sums (4,B) of term0, term1, term2_1, term2_2 over them — the all-reduce payload —
+    plus (ps1, ps1_mean, ps1_logvar) of the GLOBALLY last loop-2a sample, which every rank recomputes under
+    the same noise key (src/torchmodel.py:291,300 depend on it)."""
+    B = s0.shape[0]
+    sums = torch.zeros(4, B, dtype=torch.float64)
+    nz.at(step, samples - 1)
+    last = ps_forward_with_sample(W, pi0, s0, nz, SITES["PS_A"])
+    for j in range(j0, j1):
+        nz.at(step, j)
+        ps1, ps1_mean, ps1_logvar = ps_forward_with_sample(W, pi0, s0, nz, SITES["PS_A"])
+        po1 = po_forward(W, ps1, nz, SITES["PO_A"])
+        _, _, qs1_logvar = qs_forward_with_sample(W, po1, nz, SITES["QS_A"])
+        sums[0] += check_reward(po1).double()
+        sums[1] += (-torch.sum(entropy_normal_from_logvar(ps1_logvar)
+                               + entropy_normal_from_logvar(qs1_logvar), dim=1)).double()
+    for j in range(j0, j1):
+        nz.at(step, j)
+        s_fresh = ps_forward_with_sample(W, pi0, s0, nz, SITES["PS_B"])[0]
+        sums[2] += torch.sum(entropy_bernoulli(po_forward(W, s_fresh, nz, SITES["PO_B1"])), dim=[1, 2, 3]).double()
+        s_rep = reparameterize(last[1], last[2], nz, SITES["RP_B"])
+        sums[3] += torch.sum(entropy_bernoulli(po_forward(W, s_rep, nz, SITES["PO_B2"])), dim=[1, 2, 3]).double()
+    return sums, last
+
+
 def calculate_G_mean(W, s0, pi0, nz, step=0, extras=None):
     """ActiveInferenceModel.calculate_G_mean — src/torchmodel.py:302-327 (4-tuple).
     All 25 noises are still drawn; the eps of the two transitions is discarded."""
