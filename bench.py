@@ -105,7 +105,10 @@ def main():
     ap.add_argument("--samples", type=int, default=50)
     ap.add_argument("--horizon", type=int, default=10)
     ap.add_argument("--precision", default="bf16x3")
-    ap.add_argument("--shard", default="samples", choices=["samples", "roots"])
+    ap.add_argument("--shard", default="hybrid", choices=["hybrid", "samples", "roots"],
+                    help="N>1: hybrid = pairs of ranks split the MC samples of 2R roots (one NCCL all-reduce per "
+                         "rollout inside each pair), R*N roots in total [weak]; samples = all ranks split the "
+                         "samples of the same R roots [strong]; roots = R independent roots per rank, no collective [weak]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()
@@ -148,13 +151,21 @@ def main():
     eng = model._engine
 
     # work split over ranks
+    group, frame_seed = None, 0
     if world > 1 and args.shard == "roots":
         my_roots, shard, scaling = R, None, "weak"          # every rank owns R roots: R*world rollouts per step
         total_roots = R * world
+        frame_seed = rank
+    elif world > 1 and args.shard == "hybrid":
+        ws = 2 if world % 2 == 0 else 1                      # sample-shard degree (50 samples -> 25 + 25)
+        groups = [dist.new_group(ranks=[g * ws + i for i in range(ws)]) for g in range(world // ws)]
+        group, frame_seed = groups[rank // ws], rank // ws
+        my_roots, shard, scaling = R * ws, (shard_range(N, rank % ws, ws) if ws > 1 else None), "weak"
+        total_roots = R * world                              # per-GPU work is constant: R roots x N samples x T
     else:
         my_roots, shard, scaling = R, (shard_range(N, rank, world) if world > 1 else None), ("strong" if world > 1 else "weak")
         total_roots = R
-    frames = torch.from_numpy(synthetic.make_frames(my_roots, seed=rank if args.shard == "roots" else 0))
+    frames = torch.from_numpy(synthetic.make_frames(my_roots, seed=frame_seed))
     o_host = frames.repeat_interleave(4, dim=0).reshape(4 * my_roots, 4096).contiguous().pin_memory()
     o_dev = o_host.to(dev)
     out_host = torch.empty(4, 4 * my_roots).pin_memory()
@@ -163,7 +174,7 @@ def main():
     def step_device():
         out = eng.rollout(o_dev, None, T, N, calc_mean=False, four=False, shard=shard, want_po1=False)
         if shard is not None:
-            dist.all_reduce(out["sums"])
+            dist.all_reduce(out["sums"], group=group)
             eng.combine(out["sums"], N)
         return out
 
@@ -173,7 +184,7 @@ def main():
         else:
             o = o_host.to(dev, non_blocking=True)
             out = eng.rollout(o, None, T, N, calc_mean=False, four=False, shard=shard, want_po1=False)
-            dist.all_reduce(out["sums"])
+            dist.all_reduce(out["sums"], group=group)
             G, t0, t1, t2 = eng.combine(out["sums"], N)
             out_host[0].copy_(G, non_blocking=True)
             out_host[1].copy_(t0, non_blocking=True)
@@ -213,6 +224,15 @@ def main():
     ms_e2e = ms_dev if args.quick else timed(step_e2e, args.steps, 1)
     value = total_roots / (ms_dev * 1e-3)
     e2e = total_roots / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel (ct3: ConvT 64->32 as tcgen05 implicit GEMM): every launch of the same
+    # steps bracketed by CUDA events on the launch stream, in a separate pass so the events do not perturb
+    # `value` (all ranks run it: the sharded step contains the all-reduce)
+    layers = {}
+    if args.precision != "fp32_simt":
+        eng.profile_begin()
+        for _ in range(min(args.steps, 3)):
+            step_device()
+        layers = eng.profile_end()
 
     if rank != 0:
         if world > 1:
@@ -232,20 +252,14 @@ def main():
         "vs_baseline": None, "dtype": {"fp32_simt": "f32", "bf16x3": "bf16x3 (hi/lo split, f32 accumulate)",
                                        "bf16x1": "bf16"}[args.precision],
         "data": "synthetic", "config": dict(config, precision=args.precision, shard=args.shard if world > 1 else "none",
+                                            roots_total=total_roots, roots_per_rank=my_roots,
+                                            samples_per_rank=(shard[1] - shard[0]) if shard else N,
                                             l2="flushed between timed iterations (160 MB write)"),
         "node_evals_per_s": value * 4 * N * T, "algorithmic_tflops": flops_step / (ms_dev * 1e-3) / 1e12,
         "e2e": {"value": e2e, "unit": "rollouts/s", "h2d_bytes_per_step": int(o_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    # roofline of the dominant kernel (ct3: ConvT 64->32 as tcgen05 implicit GEMM): every launch of the same
-    # steps bracketed by CUDA events on the launch stream, in a separate pass so the events do not perturb `value`
-    layers = {}
-    if args.precision != "fp32_simt":
-        eng.profile_begin()
-        for _ in range(min(args.steps, 3)):
-            step_device()
-        layers = eng.profile_end()
     roof = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None,
             "peak_source": peak_src, "kernel": "k_tc_conv<ct3> (ConvT 64->32, 32x32->64x64, + last-deconv projection)"}
     if layers and layers["ct3"][1] > 0:
