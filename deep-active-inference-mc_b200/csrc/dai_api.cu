@@ -845,8 +845,10 @@ int dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, in
     h->launches += tc_to_blocked(in, nrows, hw_in, 64, h->act0.p, st);
     std::string terr;
     void* dst = layer == 3 ? (void*)out : h->act1.p;
+    h->timer.begin(layer, nrows, st);
     const int nl = tc_layer(h->tcw, h->w, precision, layer, h->act0.p, dst, nrows, st, &terr);
     if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core layer: %s", terr.c_str());
+    h->timer.end(st);
     h->launches += nl;
     if (layer != 3) h->launches += tc_from_blocked(h->act1.p, nrows, hw_out, 64, out, st);
     return post_launch(h, "debug layer (tc)");

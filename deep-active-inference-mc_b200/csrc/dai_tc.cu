@@ -15,6 +15,8 @@
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/dai_b200.h"
@@ -156,10 +158,16 @@ struct ConvParams {
     const float* bias;       // [Cout]
     void* out;               // blocked bf16 planes (ct1, ct2) or projected fp32 planes [row][9][HO][WO] (ct3)
     float w4[288];           // ct3 only: last deconv's weights [c 32][tap 9] (kernel params = constant bank)
+    int32_t dbg;             // experiments only (env DAI_TC_DBG): 1 = epilogue does no work, 2 = no MMAs issued
+    long long* counters;     // experiments only: per CTA {mma_total, mma_wait_acc, mma_wait_a, epi_total, epi_wait, tiles, 0, 0}
 };
 
-template <int MODE_, int NPH_, int HIN_, int WIN_, int NA_, bool TWO_PASS_>
+template <int MODE_, int NPH_, int HIN_, int WIN_, int NA_, bool TWO_PASS_, int EPI_WARPS_ = 8, bool CONCAT_ = false>
 struct Cfg {
+    // CONCAT (bf16x3 only): a weight block stores its hi rows followed by its lo rows, so A_hi * [B_hi; B_lo] is ONE
+    // MMA of doubled N (the fixed ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times);
+    // the hi*lo part lands in a second column block that the epilogue adds.
+    static constexpr bool CONCAT = CONCAT_;
     // TWO_PASS: per tile, all MMAs on the hi plane of the halo first, then all on the lo plane (the planes can
     // then share a 3-slot ring); otherwise both planes are waited for and the three products of one (tap, k)
     // step are issued back to back.
@@ -168,7 +176,7 @@ struct Cfg {
     static constexpr int NPH = NPH_;         // Cout
     static constexpr int HIN = HIN_, WIN = WIN_;
     static constexpr int NA = NA_;           // halo ring slots; one slot = one bf16 plane (hi or lo) of one tile
-    static constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter
+    static constexpr int EPI_WARPS = EPI_WARPS_;   // 2 or 4 warps per TMEM lane quarter
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int TH = 16, TW = 8;    // tile of the m-grid: 128 pixels
     static constexpr int HY = MODE == 0 ? TH + 2 : TH + 1;
@@ -177,7 +185,7 @@ struct Cfg {
     static constexpr int PLANE_A = 8 * KC_STRIDE;              // one bf16 plane (64 channels) = one ring slot
     static constexpr int TILES_X = WIN / TW, TILES_Y = HIN / TH;
     static constexpr int TILES = TILES_X * TILES_Y;
-    static constexpr int ACC_COLS = MODE == 0 ? NPH : 4 * NPH;
+    static constexpr int ACC_COLS = (MODE == 0 ? NPH : 4 * NPH) * (CONCAT_ ? 2 : 1);
     static constexpr int NACC = 2;
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
     static constexpr int W_BYTES = 9 * NPH * 256;              // all 9 taps, hi + lo, resident
@@ -269,10 +277,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             mbar_wait(w_full, 0);
             tc_fence_after();
             int it = 0, cnt = 0;
+            long long t_begin = clock64(), w_acc = 0, w_a = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it % C::NACC;
                 const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
+                long long tw = clock64();
                 mbar_wait(&acc_empty[buf], aph ^ 1u);
+                w_acc += clock64() - tw;
                 if (C::TWO_PASS) {
                     for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
                         const int s = cnt % C::NA;
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     }
                 } else {
                     const int s0 = cnt % C::NA;
+                    tw = clock64();
                     mbar_wait(&a_full[s0], (uint32_t)(cnt / C::NA) & 1u);
                     ++cnt;
                     int s1 = s0;
@@ -315,10 +327,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
                         ++cnt;
                     }
+                    w_a += clock64() - tw;
                     tc_fence_after();
                     const uint32_t a_hi_base = smem_u32(smA + (size_t)s0 * C::PLANE_A);
                     const uint32_t a_lo_base = smem_u32(smA + (size_t)s1 * C::PLANE_A);
-                    for (int u = 0; u < p.nunits; ++u) {
+                    for (int u = 0; u < ((p.dbg & 2) ? 0 : p.nunits); ++u) {
                         const Unit un = p.units[u];
                         const uint32_t n = (uint32_t)un.n;
                         const uint32_t idesc = umma_idesc(un.n);
@@ -329,13 +342,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_hi = umma_desc(a_hi_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                            const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                            umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
-                            if (nplanes == 2) {
+                            if (C::CONCAT && nplanes == 2) {
+                                // block = [kc][2n rows: hi then lo][8]
+                                const uint64_t b_all = umma_desc(w_base + (uint32_t)(2 * k) * 2u * n * 16u, 2u * n * 16u, 128);
                                 const uint64_t a_lo = umma_desc(a_lo_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                                const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                                umma_bf16(d, a_lo, b_hi, idesc, 1u);
-                                umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                umma_bf16(d, a_hi, b_all, umma_idesc(2 * un.n), (un.init && k == 0) ? 0u : 1u);   // [A_hi*B_hi | A_hi*B_lo]
+                                umma_bf16(d, a_lo, b_all, idesc, 1u);                                            // A_lo*B_hi (first n rows)
+                            } else {
+                                const uint32_t kstep = C::CONCAT ? 2u * n * 16u : n * 16u;
+                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * kstep, kstep, 128);
+                                umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
+                                if (nplanes == 2) {
+                                    const uint64_t a_lo = umma_desc(a_lo_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                                    const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                    umma_bf16(d, a_lo, b_hi, idesc, 1u);
+                                    umma_bf16(d, a_hi, b_lo, idesc, 1u);
+                                }
                             }
                         }
                     }
@@ -344,29 +366,44 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                 }
                 umma_commit(&acc_full[buf]);
             }
+            if (p.counters) {
+                long long* c = p.counters + (size_t)blockIdx.x * 8;
+                c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = it;
+            }
         }
     } else if (warp >= 4) {
         // ===== epilogue: lane = pixel of the tile; `half` = which half of the tile's outputs this warp owns =====
         const int ew = warp & 3;                  // the TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;
+        const int grp = (warp - 4) >> 2;          // 0..EPI_WARPS/4-1
+        const int half = grp & 1;
         const int m = ew * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
         int it = 0;
+        long long e_begin = clock64(), e_wait = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int buf = it % C::NACC;
             const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
             const int row = tile / C::TILES, t = tile % C::TILES;
             const int y = (t / C::TILES_X) * C::TH + ty, x = (t % C::TILES_X) * C::TW + tx;
+            const long long ew0 = clock64();
             mbar_wait(&acc_full[buf], aph);
+            e_wait += clock64() - ew0;
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
-            if (C::MODE == 0) {
+            if (p.dbg & 1) {
+            } else if (C::MODE == 0) {
                 // 32 of the 64 output channels -> blocked bf16 hi/lo [plane][row][kc][H][W][8]
                 __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
                 const size_t plane = (size_t)p.nrows * C::NPH * C::HIN * C::WIN;
                 const int c0 = half * 32;
                 uint32_t r[32];
                 tmem_ld32(tbase + c0, r);
+                if (C::CONCAT && nplanes == 2) {
+                    uint32_t r2[32];
+                    tmem_ld32(tbase + C::NPH + c0, r2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t hi[4], lo[4];
@@ -391,36 +428,48 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     // so its channel contraction is done here, in registers, per output pixel:
                     //   d[t] = sum_c relu(acc[c] + b[c]) * w4[c][t],  t = kh*3+kw
                     // and only the 9 projections leave the SM ([row][t][HO][WO] fp32, 36 B/pixel instead of 128).
+                    // With 16 epilogue warps the 9 taps are split 5 + 4 between two warps of the same (quarter, py).
                     float* out = reinterpret_cast<float*>(p.out) + (size_t)row * 9 * HO * WO;
-                    float dl[9], dr[9];
-                    {
-                        uint32_t r[32];
-                        tmem_ld32(tbase + slot_l * 32, r);
-#pragma unroll
-                        for (int t9 = 0; t9 < 9; ++t9) dl[t9] = 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float v = fmaxf(__uint_as_float(r[c]) + sbias[c], 0.0f);
-#pragma unroll
-                            for (int t9 = 0; t9 < 9; ++t9) dl[t9] = fmaf(v, p.w4[c * 9 + t9], dl[t9]);
-                        }
-                    }
-                    {
-                        uint32_t r[32];
-                        tmem_ld32(tbase + slot_r * 32, r);
-#pragma unroll
-                        for (int t9 = 0; t9 < 9; ++t9) dr[t9] = 0.0f;
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float v = fmaxf(__uint_as_float(r[c]) + sbias[c], 0.0f);
-#pragma unroll
-                            for (int t9 = 0; t9 < 9; ++t9) dr[t9] = fmaf(v, p.w4[c * 9 + t9], dr[t9]);
-                        }
-                    }
                     const size_t o = (size_t)oy * WO + ox;
+                    uint32_t rl[32], rr[32];
+                    tmem_ld32(tbase + slot_l * 32, rl);
+                    tmem_ld32(tbase + slot_r * 32, rr);
+                    if (C::EPI_WARPS == 16 && (grp >> 1) == 1) {
+                        float dl[4], dr[4];
 #pragma unroll
-                    for (int t9 = 0; t9 < 9; ++t9)
-                        *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                        for (int t9 = 0; t9 < 4; ++t9) { dl[t9] = 0.0f; dr[t9] = 0.0f; }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float vl = fmaxf(__uint_as_float(rl[c]) + sbias[c], 0.0f);
+                            const float vr = fmaxf(__uint_as_float(rr[c]) + sbias[c], 0.0f);
+#pragma unroll
+                            for (int t9 = 0; t9 < 4; ++t9) {
+                                dl[t9] = fmaf(vl, p.w4[c * 9 + 5 + t9], dl[t9]);
+                                dr[t9] = fmaf(vr, p.w4[c * 9 + 5 + t9], dr[t9]);
+                            }
+                        }
+#pragma unroll
+                        for (int t9 = 0; t9 < 4; ++t9)
+                            *reinterpret_cast<float2*>(out + (size_t)(5 + t9) * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                    } else {
+                        constexpr int NT = C::EPI_WARPS == 16 ? 5 : 9;
+                        float dl[NT], dr[NT];
+#pragma unroll
+                        for (int t9 = 0; t9 < NT; ++t9) { dl[t9] = 0.0f; dr[t9] = 0.0f; }
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float vl = fmaxf(__uint_as_float(rl[c]) + sbias[c], 0.0f);
+                            const float vr = fmaxf(__uint_as_float(rr[c]) + sbias[c], 0.0f);
+#pragma unroll
+                            for (int t9 = 0; t9 < NT; ++t9) {
+                                dl[t9] = fmaf(vl, p.w4[c * 9 + t9], dl[t9]);
+                                dr[t9] = fmaf(vr, p.w4[c * 9 + t9], dr[t9]);
+                            }
+                        }
+#pragma unroll
+                        for (int t9 = 0; t9 < NT; ++t9)
+                            *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                    }
                 } else {
                     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
                     const size_t plane = (size_t)p.nrows * C::NPH * HO * WO;
@@ -449,6 +498,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (p.counters && warp == 4 && lane == 0) {
+            long long* c = p.counters + (size_t)blockIdx.x * 8;
+            c[3] = clock64() - e_begin; c[4] = e_wait;
         }
     }
     tc_fence_before();
@@ -607,9 +660,9 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-using CfgCt1 = Cfg<0, 64, 16, 16, 3, false>;     // 144 KB of weights + 3 x 22.5 KB halo planes
+using CfgCt1 = Cfg<0, 64, 16, 16, 3, false, 8, true>;   // 144 KB of weights + 3 x 22.5 KB halo planes
 using CfgCt2 = Cfg<1, 64, 16, 16, 4, false>;     // 144 KB of weights + 4 x 19.1 KB halo planes (2 tiles in flight)
-using CfgCt3 = Cfg<1, 32, 32, 32, 6, false>;     //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
+using CfgCt3 = Cfg<1, 32, 32, 32, 6, false, 8>;  //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
 
 // ---------------------------------------------------------------------------------------
 // host: weight packing, tensor maps, launches
@@ -646,8 +699,20 @@ struct Sub { int kh, kw; };
 
 // One weight block = [plane hi|lo][kc 8][n][8] bf16 with n = sub * Cout + co, K = Cin = 64:
 // the UMMA no-swizzle K-major layout of a (n x 64) operand.  ConvTranspose2d weight is (Cin,Cout,3,3).
-void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst) {
+void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst, bool concat) {
     const int n = nsub * Cout;
+    if (concat) {      // [kc 8][2n rows: hi rows then lo rows][8]
+        for (int s = 0; s < nsub; ++s)
+            for (int co = 0; co < Cout; ++co)
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float v = W[(((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw];
+                    const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                    const int nn = s * Cout + co, kc = ci >> 3, e = ci & 7;
+                    dst[((size_t)kc * 2 * n + nn) * 8 + e] = hi;
+                    dst[((size_t)kc * 2 * n + n + nn) * 8 + e] = lo;
+                }
+        return;
+    }
     for (int s = 0; s < nsub; ++s)
         for (int co = 0; co < Cout; ++co)
             for (int ci = 0; ci < Cin; ++ci) {
@@ -664,7 +729,7 @@ void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs,
 // (y+dy, x+dx) with kh = 1 (py = 0); kh = 0 for dy = 1 and kh = 2 for dy = 0 (py = 1); same in x.
 inline int k_of(int parity, int d) { return parity == 0 ? 1 : (d == 1 ? 0 : 2); }
 
-int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool grouped, LayerPack* lp,
+int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool grouped, bool concat, LayerPack* lp,
                 std::vector<void*>* allocs, std::string* err) {
     std::vector<uint16_t> host((size_t)9 * Cout * 128);       // 9 taps * Cout * 64 k * 2 planes
     int nu = 0;
@@ -673,7 +738,7 @@ int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool g
         Unit& u = lp->units[nu++];
         u.oy = (int16_t)oy; u.ox = (int16_t)ox; u.col = (int16_t)col; u.n = (int16_t)(nsub * Cout); u.init = (int16_t)init;
         u.woff = (int32_t)(off * 2);
-        pack_block(W, Cin, Cout, subs, nsub, host.data() + off);
+        pack_block(W, Cin, Cout, subs, nsub, host.data() + off, concat);
         off += (size_t)nsub * Cout * 128;
     };
     if (mode == 0) {
@@ -741,12 +806,31 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     p.wpack = lp.wpack; p.bias = bias; p.out = out;
     if (w4) memcpy(p.w4, w4, sizeof(p.w4));
+    if (const char* e = getenv("DAI_TC_DBG")) p.dbg = atoi(e);
+    static long long* dbg_counters = nullptr;
+    const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;
+    if (want_counters) {
+        if (!dbg_counters) cudaMalloc(&dbg_counters, 8 * 8 * 512);
+        cudaMemsetAsync(dbg_counters, 0, 8 * 8 * 512, st);
+        p.counters = dbg_counters;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = nrows * C::TILES;
     const int grid = ntiles < sms ? ntiles : sms;
     k_tc_conv<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+    if (want_counters) {
+        static int printed = 0;
+        cudaStreamSynchronize(st);
+        long long h[8 * 512];
+        cudaMemcpy(h, dbg_counters, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < grid; ++i) for (int j = 0; j < 6; ++j) a[j] += (double)h[i * 8 + j] / grid;
+        if (printed++ % 23 == 3)
+            fprintf(stderr, "[tc counters] mode %d nph %d rows %d: per CTA cycles: mma loop %.0f (wait acc_empty %.0f, wait a_full %.0f) | "
+                    "epilogue loop %.0f (wait acc_full %.0f) | tiles %.1f\n", C::MODE, C::NPH, nrows, a[0], a[1], a[2], a[3], a[4], a[5]);
+    }
     return 1;
 }
 
@@ -808,9 +892,9 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         }
         im->attrs_set = true;
     }
-    if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, &im->ct1, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, &im->ct2, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, &im->ct3, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, CfgCt1::CONCAT, &im->ct1, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, CfgCt2::CONCAT, &im->ct2, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, CfgCt3::CONCAT, &im->ct3, allocs, err) != 0) return -1;
     {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
         // of [plane][kc 8][256 n][8]
         const std::vector<float>& W = raw.at("po_net.9.weight");

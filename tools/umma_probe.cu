@@ -19,7 +19,7 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
 }
 
 // mode bits: 1 = alternate accumulator (independent D), 2 = alternate B operand, 4 = alternate A operand
-__global__ void probe(int n, int mode, int iters, long long* out) {
+__global__ void probe(int n, int mode, int iters, long long* out, int a_shift, int a_sbo, int a_lbo) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tslot;
@@ -44,7 +44,7 @@ __global__ void probe(int n, int mode, int iters, long long* out) {
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
             const uint32_t d = tmem + ((mode & 1) ? (uint32_t)((i & 1) * 256) : 0u);
-            const uint64_t a = umma_desc(((mode & 4) && (i & 1)) ? a1 : a0, 2048, 128);
+            const uint64_t a = umma_desc((((mode & 4) && (i & 1)) ? a1 : a0) + (uint32_t)a_shift, (uint32_t)a_lbo, (uint32_t)a_sbo);
             const uint64_t b = umma_desc(((mode & 2) && (i & 1)) ? b1 : b0, (uint32_t)n * 16u, 128);
             umma(d, a, b, idesc, i > 1 ? 1u : 0u);
         }
@@ -54,7 +54,7 @@ __global__ void probe(int n, int mode, int iters, long long* out) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
         }
-        out[0] = clock64() - t0;
+        out[blockIdx.x] = clock64() - t0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -66,19 +66,37 @@ int main() {
     cudaMalloc(&d, 8);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     const int iters = 4096;
-    printf("%5s %28s %12s %10s\n", "N", "pattern", "cyc/MMA", "ideal");
-    const char* names[8] = {"same D, same A, same B", "alt D", "alt B", "alt D + alt B", "alt A", "alt D + alt A", "alt A + alt B", "alt D + alt A + alt B"};
+    printf("all-SM contention: cycles per MMA (max over CTAs) vs grid size\n%5s %6s %12s\n", "N", "grid", "cyc/MMA");
+    long long* dd; cudaMalloc(&dd, 8 * 512);
     for (int n : {32, 64, 128, 256}) {
-        for (int mode = 0; mode < 8; ++mode) {
+        for (int grid : {1, 2, 4, 74, 148, 296}) {
+            long long h[512];
+            for (int rep = 0; rep < 2; ++rep) {
+                probe<<<grid, 128, 160 * 1024>>>(n, 0, iters, dd, 0, 128, 2048);
+                cudaDeviceSynchronize();
+                cudaMemcpy(h, dd, 8 * grid, cudaMemcpyDeviceToHost);
+            }
+            long long mx = 0, mn = 1ll << 60;
+            for (int i = 0; i < grid; ++i) { mx = h[i] > mx ? h[i] : mx; mn = h[i] < mn ? h[i] : mn; }
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+            printf("%5d %6d %12.1f (min %.1f)\n", n, grid, (double)mx / iters, (double)mn / iters);
+        }
+    }
+    printf("A-operand geometry (halo windows): cycles per MMA\n%5s %8s %6s %6s %12s\n", "N", "shift", "SBO", "LBO", "cyc/MMA");
+    const int geo[][3] = {{0, 128, 2048}, {16, 128, 2048}, {0, 144, 2448}, {16, 144, 2448}, {0, 160, 2880}, {32, 160, 2880},
+                          {0, 256, 4096}, {16, 256, 4096}, {0, 1024, 128}};
+    for (int n : {32, 64, 128, 256}) {
+        for (auto& g : geo) {
             long long c = 0;
             for (int rep = 0; rep < 2; ++rep) {
-                probe<<<1, 128, 160 * 1024>>>(n, mode, iters, d);
+                probe<<<1, 128, 160 * 1024>>>(n, 0, iters, d, g[0], g[1], g[2]);
                 cudaDeviceSynchronize();
                 cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
             }
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-            printf("%5d %28s %12.1f %10.1f\n", n, names[mode], (double)c / iters, n / 2.0);
+            printf("%5d %8d %6d %6d %12.1f\n", n, g[0], g[1], g[2], (double)c / iters);
         }
     }
     return 0;
