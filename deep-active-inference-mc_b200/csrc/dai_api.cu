@@ -335,8 +335,9 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
         chs = (ch / B) * B;
         if (chs == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
     }
-    RET(reserve(h, h->qc1, (size_t)chs * 961 * 32 * sizeof(float)));
-    RET(reserve(h, h->qc2, (size_t)chs * 225 * 32 * sizeof(float)));
+    const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
+    RET(reserve(h, h->qc1, (size_t)chs * 32768 * sizeof(float)));   // (31,31,32) fp32, or 2 x 4 parities x (16,16,32) bf16
+    RET(reserve(h, h->qc2, (size_t)chs * 8192 * sizeof(float)));    // (15,15,32) fp32, or 2 x 4 parities x (8,8,32) bf16
     RET(reserve(h, h->qc3, (size_t)chs * 49 * 64 * sizeof(float)));
     RET(reserve(h, h->qc4, (size_t)chs * 576 * sizeof(float)));
     for (int r0 = 0; r0 < rows; r0 += chs) {
@@ -349,7 +350,15 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
         a.mean = mean + (size_t)r0 * S_DIM; a.logvar = logvar + (size_t)r0 * S_DIM;
         a.samp = samp ? samp + (size_t)r0 * S_DIM : nullptr;
         a.nk = nk;
-        h->launches += launch_qs(h->w, a, st);
+        if (!tc) {
+            h->launches += launch_qs(h->w, a, st);
+        } else {
+            h->launches += launch_qs_conv1(h->w, a.img, n, nullptr, h->qc1.p, st);
+            std::string terr;
+            const int nl = tc_qs_convs(h->tcw, h->w, h->cfg.precision, h->qc1.p, h->qc2.p, a.c3, n, st, &terr);
+            if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder convs: %s", terr.c_str());
+            h->launches += nl + launch_qs_tail(h->w, a, st);
+        }
     }
     return post_launch(h, "encoder");
 }

@@ -89,6 +89,10 @@ struct QsArgs {
     NoiseKey nk;
 };
 int  launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st);
+// the same encoder in pieces, so conv2/conv3 can run on tensor cores (dai_tc.cu) between conv1 and the tail
+int  launch_qs_conv1(const DevWeights& w, const float* img, int rows, float* c1, void* c1_parity, cudaStream_t st);
+int  launch_qs_conv23_simt(const DevWeights& w, const float* c1, int rows, float* c2, float* c3, cudaStream_t st);
+int  launch_qs_tail(const DevWeights& w, const QsArgs& a, cudaStream_t st);
 
 // ---- habit net -----------------------------------------------------------------------
 int  launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float* q, float* logq, cudaStream_t st);

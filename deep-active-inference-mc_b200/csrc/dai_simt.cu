@@ -616,7 +616,7 @@ int launch_reward_only(const float* o, int B, float* r, cudaStream_t st) {
 // ======================================================================================
 __global__ void __launch_bounds__(256) k_qs_conv1(const float* __restrict__ img, int rows,
                                                   const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                  float* __restrict__ out) {
+                                                  float* __restrict__ out, unsigned short* __restrict__ outp) {
     __shared__ float ws[9 * 32];
     __shared__ float bs[32];
     for (int i = threadIdx.x; i < 288; i += 256) ws[i] = wgt[i];
@@ -632,6 +632,37 @@ __global__ void __launch_bounds__(256) k_qs_conv1(const float* __restrict__ img,
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) v[kh * 3 + kw] = __ldg(in + kh * 64 + kw);
+    if (outp) {
+        // parity-split channel-blocked bf16 hi/lo planes for the tensor-core conv2:
+        // [plane][row][parity = (oy&1)*2 + (ox&1)][kc 4][16][16][8]
+        const size_t plane = (size_t)rows * 4 * 4 * 256 * 8;
+        const int par = (oy & 1) * 2 + (ox & 1);
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y2[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = kc * 8 + e * 2 + j;
+                    float acc = bs[c];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) acc = fmaf(v[t], ws[t * 32 + c], acc);
+                    y2[j] = fmaxf(acc, 0.0f);
+                }
+                const __nv_bfloat162 h = __floats2bfloat162_rn(y2[0], y2[1]);
+                hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(y2[0] - __uint_as_float(hi[e] << 16),
+                                                               y2[1] - __uint_as_float(hi[e] & 0xffff0000u));
+                lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const size_t o = (((((size_t)r * 4 + par) * 4 + kc) * 16 + (oy >> 1)) * 16 + (ox >> 1)) * 8;
+            *reinterpret_cast<uint4*>(outp + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(outp + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        return;
+    }
     float* o = out + (size_t)idx * 32;
 #pragma unroll
     for (int c4 = 0; c4 < 8; ++c4) {
@@ -702,24 +733,43 @@ __global__ void __launch_bounds__(QF_NT) k_qs_fc(DevWeights w, QsArgs a) {
     }
 }
 
-int launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
-    if (a.rows <= 0) return 0;
+// conv1 -> fp32 NHWC (c1) or parity-split blocked bf16 planes (c1p) for the tensor-core conv2
+int launch_qs_conv1(const DevWeights& w, const float* img, int rows, float* c1, void* c1p, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    k_qs_conv1<<<(rows * 961 + 255) / 256, 256, 0, st>>>(img, rows, w.qc1_w, w.qc1_b, c1, static_cast<unsigned short*>(c1p));
+    return 1;
+}
+
+// conv2, conv3 on CUDA cores: c1 (31,31,32) -> c2 (15,15,32) -> c3 (7,7,64), fp32 NHWC
+int launch_qs_conv23_simt(const DevWeights& w, const float* c1, int rows, float* c2, float* c3, cudaStream_t st) {
     int n = 0;
-    k_qs_conv1<<<(a.rows * 961 + 255) / 256, 256, 0, st>>>(a.img, a.rows, w.qc1_w, w.qc1_b, a.c1);
-    ++n;
     ConvGeom g{};
-    g.mode = 3; g.M = a.rows * 225; g.Hm = 15; g.Wm = 15; g.Hin = 31; g.Win = 31; g.Cin = 32;
-    g.Hout = 15; g.Wout = 15; g.Cout = 32; g.in = a.c1; g.W = w.qc2_w; g.bias = w.qc2_b; g.out = a.c2;
+    g.mode = 3; g.M = rows * 225; g.Hm = 15; g.Wm = 15; g.Hin = 31; g.Win = 31; g.Cin = 32;
+    g.Hout = 15; g.Wout = 15; g.Cout = 32; g.in = c1; g.W = w.qc2_w; g.bias = w.qc2_b; g.out = c2;
     n += launch_gemm<128, 32>(g, 1, st);
-    g.M = a.rows * 49; g.Hm = 7; g.Wm = 7; g.Hin = 15; g.Win = 15; g.Cin = 32;
-    g.Hout = 7; g.Wout = 7; g.Cout = 64; g.in = a.c2; g.W = w.qc3_w; g.bias = w.qc3_b; g.out = a.c3;
+    g.M = rows * 49; g.Hm = 7; g.Wm = 7; g.Hin = 15; g.Win = 15; g.Cin = 32;
+    g.Hout = 7; g.Wout = 7; g.Cout = 64; g.in = c2; g.W = w.qc3_w; g.bias = w.qc3_b; g.out = c3;
     n += launch_gemm<64, 64>(g, 1, st);
-    g.M = a.rows * 9; g.Hm = 3; g.Wm = 3; g.Hin = 7; g.Win = 7; g.Cin = 64;
+    return n;
+}
+
+// conv4 (7,7,64) -> (3,3,64) and the fused FC stack; a.c3 holds conv3's output
+int launch_qs_tail(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    ConvGeom g{};
+    g.mode = 3; g.M = a.rows * 9; g.Hm = 3; g.Wm = 3; g.Hin = 7; g.Win = 7; g.Cin = 64;
     g.Hout = 3; g.Wout = 3; g.Cout = 64; g.in = a.c3; g.W = w.qc4_w; g.bias = w.qc4_b; g.out = a.c4;
-    n += launch_gemm<64, 64>(g, 1, st);
+    int n = launch_gemm<64, 64>(g, 1, st);
     const size_t smem = (QF_TM * (576 + 256 + 256 + 20)) * sizeof(float) + QF_TM * 8 * sizeof(uint32_t);
     k_qs_fc<<<(a.rows + QF_TM - 1) / QF_TM, QF_NT, smem, st>>>(w, a);
     return n + 1;
+}
+
+int launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    int n = launch_qs_conv1(w, a.img, a.rows, a.c1, nullptr, st);
+    n += launch_qs_conv23_simt(w, a.c1, a.rows, a.c2, a.c3, st);
+    return n + launch_qs_tail(w, a, st);
 }
 
 // ======================================================================================

@@ -144,6 +144,7 @@ struct Unit {            // one MMA group of a tile: a tap shift of the halo x a
     int16_t col;         // TMEM column offset inside the tile's accumulator block
     int16_t n;           // N of the MMA
     int16_t init;        // 1: its first MMA overwrites the accumulator
+    int16_t kc0;         // first 8-channel plane of the halo this unit reads (parity plane of a strided conv)
     int32_t woff;        // byte offset of its weight block in the resident weight image
 };
 
@@ -162,34 +163,48 @@ struct ConvParams {
     long long* counters;     // experiments only: per CTA {mma_total, mma_wait_acc, mma_wait_a, epi_total, epi_wait, tiles, 0, 0}
 };
 
-template <int MODE_, int NPH_, int HIN_, int WIN_, int NA_, bool TWO_PASS_, int EPI_WARPS_ = 8, bool CONCAT_ = false>
-struct Cfg {
-    // CONCAT (bf16x3 only): a weight block stores its hi rows followed by its lo rows, so A_hi * [B_hi; B_lo] is ONE
-    // MMA of doubled N (the fixed ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times);
-    // the hi*lo part lands in a second column block that the epilogue adds.
-    static constexpr bool CONCAT = CONCAT_;
-    // TWO_PASS: per tile, all MMAs on the hi plane of the halo first, then all on the lo plane (the planes can
-    // then share a 3-slot ring); otherwise both planes are waited for and the three products of one (tap, k)
-    // step are issued back to back.
-    static constexpr bool TWO_PASS = TWO_PASS_;
-    static constexpr int MODE = MODE_;       // 0: convT k3 s1 p1; 1: convT k3 s2 p1 op1 (4 sub-pixel phases)
-    static constexpr int NPH = NPH_;         // Cout
-    static constexpr int HIN = HIN_, WIN = WIN_;
-    static constexpr int NA = NA_;           // halo ring slots; one slot = one bf16 plane (hi or lo) of one tile
-    static constexpr int EPI_WARPS = EPI_WARPS_;   // 2 or 4 warps per TMEM lane quarter
-    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+enum { OUT_BLOCKED = 0, OUT_PROJ = 1, OUT_PARITY = 2, OUT_NHWC_F32 = 3 };
+
+// Layer traits:
+//   MODE     0: convT k3 s1 p1; 1: convT k3 s2 p1 op1 (4 sub-pixel phases); 2: conv k3 s2 valid (parity-split input)
+//   NPH      Cout;  KCIN  Cin/8
+//   GH,GW    m-grid the 16x8 tiles cover (output grid for MODE 0/2, input grid for MODE 1); VH,VW its valid part
+//   PH,PW    height/width of one input plane in HBM (MODE 2: of one parity plane)
+//   NA       halo ring slots (one slot = one bf16 plane, hi or lo, of one tile)
+//   TWO_PASS per tile all MMAs on the hi plane first, then all on the lo plane (planes can share a 3-slot ring);
+//            otherwise both planes are waited for and the products of one (tap, k) step are issued back to back
+//   CONCAT   (bf16x3) a weight block stores hi rows then lo rows: A_hi*[B_hi;B_lo] is ONE MMA of doubled N — the fixed
+//            ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times; the hi*lo part lands in a
+//            second column block that the epilogue adds
+struct TrCt1 { static constexpr int MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = true; };
+struct TrCt2 { static constexpr int MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false; };
+struct TrCt3 { static constexpr int MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 6,
+               EPI_WARPS = 8, OUT = OUT_PROJ; static constexpr bool TWO_PASS = false, CONCAT = false; };
+// encoder: Conv2d 32->32 (31x31 -> 15x15) and 32->64 (15x15 -> 7x7), k3 s2 valid
+struct TrQc2 { static constexpr int MODE = 2, NPH = 32, KCIN = 4, GH = 16, GW = 16, VH = 15, VW = 15, PH = 16, PW = 16, NA = 4,
+               EPI_WARPS = 8, OUT = OUT_PARITY; static constexpr bool TWO_PASS = false, CONCAT = false; };
+struct TrQc3 { static constexpr int MODE = 2, NPH = 64, KCIN = 4, GH = 16, GW = 8, VH = 7, VW = 7, PH = 8, PW = 8, NA = 4,
+               EPI_WARPS = 8, OUT = OUT_NHWC_F32; static constexpr bool TWO_PASS = false, CONCAT = false; };
+
+template <class T>
+struct Cfg : T {
+    static constexpr int THREADS = 128 + 32 * T::EPI_WARPS;
     static constexpr int TH = 16, TW = 8;    // tile of the m-grid: 128 pixels
-    static constexpr int HY = MODE == 0 ? TH + 2 : TH + 1;
-    static constexpr int HX = MODE == 0 ? TW + 2 : TW + 1;
+    static constexpr int HY = T::MODE == 0 ? TH + 2 : TH + 1;
+    static constexpr int HX = T::MODE == 0 ? TW + 2 : TW + 1;
+    static constexpr int KPLANES = T::MODE == 2 ? 4 * T::KCIN : T::KCIN;   // 8-channel planes in the halo (x4 parities)
+    static constexpr int KSTEPS = T::KCIN / 2;                            // k16 steps per tap
     static constexpr int KC_STRIDE = HY * HX * 16;             // bytes of one 8-channel plane of the halo
-    static constexpr int PLANE_A = 8 * KC_STRIDE;              // one bf16 plane (64 channels) = one ring slot
-    static constexpr int TILES_X = WIN / TW, TILES_Y = HIN / TH;
+    static constexpr int PLANE_A = KPLANES * KC_STRIDE;        // one bf16 plane (hi or lo) = one ring slot
+    static constexpr int TILES_X = (T::GW + TW - 1) / TW, TILES_Y = (T::GH + TH - 1) / TH;
     static constexpr int TILES = TILES_X * TILES_Y;
-    static constexpr int ACC_COLS = (MODE == 0 ? NPH : 4 * NPH) * (CONCAT_ ? 2 : 1);
+    static constexpr int ACC_COLS = (T::MODE == 1 ? 4 * T::NPH : T::NPH) * (T::CONCAT ? 2 : 1);
     static constexpr int NACC = 2;
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
-    static constexpr int W_BYTES = 9 * NPH * 256;              // all 9 taps, hi + lo, resident
-    static constexpr int SMEM_A = NA * PLANE_A;
+    static constexpr int W_BYTES = 9 * T::NPH * T::KCIN * 32;  // all 9 taps, hi + lo, resident
+    static constexpr int SMEM_A = T::NA * PLANE_A;
     static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + 1024; // + barriers, tmem slot, bias
 };
 
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int row = tile / C::TILES, t = tile % C::TILES;
                 const int y0 = (t / C::TILES_X) * C::TH, x0 = (t % C::TILES_X) * C::TW;
-                const int hy0 = C::MODE == 0 ? y0 - 1 : y0, hx0 = C::MODE == 0 ? x0 - 1 : x0;
+                const int hy0 = C::MODE == 0 ? y0 - 1 : y0, hx0 = C::MODE == 0 ? x0 - 1 : x0;   // MODE 2: parity-plane coords
                 for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
                     const int s = cnt % C::NA;
                     const uint32_t ph = (uint32_t)(cnt / C::NA) & 1u;
@@ -269,7 +284,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
         // ===== weights: all taps, once =====
         if (lane == 0) {
             mbar_expect_tx(w_full, C::W_BYTES);
-            for (int off = 0; off < C::W_BYTES; off += 8192) bulk_load(smW + off, p.wpack + off, 8192, w_full);
+            for (int off = 0; off < C::W_BYTES; off += 4096) bulk_load(smW + off, p.wpack + off, 4096, w_full);
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
@@ -296,11 +311,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                             const uint32_t n = (uint32_t)un.n;
                             const uint32_t idesc = umma_idesc(un.n);
                             const uint32_t w_base = smem_u32(smW + un.woff);
-                            const uint32_t b_plane = 8u * n * 16u;            // hi -> lo plane of this weight block
-                            const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+                            const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;     // hi -> lo plane of this weight block
+                            const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
                             const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                            for (int k = 0; k < C::KSTEPS; ++k) {
                                 const uint64_t a_d = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
                                 const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
                                 if (pl == 0) {
@@ -336,11 +351,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         const uint32_t n = (uint32_t)un.n;
                         const uint32_t idesc = umma_idesc(un.n);
                         const uint32_t w_base = smem_u32(smW + un.woff);
-                        const uint32_t b_plane = 8u * n * 16u;
-                        const uint32_t a_off = (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+                        const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;     // hi -> lo plane of this weight block
+                        const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
                         const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < C::KSTEPS; ++k) {
                             const uint64_t a_hi = umma_desc(a_hi_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
                             if (C::CONCAT && nplanes == 2) {
                                 // block = [kc][2n rows: hi then lo][8]
@@ -391,11 +406,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
             if (p.dbg & 1) {
-            } else if (C::MODE == 0) {
-                // 32 of the 64 output channels -> blocked bf16 hi/lo [plane][row][kc][H][W][8]
-                __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-                const size_t plane = (size_t)p.nrows * C::NPH * C::HIN * C::WIN;
-                const int c0 = half * 32;
+            } else if (C::MODE != 1) {
+                // 32 of the NPH output channels of this pixel (half = which 32, when NPH = 64)
+                const int c0 = (C::NPH == 64) ? half * 32 : 0;
+                const bool active = (C::NPH == 64 || half == 0) && y < C::VH && x < C::VW;
                 uint32_t r[32];
                 tmem_ld32(tbase + c0, r);
                 if (C::CONCAT && nplanes == 2) {
@@ -404,22 +418,44 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                 }
+                if (active && C::OUT == OUT_NHWC_F32) {
+                    float* out = reinterpret_cast<float*>(p.out) + (((size_t)row * C::VH + y) * C::VW + x) * C::NPH + c0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t hi[4], lo[4];
+                    for (int q = 0; q < 8; ++q) {
+                        float4 v;
+                        v.x = fmaxf(__uint_as_float(r[q * 4 + 0]) + sbias[c0 + q * 4 + 0], 0.0f);
+                        v.y = fmaxf(__uint_as_float(r[q * 4 + 1]) + sbias[c0 + q * 4 + 1], 0.0f);
+                        v.z = fmaxf(__uint_as_float(r[q * 4 + 2]) + sbias[c0 + q * 4 + 2], 0.0f);
+                        v.w = fmaxf(__uint_as_float(r[q * 4 + 3]) + sbias[c0 + q * 4 + 3], 0.0f);
+                        *reinterpret_cast<float4*>(out + q * 4) = v;
+                    }
+                } else if (active) {
+                    // blocked bf16 hi/lo [plane][row][kc][H][W][8], or its parity-split form
+                    // [plane][row][parity][kc][H/2][W/2][8] for a following strided conv
+                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+                    constexpr int KCO = C::NPH / 8;
+                    constexpr int OH = C::OUT == OUT_PARITY ? (C::VH + 1) / 2 : C::GH, OW = C::OUT == OUT_PARITY ? (C::VW + 1) / 2 : C::GW;
+                    constexpr int NPAR = C::OUT == OUT_PARITY ? 4 : 1;
+                    const size_t plane = (size_t)p.nrows * NPAR * KCO * OH * OW * 8;
+                    const int par = C::OUT == OUT_PARITY ? ((y & 1) * 2 + (x & 1)) : 0;
+                    const int py = C::OUT == OUT_PARITY ? (y >> 1) : y, px = C::OUT == OUT_PARITY ? (x >> 1) : x;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        split2(r[q * 8 + 2 * e], r[q * 8 + 2 * e + 1], sbias[c0 + q * 8 + 2 * e], sbias[c0 + q * 8 + 2 * e + 1],
-                               1.0f, 1.0f, hi[e], lo[e]);
-                    const int kc = (c0 >> 3) + q;
-                    const size_t o = ((((size_t)row * (C::NPH / 8) + kc) * C::HIN + y) * C::WIN + x) * 8;
-                    *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            split2(r[q * 8 + 2 * e], r[q * 8 + 2 * e + 1], sbias[c0 + q * 8 + 2 * e], sbias[c0 + q * 8 + 2 * e + 1],
+                                   1.0f, 1.0f, hi[e], lo[e]);
+                        const int kc = (c0 >> 3) + q;
+                        const size_t o = (((((size_t)row * NPAR + par) * KCO + kc) * OH + py) * OW + px) * 8;
+                        *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
                 }
             } else {
                 // TMEM column slots are [00, 01, 11, 10] (host unit table): this warp takes output row parity
                 // py = half and both column parities, so every store covers two neighbouring output pixels.
-                constexpr int HO = 2 * C::HIN, WO = 2 * C::WIN;
+                constexpr int HO = 2 * C::GH, WO = 2 * C::GW;
                 const int py = half;
                 const int slot_l = py == 0 ? 0 : 3, slot_r = py == 0 ? 1 : 2;   // px = 0, px = 1
                 const int oy = 2 * y + py, ox = 2 * x;
@@ -660,9 +696,11 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-using CfgCt1 = Cfg<0, 64, 16, 16, 3, false, 8, true>;   // 144 KB of weights + 3 x 22.5 KB halo planes
-using CfgCt2 = Cfg<1, 64, 16, 16, 4, false>;     // 144 KB of weights + 4 x 19.1 KB halo planes (2 tiles in flight)
-using CfgCt3 = Cfg<1, 32, 32, 32, 6, false, 8>;  //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
+using CfgCt1 = Cfg<TrCt1>;   // 144 KB of weights + 3 x 22.5 KB halo planes
+using CfgCt2 = Cfg<TrCt2>;   // 144 KB of weights + 4 x 19.1 KB halo planes (2 tiles in flight)
+using CfgCt3 = Cfg<TrCt3>;   //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
+using CfgQc2 = Cfg<TrQc2>;   //  36 KB of weights + 4 x 38.3 KB halo planes (4 parities x 4 kc)
+using CfgQc3 = Cfg<TrQc3>;   //  72 KB of weights + 4 x 38.3 KB halo planes
 
 // ---------------------------------------------------------------------------------------
 // host: weight packing, tensor maps, launches
@@ -674,7 +712,7 @@ struct LayerPack {
 };
 
 struct TcImpl {
-    LayerPack ct1, ct2, ct3;
+    LayerPack ct1, ct2, ct3, qc2, qc3;
     float w4[288];               // po_net.19.weight as [c][tap]
     uint8_t* fc4_wpack = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -699,29 +737,28 @@ struct Sub { int kh, kw; };
 
 // One weight block = [plane hi|lo][kc 8][n][8] bf16 with n = sub * Cout + co, K = Cin = 64:
 // the UMMA no-swizzle K-major layout of a (n x 64) operand.  ConvTranspose2d weight is (Cin,Cout,3,3).
-void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst, bool concat) {
-    const int n = nsub * Cout;
-    if (concat) {      // [kc 8][2n rows: hi rows then lo rows][8]
-        for (int s = 0; s < nsub; ++s)
-            for (int co = 0; co < Cout; ++co)
-                for (int ci = 0; ci < Cin; ++ci) {
-                    const float v = W[(((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw];
-                    const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
-                    const int nn = s * Cout + co, kc = ci >> 3, e = ci & 7;
-                    dst[((size_t)kc * 2 * n + nn) * 8 + e] = hi;
-                    dst[((size_t)kc * 2 * n + n + nn) * 8 + e] = lo;
-                }
-        return;
-    }
+// One weight block = [plane hi|lo][kc Cin/8][n][8] bf16 with n = sub * Cout + co: the UMMA no-swizzle K-major layout
+// of an (n x Cin) operand (concat: [kc][2n rows: hi rows then lo rows][8]).  ConvTranspose2d weights are
+// (Cin,Cout,3,3), Conv2d weights (Cout,Cin,3,3).
+void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst, bool concat,
+                bool conv_layout) {
+    const int n = nsub * Cout, KC = Cin / 8;
     for (int s = 0; s < nsub; ++s)
         for (int co = 0; co < Cout; ++co)
             for (int ci = 0; ci < Cin; ++ci) {
-                const float v = W[(((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw];
+                const size_t wi = conv_layout ? (((size_t)co * Cin + ci) * 3 + subs[s].kh) * 3 + subs[s].kw
+                                              : (((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw;
+                const float v = W[wi];
                 const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
                 const int nn = s * Cout + co, kc = ci >> 3, e = ci & 7;
-                const size_t o = ((size_t)kc * n + nn) * 8 + e;
-                dst[o] = hi;
-                dst[(size_t)8 * n * 8 + o] = lo;
+                if (concat) {
+                    dst[((size_t)kc * 2 * n + nn) * 8 + e] = hi;
+                    dst[((size_t)kc * 2 * n + n + nn) * 8 + e] = lo;
+                } else {
+                    const size_t o = ((size_t)kc * n + nn) * 8 + e;
+                    dst[o] = hi;
+                    dst[(size_t)KC * n * 8 + o] = lo;
+                }
             }
 }
 
@@ -731,22 +768,31 @@ inline int k_of(int parity, int d) { return parity == 0 ? 1 : (d == 1 ? 0 : 2); 
 
 int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool grouped, bool concat, LayerPack* lp,
                 std::vector<void*>* allocs, std::string* err) {
-    std::vector<uint16_t> host((size_t)9 * Cout * 128);       // 9 taps * Cout * 64 k * 2 planes
+    std::vector<uint16_t> host((size_t)9 * Cout * Cin * 2);   // 9 taps * Cout * Cin * 2 planes
+    const int KC = Cin / 8;
     int nu = 0;
     size_t off = 0;                                            // in uint16 elements
-    auto add = [&](int oy, int ox, int col, const Sub* subs, int nsub, int init) {
+    auto add = [&](int oy, int ox, int col, const Sub* subs, int nsub, int init, int kc0) {
         Unit& u = lp->units[nu++];
         u.oy = (int16_t)oy; u.ox = (int16_t)ox; u.col = (int16_t)col; u.n = (int16_t)(nsub * Cout); u.init = (int16_t)init;
+        u.kc0 = (int16_t)kc0;
         u.woff = (int32_t)(off * 2);
-        pack_block(W, Cin, Cout, subs, nsub, host.data() + off, concat);
-        off += (size_t)nsub * Cout * 128;
+        pack_block(W, Cin, Cout, subs, nsub, host.data() + off, concat, mode == 2);
+        off += (size_t)nsub * Cout * Cin * 2;
     };
     if (mode == 0) {
         // convT s1 p1: oy = iy - 1 + kh; halo origin (y0-1, x0-1) => local row = ty + 2 - kh
         for (int kh = 0; kh < 3; ++kh)
             for (int kw = 0; kw < 3; ++kw) {
                 Sub s{kh, kw};
-                add(2 - kh, 2 - kw, 0, &s, 1, nu == 0);
+                add(2 - kh, 2 - kw, 0, &s, 1, nu == 0, 0);
+            }
+    } else if (mode == 2) {
+        // conv s2 valid: input (2*oy+kh, 2*ox+kw) = parity plane (kh&1, kw&1) at (oy + (kh>>1), ox + (kw>>1))
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) {
+                Sub s{kh, kw};
+                add(kh >> 1, kw >> 1, 0, &s, 1, nu == 0, ((kh & 1) * 2 + (kw & 1)) * KC);
             }
     } else if (!grouped) {
         for (int py = 0; py < 2; ++py)
@@ -755,20 +801,20 @@ int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool g
                 for (int dy = 0; dy <= py; ++dy)
                     for (int dx = 0; dx <= px; ++dx) {
                         Sub s{k_of(py, dy), k_of(px, dx)};
-                        add(dy, dx, (py * 2 + px) * Cout, &s, 1, first);
+                        add(dy, dx, (py * 2 + px) * Cout, &s, 1, first, 0);
                         first = false;
                     }
             }
     } else {
         // column slots [00, 01, 11, 10]; every shift of the halo feeds all phases that read it in one MMA
         const Sub g00[4] = {{k_of(0, 0), k_of(0, 0)}, {k_of(0, 0), k_of(1, 0)}, {k_of(1, 0), k_of(1, 0)}, {k_of(1, 0), k_of(0, 0)}};
-        add(0, 0, 0, g00, 4, 1);
+        add(0, 0, 0, g00, 4, 1, 0);
         const Sub g01[2] = {{k_of(0, 0), k_of(1, 1)}, {k_of(1, 0), k_of(1, 1)}};        // phases 01, 11
-        add(0, 1, 1 * Cout, g01, 2, 0);
+        add(0, 1, 1 * Cout, g01, 2, 0, 0);
         const Sub g10[2] = {{k_of(1, 1), k_of(1, 0)}, {k_of(1, 1), k_of(0, 0)}};        // phases 11, 10
-        add(1, 0, 2 * Cout, g10, 2, 0);
+        add(1, 0, 2 * Cout, g10, 2, 0, 0);
         const Sub g11[1] = {{k_of(1, 1), k_of(1, 1)}};                                  // phase 11
-        add(1, 1, 2 * Cout, g11, 1, 0);
+        add(1, 1, 2 * Cout, g11, 1, 0, 0);
     }
     lp->nunits = nu;
     void* d = nullptr;
@@ -780,11 +826,12 @@ int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool g
 }
 
 // blocked bf16 activation tensor [plane 2][rows][kc 8][H][W][8] -> 5-D map (W*8, H, kc, rows, plane), box = halo
-int make_map(TcImpl* im, const void* base, int rows, int H, int W, int HX, int HY, CUtensorMap* map, std::string* err) {
-    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, 8, (cuuint64_t)rows, 2};
-    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)8 * H * W * 16,
-                             (cuuint64_t)rows * 8 * H * W * 16};
-    cuuint32_t box[5] = {(cuuint32_t)HX * 8, (cuuint32_t)HY, 8, 1, 1};
+int make_map(TcImpl* im, const void* base, int rows, int H, int W, int kplanes, int HX, int HY, CUtensorMap* map,
+             std::string* err) {
+    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)kplanes, (cuuint64_t)rows, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)kplanes * H * W * 16,
+                             (cuuint64_t)rows * kplanes * H * W * 16};
+    cuuint32_t box[5] = {(cuuint32_t)HX * 8, (cuuint32_t)HY, (cuuint32_t)kplanes, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = im->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -800,7 +847,7 @@ template <class C>
 int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precision, const void* in, void* out, int nrows,
                 cudaStream_t st, std::string* err, const float* w4 = nullptr) {
     CUtensorMap map;
-    if (make_map(im, in, nrows, C::HIN, C::WIN, C::HX, C::HY, &map, err) != 0) return -1;
+    if (make_map(im, in, nrows, C::PH, C::PW, C::KPLANES, C::HX, C::HY, &map, err) != 0) return -1;
     ConvParams p{};
     for (int i = 0; i < lp.nunits; ++i) p.units[i] = lp.units[i];
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
@@ -886,6 +933,8 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         if (cudaFuncSetAttribute(k_tc_conv<CfgCt1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt1::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgCt2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgQc2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgQc3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_fc4, cudaFuncAttributeMaxDynamicSharedMemorySize, FC4_SMEM) != cudaSuccess) {
             *err = std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(cudaGetLastError());
             return -1;
@@ -895,6 +944,8 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
     if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, CfgCt1::CONCAT, &im->ct1, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, CfgCt2::CONCAT, &im->ct2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, CfgCt3::CONCAT, &im->ct3, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("qs_net.2.weight"), 2, 32, 32, false, false, &im->qc2, allocs, err) != 0) return -1;
+    if (build_layer(raw.at("qs_net.4.weight"), 2, 32, 64, false, false, &im->qc3, allocs, err) != 0) return -1;
     {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
         // of [plane][kc 8][256 n][8]
         const std::vector<float>& W = raw.at("po_net.9.weight");
@@ -940,6 +991,17 @@ int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer,
     }
     *err = "unknown tensor-core layer";
     return -1;
+}
+
+// encoder conv2 + conv3 on tensor cores: c1 = conv1 output in parity-split blocked planes
+// [plane][row][parity 4][kc 4][16][16][8]; c2 = same form of the 15x15x32 map ([..][8][8][8]); c3 = fp32 NHWC (7,7,64)
+int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
+                cudaStream_t st, std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(tw.impl);
+    if (!im) { *err = "tensor-core weights not packed"; return -1; }
+    if (launch_conv<CfgQc2>(im, im->qc2, w.qc2_b, precision, c1, c2, rows, st, err) < 0) return -1;
+    if (launch_conv<CfgQc3>(im, im->qc3, w.qc3_b, precision, c2, c3, rows, st, err) < 0) return -1;
+    return 2;
 }
 
 int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* h3b, size_t rows_pad, int row0,

@@ -42,6 +42,11 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
                      const uint32_t* mask, int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4,
                      cudaStream_t st, std::string* err, LayerTimer* timer = nullptr);
 
+// Encoder conv2 (32->32, 31x31->15x15) and conv3 (32->64, 15x15->7x7) on tensor cores.  c1 / c2 are parity-split
+// channel-blocked bf16 hi/lo planes, c3 is fp32 NHWC (rows,7,7,64).  Returns launches or -1.
+int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
+                cudaStream_t st, std::string* err);
+
 // One tensor-core layer (1: ct1, 2: ct2, 3: ct3) on channel-blocked bf16 hi/lo input planes.
 int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer, const void* in, void* out, int nrows,
              cudaStream_t st, std::string* err);
