@@ -299,7 +299,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
         const int n = std::min(ch, rows - r0);
         const uint32_t* mask = nullptr;
         if (fc.nk.training) {
-            h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), st);
+            h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), tc ? 1 : 0, st);
             mask = ptr<uint32_t>(h->mask);
         }
         const float* h3c = tc ? nullptr : fc.h3 + (size_t)r0 * 256;

@@ -55,8 +55,9 @@ struct PoFcArgs {
 };
 int  launch_po_fc123(const DevWeights& w, const PoFcArgs& a, cudaStream_t st);
 
-// permuted dropout mask bits of the 16384-wide FC4 output, [rows][512] words in NHWC bit order
-int  launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, cudaStream_t st);
+// permuted dropout mask bits of the 16384-wide FC4 output, [rows][512] words in the consumer's column order
+// (tc_order 0: NHWC p*64+c for the CUDA-core FC4; 1: the tensor-core FC4's ((pg*8+kc)*4+pl)*8+ce)
+int  launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, int tc_order, cudaStream_t st);
 
 // fp32 SIMT layers over a chunk of decoder rows [row0, row0+nrows)
 int  launch_fc4_simt(const DevWeights& w, const float* h3, const uint32_t* mask, int nrows, float* act0, cudaStream_t st);

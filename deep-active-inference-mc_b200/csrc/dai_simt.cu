@@ -228,7 +228,7 @@ int launch_po_fc123(const DevWeights& w, const PoFcArgs& a, cudaStream_t st) {
 // (64,16,16), src/torchmodel.py:119) to the NHWC bit order n' = p*64 + c the layers use.
 // One CTA per row; words[512] per row.
 // ======================================================================================
-__global__ void __launch_bounds__(128) k_fc4_mask(RowMap map, NoiseKey nk, int row0, int nrows, uint32_t* mask) {
+__global__ void __launch_bounds__(128) k_fc4_mask(RowMap map, NoiseKey nk, int row0, int nrows, uint32_t* mask, int tc_order) {
     __shared__ uint32_t orig[512];
     const int r = row0 + blockIdx.x;
     int set, slot, b;
@@ -238,21 +238,30 @@ __global__ void __launch_bounds__(128) k_fc4_mask(RowMap map, NoiseKey nk, int r
     const uint4 w = noise_block(nk, (uint32_t)(map.site[set] + 3), (uint32_t)tid, (uint32_t)b, map.sample_of(slot));
     orig[tid * 4 + 0] = w.x; orig[tid * 4 + 1] = w.y; orig[tid * 4 + 2] = w.z; orig[tid * 4 + 3] = w.w;
     __syncthreads();
-    for (int i = tid; i < 512; i += 128) {          // output word i covers n' = i*32 .. i*32+31
-        const int p = i >> 1, c0 = (i & 1) * 32;
+    for (int i = tid; i < 512; i += 128) {          // output word i covers columns i*32 .. i*32+31
         uint32_t word = 0;
+        if (!tc_order) {                            // NHWC order: column = p*64 + c
+            const int p = i >> 1, c0 = (i & 1) * 32;
 #pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const int e = (c0 + j) * 256 + p;
-            word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
+            for (int j = 0; j < 32; ++j) {
+                const int e = (c0 + j) * 256 + p;
+                word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
+            }
+        } else {                                    // tensor-core FC4 order: column = ((pg*8 + kc)*4 + pl)*8 + ce
+            const int pg = i >> 3, kc = i & 7;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const int e = (kc * 8 + (j & 7)) * 256 + pg * 4 + (j >> 3);
+                word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
+            }
         }
         out[i] = word;
     }
 }
 
-int launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, cudaStream_t st) {
+int launch_fc4_mask(const RowMap& map, const NoiseKey& nk, int row0, int nrows, uint32_t* mask, int tc_order, cudaStream_t st) {
     if (nrows <= 0) return 0;
-    k_fc4_mask<<<nrows, 128, 0, st>>>(map, nk, row0, nrows, mask);
+    k_fc4_mask<<<nrows, 128, 0, st>>>(map, nk, row0, nrows, mask, tc_order);
     return 1;
 }
 

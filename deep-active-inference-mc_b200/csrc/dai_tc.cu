@@ -667,23 +667,27 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
                 uint32_t r[32];
                 tmem_ld32(tbase + c0, r);
                 if (row < p.nrows) {
-                    const int n0 = nt * 256 + half * 128 + c0;           // NHWC column = px * 64 + c
+                    // GEMM column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel
+                    // 8*kc + e.  A 256-column tile is one group of 4 pixels x 64 channels and the 32 columns loaded here
+                    // are 4 pixels x 8 channels of one kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores.
+                    const int n0 = nt * 256 + half * 128 + c0;
                     const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
                     const float sc = p.mask ? 2.0f : 1.0f;
-                    const int px = n0 >> 6, kc0 = (n0 & 63) >> 3;
+                    const int kc = (n0 >> 5) & 7;
+                    uint32_t hi[4][4], lo[4][4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t hi[4], lo[4];
+                    for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int j0 = q * 8 + 2 * e, j1 = j0 + 1;
+                            const int j0 = pl * 8 + 2 * e, j1 = j0 + 1;
                             split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
-                                   ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[e], lo[e]);
+                                   ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[pl][e], lo[pl][e]);
                         }
-                        const size_t o = (((size_t)row * 8 + kc0 + q) * 256 + px) * 8;
-                        *reinterpret_cast<uint4*>(p.out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(p.out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                    const size_t o = (((size_t)row * 8 + kc) * 256 + nt * 4) * 8;
+                    st_global_256(p.out + o, hi[0], hi[1]);
+                    st_global_256(p.out + o + 16, hi[2], hi[3]);
+                    st_global_256(p.out + plane + o, lo[0], lo[1]);
+                    st_global_256(p.out + plane + o + 16, lo[2], lo[3]);
                 }
             }
             tc_fence_before();
@@ -715,6 +719,7 @@ struct TcImpl {
     LayerPack ct1, ct2, ct3, qc2, qc3;
     float w4[288];               // po_net.19.weight as [c][tap]
     uint8_t* fc4_wpack = nullptr;
+    float* fc4_bias = nullptr;     // po_net.9.bias in the tensor-core FC4's column order
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
     bool attrs_set = false;
 };
@@ -950,8 +955,13 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         // of [plane][kc 8][256 n][8]
         const std::vector<float>& W = raw.at("po_net.9.weight");
         std::vector<uint16_t> host((size_t)16384 * 256 * 2);
+        std::vector<float> bias_tc(16384);
+        const std::vector<float>& braw = raw.at("po_net.9.bias");
         for (int n = 0; n < 16384; ++n) {
-            const int px = n >> 6, c = n & 63, e = c * 256 + px;
+            // column n = ((pg*8 + kc)*4 + pl)*8 + ce  <->  pixel px = 4*pg + pl, channel c = 8*kc + ce
+            const int ce = n & 7, pl = (n >> 3) & 3, kc8 = (n >> 5) & 7, pg = n >> 8;
+            const int px = pg * 4 + pl, c = kc8 * 8 + ce, e = c * 256 + px;
+            bias_tc[n] = braw[e];
             const int nt = n >> 8, nl = n & 255;
             for (int k = 0; k < 256; ++k) {
                 const float v = W[(size_t)e * 256 + k];
@@ -968,6 +978,11 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         allocs->push_back(d);
         if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(fc4 weights)"; return -1; }
         im->fc4_wpack = static_cast<uint8_t*>(d);
+        void* db = nullptr;
+        if (cudaMalloc(&db, 16384 * 4) != cudaSuccess) { *err = "cudaMalloc(fc4 bias)"; return -1; }
+        allocs->push_back(db);
+        if (cudaMemcpy(db, bias_tc.data(), 16384 * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(fc4 bias)"; return -1; }
+        im->fc4_bias = static_cast<float*>(db);
     }
     const std::vector<float>& w19 = raw.at("po_net.19.weight");     // (Cin 32, Cout 1, 3, 3)
     for (int c = 0; c < 32; ++c)
@@ -1011,7 +1026,7 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
     Fc4Params p{};
     p.a = static_cast<const __nv_bfloat16*>(h3b) + (size_t)row0 * 8;
     p.a_kc_stride = rows_pad * 8; p.a_plane = 32 * rows_pad * 8;
-    p.wpack = im->fc4_wpack; p.bias = w.po_b3; p.mask = mask; p.out = static_cast<__nv_bfloat16*>(act0);
+    p.wpack = im->fc4_wpack; p.bias = im->fc4_bias; p.mask = mask; p.out = static_cast<__nv_bfloat16*>(act0);
     p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
