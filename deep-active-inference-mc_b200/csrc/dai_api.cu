@@ -74,7 +74,7 @@ struct dai_handle {
     uint64_t seed = 1234, call = 0;
     uint64_t launches = 0, calls = 0;
     // workspaces (grow-only)
-    DevBuf ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
+    DevBuf mlpA, mlpB, ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
         pi_eye, traj, root, stage_in, stage_out, scratch;
     LayerTimer timer;
     float* pinned = nullptr;   // small host result buffer
@@ -274,6 +274,28 @@ int commit(dai_handle* h) {
     return DAI_OK;
 }
 
+// ---- MLPs: CUDA-core fused kernels (fp32_simt) or first layer / tcgen05 hidden layers / tail ----------
+
+int run_ps(dai_handle* h, cudaStream_t st, const PsArgs& pa) {
+    const int rows = (pa.nA + pa.nB) * pa.B;
+    if (rows <= 0) return DAI_OK;
+    if (h->cfg.precision == DAI_PREC_FP32_SIMT) {
+        h->launches += launch_ps(h->w, pa, st);
+        return post_launch(h, "transition");
+    }
+    const size_t rows_pad = ((size_t)rows + 127) / 128 * 128 + 128;
+    RET(reserve(h, h->mlpA, rows_pad * 512 * 2 * sizeof(unsigned short)));
+    RET(reserve(h, h->mlpB, rows_pad * 512 * 2 * sizeof(unsigned short)));
+    const NoiseRows nr = ps_noise_rows(pa);
+    std::string terr;
+    h->launches += launch_ps_l0(h->w, pa, rows_pad, h->mlpA.p, st);
+    int n1 = tc_dense_hidden(h->tcw, TC_PS1, h->cfg.precision, h->mlpA.p, h->mlpB.p, rows, rows_pad, pa.nk, nr, 1, st, &terr);
+    int n2 = n1 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_PS2, h->cfg.precision, h->mlpB.p, h->mlpA.p, rows, rows_pad, pa.nk, nr, 2, st, &terr);
+    if (n1 < 0 || n2 < 0) return fail(h, DAI_E_CUDA, "tensor-core transition: %s", terr.c_str());
+    h->launches += n1 + n2 + launch_ps_tail(h->w, pa, rows_pad, h->mlpA.p, st);
+    return post_launch(h, "transition");
+}
+
 // ---- decoder over row sets -----------------------------------------------------------
 
 // Runs Po on `fc` rows (sets x slots x B): FC1..3 fused, then per chunk FC4 -> ct1 -> ct2 -> ct3 -> pixel
@@ -294,7 +316,20 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     fc.h3 = tc ? nullptr : ptr<float>(h->h3);
     fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
     fc.rows_pad = rows_pad;
-    h->launches += launch_po_fc123(h->w, fc, st);
+    if (!tc) {
+        h->launches += launch_po_fc123(h->w, fc, st);
+    } else {
+        // FC1 on CUDA cores (K = 10), FC2 / FC3 on tensor cores; FC3's K-blocked output is FC4's A operand
+        RET(reserve(h, h->mlpA, rows_pad * 512 * 2 * sizeof(unsigned short)));
+        RET(reserve(h, h->mlpB, rows_pad * 512 * 2 * sizeof(unsigned short)));
+        const NoiseRows nr = map_noise_rows(fc.map);
+        std::string terr;
+        h->launches += launch_po_l0(h->w, fc, rows_pad, h->mlpA.p, st);
+        int n1 = tc_dense_hidden(h->tcw, TC_PO1, h->cfg.precision, h->mlpA.p, h->mlpB.p, rows, rows_pad, fc.nk, nr, 1, st, &terr);
+        int n2 = n1 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_PO2, h->cfg.precision, h->mlpB.p, h->h3.p, rows, rows_pad, fc.nk, nr, 2, st, &terr);
+        if (n1 < 0 || n2 < 0) return fail(h, DAI_E_CUDA, "tensor-core decoder FCs: %s", terr.c_str());
+        h->launches += n1 + n2;
+    }
     for (int r0 = 0; r0 < rows; r0 += ch) {
         const int n = std::min(ch, rows - r0);
         const uint32_t* mask = nullptr;
@@ -357,7 +392,18 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
             std::string terr;
             const int nl = tc_qs_convs(h->tcw, h->w, h->cfg.precision, h->qc1.p, h->qc2.p, a.c3, n, st, &terr);
             if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder convs: %s", terr.c_str());
-            h->launches += nl + launch_qs_tail(h->w, a, st);
+            h->launches += nl;
+            // conv4 on CUDA cores -> K-blocked operand; FC1..3 on tensor cores; tail (256 -> 20) on CUDA cores
+            const size_t rp = ((size_t)n + 127) / 128 * 128 + 128;
+            RET(reserve(h, h->mlpA, rp * 576 * 2 * sizeof(unsigned short)));
+            RET(reserve(h, h->mlpB, rp * 576 * 2 * sizeof(unsigned short)));
+            const NoiseRows nr = map_noise_rows(a.map);
+            h->launches += launch_qs_conv4_kblocked(h->w, a.c3, n, rp, h->mlpA.p, st);
+            int n0 = tc_dense_hidden(h->tcw, TC_QS0, h->cfg.precision, h->mlpA.p, h->mlpB.p, n, rp, nk, nr, 0, st, &terr);
+            int n1 = n0 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_QS1, h->cfg.precision, h->mlpB.p, h->mlpA.p, n, rp, nk, nr, 1, st, &terr);
+            int n2 = n1 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_QS2, h->cfg.precision, h->mlpA.p, h->mlpB.p, n, rp, nk, nr, 2, st, &terr);
+            if (n0 < 0 || n1 < 0 || n2 < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder FCs: %s", terr.c_str());
+            h->launches += n0 + n1 + n2 + launch_qs_tail20(h->w, a, rp, h->mlpB.p, st);
         }
     }
     return post_launch(h, "encoder");
@@ -401,8 +447,7 @@ int run_step(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
     pa.meanA = meanA; pa.logvarA = logvarA; pa.sampA = sampA;
     pa.meanB = meanB; pa.logvarB = nullptr; pa.sampB = sampB;
     pa.nk = sp.nk;
-    h->launches += launch_ps(h->w, pa, st);
-    RET(post_launch(h, "transition"));
+    RET(run_ps(h, st, pa));
 
     const int rows = 3 * Sl * B;
     RET(reserve(h, h->img, (size_t)std::max(Sl, 1) * B * IMG * sizeof(float)));
@@ -539,7 +584,7 @@ int dai_destroy(dai_handle* h) {
     if (!h) return DAI_E_INVALID;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
+    DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
                       &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -612,7 +657,7 @@ int dai_get_stats(dai_handle* h, dai_stats* out, int reset) {
     out->kernel_launches = h->launches;
     out->calls = h->calls;
     size_t total = 0;
-    DevBuf* bufs[] = {&h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
+    DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
                       &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
     for (DevBuf* b : bufs) total += b->cap;
@@ -652,8 +697,7 @@ int dai_transition(dai_handle* h, const float* pi, const float* s0, int B, float
     pa.meanA = mean; pa.logvarA = logvar; pa.sampA = sample;
     pa.nk = make_key(h, h->call++, 0);
     ++h->calls;
-    h->launches += launch_ps(h->w, pa, (cudaStream_t)stream);
-    return post_launch(h, "transition");
+    return run_ps(h, (cudaStream_t)stream, pa);
 }
 
 int dai_habit(dai_handle* h, const float* s, int B, float* logits, float* q, float* logq, void* stream) {
@@ -723,8 +767,7 @@ int dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, con
     PsArgs pa{};
     pa.pi = pi0; pa.s0 = s0; pa.B = D; pa.nA = 0; pa.nB = 1; pa.sample0 = 0; pa.extra_slot = -1;
     pa.siteA = SITE_PS_A; pa.siteB = SITE_PS_B; pa.sampB = sampB; pa.nk = nk;
-    h->launches += launch_ps(h->w, pa, st);
-    RET(post_launch(h, "transition"));
+    RET(run_ps(h, st, pa));
     RET(reserve(h, h->img, (size_t)D * IMG * sizeof(float)));
     RET(reserve(h, h->hsum, (size_t)3 * D * sizeof(float)));
     RET(reserve(h, h->reward, (size_t)3 * D * sizeof(float)));

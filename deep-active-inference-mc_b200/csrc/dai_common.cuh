@@ -76,6 +76,25 @@ struct RowMap {
     __host__ __device__ int rows() const { return nsets * Sl * B; }
 };
 
+// Noise identity of the rows of a batched MLP launch: up to three consecutive row sets, each (slot, b)-ordered,
+// each standing for one of the reference's net calls (site base); slot -> global MC sample.
+struct NoiseRows {
+    int32_t B;
+    int32_t set_end[3];     // cumulative row count at the end of each set
+    int32_t site[3];
+    int32_t sample0;        // global sample of slot 0
+    int32_t extra_slot;     // set 0 only: slot that stands for global sample `extra_sample` (or -1)
+    int32_t extra_sample;
+    __device__ __forceinline__ void decode(int r, int& site_out, int& b, uint32_t& sample) const {
+        const int set = r < set_end[0] ? 0 : (r < set_end[1] ? 1 : 2);
+        const int q = r - (set == 0 ? 0 : set_end[set - 1]);
+        const int slot = q / B;
+        b = q - slot * B;
+        site_out = site[set];
+        sample = (set == 0 && slot == extra_slot) ? (uint32_t)extra_sample : (uint32_t)(sample0 + slot);
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

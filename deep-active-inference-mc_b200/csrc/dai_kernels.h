@@ -95,6 +95,16 @@ int  launch_qs_conv1(const DevWeights& w, const float* img, int rows, float* c1,
 int  launch_qs_conv23_simt(const DevWeights& w, const float* c1, int rows, float* c2, float* c3, cudaStream_t st);
 int  launch_qs_tail(const DevWeights& w, const QsArgs& a, cudaStream_t st);
 
+// ---- pieces of the tensor-core MLP path (dai_tc.cu runs the hidden layers between them) ----------------
+// K-blocked activations: bf16 hi/lo planes [plane][N/8][rows_pad][8]
+NoiseRows ps_noise_rows(const PsArgs& a);
+NoiseRows map_noise_rows(const RowMap& m);
+int  launch_ps_l0(const DevWeights& w, const PsArgs& a, size_t rows_pad, void* out, cudaStream_t st);          // 14 -> 512
+int  launch_ps_tail(const DevWeights& w, const PsArgs& a, size_t rows_pad, const void* in, cudaStream_t st);   // 512 -> 20 + reparam
+int  launch_po_l0(const DevWeights& w, const PoFcArgs& a, size_t rows_pad, void* out, cudaStream_t st);        // 10 -> 256
+int  launch_qs_tail20(const DevWeights& w, const QsArgs& a, size_t rows_pad, const void* in, cudaStream_t st); // 256 -> 20 (+ reparam)
+int  launch_qs_conv4_kblocked(const DevWeights& w, const float* c3, int rows, size_t rows_pad, void* out, cudaStream_t st);
+
 // ---- habit net -----------------------------------------------------------------------
 int  launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float* q, float* logq, cudaStream_t st);
 

@@ -282,6 +282,8 @@ struct ConvGeom {
     const uint32_t* mask;// dense only: dropout bits [M][Cout/32]
     unsigned short* out_blocked;   // dense FC4 only: write blocked bf16 [plane hi|lo][row][kc 8][16][16][8] instead of `out`
     size_t plane;                  // elements per bf16 plane
+    unsigned short* out_kblocked;  // encoder conv4 only: K-blocked bf16 [plane][72][rows_pad][8] with k = pixel*64 + c
+    size_t rows_pad;
 };
 
 __device__ __forceinline__ int geom_ntaps(const ConvGeom& g, int phase) {
@@ -402,7 +404,15 @@ __global__ void __launch_bounds__(256) k_gather_gemm(ConvGeom g) {
             const int n = n0 + tx * TN + j;
             float v = fmaxf(acc[i][j] + __ldg(g.bias + n), 0.0f);
             if (g.mask) v = ((g.mask[(size_t)m * (g.Cout >> 5) + (n >> 5)] >> (n & 31)) & 1u) ? v * 2.0f : 0.0f;
-            if (g.out_blocked) {
+            if (g.out_kblocked) {
+                // m = image*9 + pixel: k = pixel*64 + n of the flattened (3,3,64) map
+                const int img = m / 9, k = (m - img * 9) * 64 + n;
+                const size_t o = ((size_t)(k >> 3) * g.rows_pad + img) * 8 + (k & 7);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                g.out_kblocked[o] = __bfloat16_as_ushort(hi);
+                g.out_kblocked[(size_t)72 * g.rows_pad * 8 + o] = __bfloat16_as_ushort(lo);
+            } else if (g.out_blocked) {
                 // n = pixel * 64 + c of the (16,16,64) NHWC map -> channel-blocked bf16 hi/lo planes
                 const int px = n >> 6, c = n & 63;
                 const size_t o = (((size_t)m * 8 + (c >> 3)) * 256 + px) * 8 + (c & 7);
@@ -779,6 +789,234 @@ int launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
     int n = launch_qs_conv1(w, a.img, a.rows, a.c1, nullptr, st);
     n += launch_qs_conv23_simt(w, a.c1, a.rows, a.c2, a.c3, st);
     return n + launch_qs_tail(w, a, st);
+}
+
+
+// ======================================================================================
+// Tensor-core MLP path: CUDA-core first layers and tails around the tcgen05 dense kernel.
+// Activations between layers are K-blocked bf16 hi/lo planes [plane][N/8][rows_pad][8].
+// Thread mapping: lane = row (32 rows per CTA), the 8 warps stride over the 8-column groups,
+// so every store is 32 rows x 16 B = 512 contiguous bytes.
+// ======================================================================================
+__device__ __forceinline__ void store_kblocked8(unsigned short* out, size_t plane, size_t o, const float (&v)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - __uint_as_float(hi[e] << 16),
+                                                       v[2 * e + 1] - __uint_as_float(hi[e] & 0xffff0000u));
+        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// layer 0 of Ps (14 -> 512) or Po (10 -> 256): x[KIN] per row -> relu + dropout(site + 0) -> K-blocked planes
+template <int KIN, int N>
+__device__ __forceinline__ void mlp_l0_row(const float (&x)[KIN], const float* __restrict__ Wt /*[KINpad][N]*/,
+                                           const float* __restrict__ bias, const NoiseKey& nk, int site, int b, uint32_t sample,
+                                           bool valid, int row, size_t rows_pad, unsigned short* out) {
+    const int warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)(N / 8) * rows_pad * 8;
+    uint4 drop = make_uint4(0, 0, 0, 0);
+    int have_blk = -1;
+    for (int kc = warp; kc < N / 8; kc += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(bias + kc * 8 + e);
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8 + 4));
+            v[0] = fmaf(x[k], w0.x, v[0]); v[1] = fmaf(x[k], w0.y, v[1]); v[2] = fmaf(x[k], w0.z, v[2]); v[3] = fmaf(x[k], w0.w, v[3]);
+            v[4] = fmaf(x[k], w1.x, v[4]); v[5] = fmaf(x[k], w1.y, v[5]); v[6] = fmaf(x[k], w1.z, v[6]); v[7] = fmaf(x[k], w1.w, v[7]);
+        }
+        if (nk.training) {
+            const int blk = kc >> 4;                      // 128 columns per Philox block
+            if (blk != have_blk) { drop = noise_block(nk, (uint32_t)site, (uint32_t)blk, (uint32_t)b, sample); have_blk = blk; }
+            const int wsel = (kc >> 2) & 3;
+            const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
+            const int sh = (kc & 3) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = ((mw >> (sh + e)) & 1u) ? fmaxf(v[e], 0.0f) * 2.0f : 0.0f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+        }
+        if (valid) store_kblocked8(out, plane, ((size_t)kc * rows_pad + row) * 8, v);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ps_l0(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, unsigned short* out) {
+    const int rows = (a.nA + a.nB) * a.B;
+    const int row = blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool valid = row < rows;
+    int site, b;
+    uint32_t sample;
+    nr.decode(valid ? row : rows - 1, site, b, sample);
+    float x[14];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = a.pi[b * 4 + k];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) x[4 + k] = a.s0[b * 10 + k];
+    mlp_l0_row<14, 512>(x, w.ps_w0t, w.ps_b0, a.nk, site, b, sample, valid, row, rows_pad, out);
+}
+
+__global__ void __launch_bounds__(256) k_po_l0(DevWeights w, PoFcArgs a, size_t rows_pad, unsigned short* out) {
+    const int rows = a.map.rows();
+    const int row = blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool valid = row < rows;
+    int set, slot, b;
+    a.map.decode(valid ? row : rows - 1, set, slot, b);
+    const uint32_t sample = a.map.sample_of(slot);
+    float x[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (a.mode[set] == 0) {
+            const size_t zr = a.zbcast[set] ? (size_t)b : (size_t)slot * a.map.B + b;
+            x[k] = a.z[set][zr * S_DIM + k];
+        } else {
+            const float eps = noise_normal(a.nk, (uint32_t)a.rp_site, (uint32_t)k, (uint32_t)b, sample);
+            x[k] = reparam(eps, a.rp_mean[b * S_DIM + k], a.rp_logvar[b * S_DIM + k]);
+        }
+    }
+    mlp_l0_row<10, 256>(x, w.po_w0t, w.po_b0, a.nk, a.map.site[set], b, sample, valid, row, rows_pad, out);
+}
+
+// tail: K-blocked hi/lo input [plane][K/8][rows_pad][8] -> 20 outputs per row (bias included)
+template <int K>
+__device__ __forceinline__ void tail20_row(const unsigned short* __restrict__ in, size_t rows_pad, int row,
+                                           const float* ws /*smem [20][K]*/, const float* __restrict__ bias, float (&o)[20]) {
+    const size_t plane = (size_t)(K / 8) * rows_pad * 8;
+#pragma unroll
+    for (int n = 0; n < 20; ++n) o[n] = __ldg(bias + n);
+    for (int kc = 0; kc < K / 8; ++kc) {
+        const uint4 h = *reinterpret_cast<const uint4*>(in + ((size_t)kc * rows_pad + row) * 8);
+        const uint4 l = *reinterpret_cast<const uint4*>(in + plane + ((size_t)kc * rows_pad + row) * 8);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            x[2 * e] = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+            x[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int n = 0; n < 20; ++n) {
+            const float4 w0 = *reinterpret_cast<const float4*>(ws + n * K + kc * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(ws + n * K + kc * 8 + 4);
+            o[n] = fmaf(x[0], w0.x, o[n]); o[n] = fmaf(x[1], w0.y, o[n]); o[n] = fmaf(x[2], w0.z, o[n]); o[n] = fmaf(x[3], w0.w, o[n]);
+            o[n] = fmaf(x[4], w1.x, o[n]); o[n] = fmaf(x[5], w1.y, o[n]); o[n] = fmaf(x[6], w1.z, o[n]); o[n] = fmaf(x[7], w1.w, o[n]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ps_tail(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, const unsigned short* in) {
+    extern __shared__ __align__(16) float tail_ws[];
+    for (int i = threadIdx.x; i < 20 * 512; i += 128) tail_ws[i] = w.ps_w3[i];
+    __syncthreads();
+    const int rows = (a.nA + a.nB) * a.B;
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= rows) return;
+    float o[20];
+    tail20_row<512>(in, rows_pad, row, tail_ws, w.ps_b3, o);
+    int site, b;
+    uint32_t sample;
+    nr.decode(row, site, b, sample);
+    const int q = row / a.B;
+    const int set = q < a.nA ? 0 : 1;
+    const int slot = set == 0 ? q : q - a.nA;
+#pragma unroll
+    for (int d = 0; d < S_DIM; ++d) {
+        const float mean = o[d], lv = o[S_DIM + d];
+        const float eps = noise_normal(a.nk, (uint32_t)(site + 3), (uint32_t)d, (uint32_t)b, sample);
+        const float s = reparam(eps, mean, lv);
+        const size_t oo = ((size_t)slot * a.B + b) * S_DIM + d;
+        if (set == 0) {
+            a.meanA[oo] = mean; a.logvarA[oo] = lv; if (a.sampA) a.sampA[oo] = s;
+        } else {
+            if (a.meanB) a.meanB[oo] = mean;
+            if (a.logvarB) a.logvarB[oo] = lv;
+            if (a.sampB) a.sampB[oo] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_qs_tail(DevWeights w, QsArgs a, size_t rows_pad, const unsigned short* in) {
+    extern __shared__ __align__(16) float tail_ws[];
+    for (int i = threadIdx.x; i < 20 * 256; i += 128) tail_ws[i] = w.qf3[i];
+    __syncthreads();
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= a.rows) return;
+    float o[20];
+    tail20_row<256>(in, rows_pad, row, tail_ws, w.qf3_b, o);
+    int set, slot, b;
+    a.map.decode(row, set, slot, b);
+    const uint32_t sample = a.map.sample_of(slot);
+#pragma unroll
+    for (int d = 0; d < S_DIM; ++d) {
+        const float mean = o[d], lv = o[S_DIM + d];
+        const size_t oo = (size_t)row * S_DIM + d;
+        a.mean[oo] = mean; a.logvar[oo] = lv;
+        if (a.samp) {
+            const float eps = noise_normal(a.nk, (uint32_t)(a.map.site[0] + 3), (uint32_t)d, (uint32_t)b, sample);
+            a.samp[oo] = reparam(eps, mean, lv);
+        }
+    }
+}
+
+NoiseRows ps_noise_rows(const PsArgs& a) {
+    NoiseRows nr{};
+    nr.B = a.B;
+    nr.set_end[0] = a.nA * a.B; nr.set_end[1] = (a.nA + a.nB) * a.B; nr.set_end[2] = nr.set_end[1];
+    nr.site[0] = a.siteA; nr.site[1] = a.siteB; nr.site[2] = a.siteB;
+    nr.sample0 = a.sample0; nr.extra_slot = a.extra_slot; nr.extra_sample = a.extra_sample;
+    return nr;
+}
+
+NoiseRows map_noise_rows(const RowMap& m) {
+    NoiseRows nr{};
+    nr.B = m.B;
+    for (int i = 0; i < 3; ++i) { nr.set_end[i] = (i < m.nsets ? i + 1 : m.nsets) * m.Sl * m.B; nr.site[i] = m.site[i < m.nsets ? i : m.nsets - 1]; }
+    nr.sample0 = m.sample0; nr.extra_slot = -1; nr.extra_sample = 0;
+    return nr;
+}
+
+int launch_ps_l0(const DevWeights& w, const PsArgs& a, size_t rows_pad, void* out, cudaStream_t st) {
+    const int rows = (a.nA + a.nB) * a.B;
+    if (rows <= 0) return 0;
+    k_ps_l0<<<(rows + 31) / 32, 256, 0, st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<unsigned short*>(out));
+    return 1;
+}
+
+int launch_ps_tail(const DevWeights& w, const PsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
+    const int rows = (a.nA + a.nB) * a.B;
+    if (rows <= 0) return 0;
+    k_ps_tail<<<(rows + 127) / 128, 128, 20 * 512 * sizeof(float), st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<const unsigned short*>(in));
+    return 1;
+}
+
+int launch_po_l0(const DevWeights& w, const PoFcArgs& a, size_t rows_pad, void* out, cudaStream_t st) {
+    const int rows = a.map.rows();
+    if (rows <= 0) return 0;
+    k_po_l0<<<(rows + 31) / 32, 256, 0, st>>>(w, a, rows_pad, static_cast<unsigned short*>(out));
+    return 1;
+}
+
+int launch_qs_tail20(const DevWeights& w, const QsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
+    if (a.rows <= 0) return 0;
+    k_qs_tail<<<(a.rows + 127) / 128, 128, 20 * 256 * sizeof(float), st>>>(w, a, rows_pad, static_cast<const unsigned short*>(in));
+    return 1;
+}
+
+// conv4 (7,7,64) -> (3,3,64) on CUDA cores, written as the K-blocked operand (K = 576, NHWC flatten) of the dense FC1
+int launch_qs_conv4_kblocked(const DevWeights& w, const float* c3, int rows, size_t rows_pad, void* out, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    ConvGeom g{};
+    g.mode = 3; g.M = rows * 9; g.Hm = 3; g.Wm = 3; g.Hin = 7; g.Win = 7; g.Cin = 64;
+    g.Hout = 3; g.Wout = 3; g.Cout = 64; g.in = c3; g.W = w.qc4_w; g.bias = w.qc4_b; g.out = nullptr;
+    g.out_kblocked = static_cast<unsigned short*>(out); g.rows_pad = rows_pad;
+    return launch_gemm<64, 64>(g, 1, st);
 }
 
 // ======================================================================================

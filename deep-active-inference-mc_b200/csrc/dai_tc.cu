@@ -546,100 +546,114 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------
-// FC4 (256 -> 16384, the decoder's widest layer) as a tcgen05 GEMM: tile 128 rows x 256 columns,
-// K = 256 in 4 chunks of 64.  A = h3 in K-blocked bf16 hi/lo [plane][kc 32][rows_pad][8] (written by
-// k_po_fc123), B = weights pre-packed per (n-tile, k-chunk) in the UMMA no-swizzle layout; both
-// arrive by plain bulk copies (UBLKCP).  Epilogue: bias + ReLU + MC-dropout bit + hi/lo split ->
-// channel-blocked activation planes for ct1.
+// Dense layers as tcgen05 GEMMs: tile 128 rows x NT columns, K in chunks of 64 through a 2-3 stage
+// ring.  A = activations in K-blocked bf16 hi/lo planes [plane][K/8][rows_pad][8], B = weights
+// pre-packed per (n-tile, k-chunk) in the UMMA no-swizzle layout; both arrive by plain bulk copies
+// (UBLKCP).  Two epilogues:
+//   FC4    (256 -> 16384, NT = 256): bias + ReLU + MC-dropout bit (from the permuted bit planes) +
+//          hi/lo split -> channel-blocked activation planes for ct1;
+//   HIDDEN (512->512, 256->256, 576->256; NT = 128): bias + ReLU + MC-dropout bit generated in-register
+//          from the keyed Philox stream + hi/lo split -> K-blocked planes for the next dense layer.
 // ---------------------------------------------------------------------------------------
-struct Fc4Params {
-    const __nv_bfloat16* a;      // h3 blocked, already offset to the chunk's first row
+struct DenseParams {
+    const __nv_bfloat16* a;      // K-blocked input, already offset to the launch's first row
     size_t a_kc_stride;          // elements between kc planes  (rows_pad * 8)
-    size_t a_plane;              // elements between hi and lo  (32 * rows_pad * 8)
-    const uint8_t* wpack;        // [n_tile 64][k_chunk 4] blocks of FC4_B_BYTES
-    const float* bias;           // [16384] NHWC-permuted
-    const uint32_t* mask;        // [nrows][512] dropout bits in NHWC order, or null (eval mode)
-    __nv_bfloat16* out;          // blocked [plane][nrows][kc 8][256 px][8]
-    int32_t nrows, nprod;
+    size_t a_plane;              // elements between hi and lo  (K/8 * rows_pad * 8)
+    const uint8_t* wpack;        // [n_tile][k_chunk] blocks of NT*256 bytes
+    const float* bias;
+    int32_t nrows, nprod, kchunks, ntn;
+    // FC4 epilogue
+    const uint32_t* mask;        // [nrows][512] dropout bits in the GEMM's column order, or null (eval mode)
+    __nv_bfloat16* out;          // FC4: blocked [plane][nrows][kc 8][256 px][8]; HIDDEN: K-blocked [plane][N/8][rows_pad][8]
+    // HIDDEN epilogue
+    size_t out_kc_stride, out_plane;
+    NoiseKey nk;
+    NoiseRows nr;
+    int32_t layer;               // dropout site = nr.site[set] + layer
 };
 
-constexpr int FC4_NS = 2;                          // pipeline stages
-constexpr int FC4_A_BYTES = 2 * 8 * 128 * 16;      // 32 KB: hi+lo, 8 kc, 128 rows
-constexpr int FC4_B_BYTES = 2 * 8 * 256 * 16;      // 64 KB: hi+lo, 8 kc, 256 columns
-constexpr int FC4_STAGE = FC4_A_BYTES + FC4_B_BYTES;
-constexpr int FC4_SMEM = FC4_NS * FC4_STAGE + 2048;
-constexpr int FC4_THREADS = 128 + 256;             // 8 epilogue warps
+template <int NT, bool HIDDEN>
+struct DenseCfg {
+    static constexpr int NS = NT == 256 ? 2 : 3;            // pipeline stages
+    static constexpr int A_BYTES = 2 * 8 * 128 * 16;        // 32 KB: hi+lo, 8 kc, 128 rows
+    static constexpr int B_BYTES = 2 * 8 * NT * 16;         // hi+lo, 8 kc, NT columns
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int SMEM = NS * STAGE + 1024;
+    static constexpr int THREADS = 128 + 256;               // 8 epilogue warps
+};
 
-__global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
+template <int NT, bool HIDDEN>
+__global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
+    using D = DenseCfg<NT, HIDDEN>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FC4_NS * FC4_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D::NS * D::STAGE);
     uint64_t* full = bars;                 // [NS]
-    uint64_t* empty = full + FC4_NS;       // [NS]
-    uint64_t* acc_full = empty + FC4_NS;   // [2]
+    uint64_t* empty = full + D::NS;        // [NS]
+    uint64_t* acc_full = empty + D::NS;    // [2]
     uint64_t* acc_empty = acc_full + 2;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* sbias = reinterpret_cast<float*>(tmem_slot + 2);      // [256] of the current n-tile (per accumulator buffer: [2][256])
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < FC4_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < D::NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * NT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int mtiles = (p.nrows + 127) / 128;
-    const int ntiles = mtiles * 64;
+    const int ntiles = mtiles * p.ntn;
+    const int nplanes = p.nprod == 3 ? 2 : 1;
 
     if (warp == 0) {
         if (lane == 0) {
             int cnt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int nt = tile / mtiles, mt = tile % mtiles;
-                for (int kch = 0; kch < 4; ++kch, ++cnt) {
-                    const int s = cnt % FC4_NS;
-                    const uint32_t ph = (uint32_t)(cnt / FC4_NS) & 1u;
+                for (int kch = 0; kch < p.kchunks; ++kch, ++cnt) {
+                    const int s = cnt % D::NS;
+                    const uint32_t ph = (uint32_t)(cnt / D::NS) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
-                    uint8_t* sa = smem + (size_t)s * FC4_STAGE;
-                    uint8_t* sb = sa + FC4_A_BYTES;
-                    mbar_expect_tx(&full[s], FC4_STAGE);
-                    for (int pl = 0; pl < 2; ++pl)
+                    uint8_t* sa = smem + (size_t)s * D::STAGE;
+                    uint8_t* sb = sa + D::A_BYTES;
+                    mbar_expect_tx(&full[s], nplanes == 2 ? D::STAGE : D::STAGE / 2);
+                    for (int pl = 0; pl < nplanes; ++pl)
                         for (int kc = 0; kc < 8; ++kc)
                             bulk_load(sa + (pl * 8 + kc) * 2048,
                                       p.a + pl * p.a_plane + (size_t)(kch * 8 + kc) * p.a_kc_stride + (size_t)mt * 128 * 8, 2048, &full[s]);
-                    const uint8_t* wsrc = p.wpack + ((size_t)nt * 4 + kch) * FC4_B_BYTES;
-                    for (int off = 0; off < FC4_B_BYTES; off += 8192) bulk_load(sb + off, wsrc + off, 8192, &full[s]);
+                    const uint8_t* wsrc = p.wpack + ((size_t)nt * p.kchunks + kch) * D::B_BYTES;
+                    for (int off = 0; off < (nplanes == 2 ? D::B_BYTES : D::B_BYTES / 2); off += 4096) bulk_load(sb + off, wsrc + off, 4096, &full[s]);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(256);
+            const uint32_t idesc = umma_idesc(NT);
             int it = 0, cnt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 const uint32_t aph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&acc_empty[buf], aph ^ 1u);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(buf * 256);
-                for (int kch = 0; kch < 4; ++kch, ++cnt) {
-                    const int s = cnt % FC4_NS;
-                    const uint32_t ph = (uint32_t)(cnt / FC4_NS) & 1u;
+                const uint32_t d = tmem_base + (uint32_t)(buf * NT);
+                for (int kch = 0; kch < p.kchunks; ++kch, ++cnt) {
+                    const int s = cnt % D::NS;
+                    const uint32_t ph = (uint32_t)(cnt / D::NS) & 1u;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem + (size_t)s * FC4_STAGE);
-                    const uint32_t b_base = a_base + FC4_A_BYTES;
+                    const uint32_t a_base = smem_u32(smem + (size_t)s * D::STAGE);
+                    const uint32_t b_base = a_base + D::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t a_hi = umma_desc(a_base + (uint32_t)(2 * k) * 2048u, 2048, 128);
-                        const uint64_t a_lo = umma_desc(a_base + 16384u + (uint32_t)(2 * k) * 2048u, 2048, 128);
-                        const uint64_t b_hi = umma_desc(b_base + (uint32_t)(2 * k) * 4096u, 4096, 128);
-                        const uint64_t b_lo = umma_desc(b_base + 32768u + (uint32_t)(2 * k) * 4096u, 4096, 128);
+                        const uint64_t b_hi = umma_desc(b_base + (uint32_t)(2 * k) * (NT * 16u), NT * 16u, 128);
                         umma_bf16(d, a_hi, b_hi, idesc, (kch == 0 && k == 0) ? 0u : 1u);
-                        if (p.nprod == 3) {
+                        if (nplanes == 2) {
+                            const uint64_t a_lo = umma_desc(a_base + 16384u + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                            const uint64_t b_lo = umma_desc(b_base + 8u * NT * 16u + (uint32_t)(2 * k) * (NT * 16u), NT * 16u, 128);
                             umma_bf16(d, a_lo, b_hi, idesc, 1u);
                             umma_bf16(d, a_hi, b_lo, idesc, 1u);
                         }
@@ -652,7 +666,6 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
     } else if (warp >= 4) {
         const int ew = warp & 3, half = (warp - 4) >> 2;       // lane quarter; column half of the tile
         const int m = ew * 32 + lane;
-        const size_t plane = (size_t)p.nrows * 16384;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
@@ -661,18 +674,30 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
             const int row = mt * 128 + m;
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
-            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 256 + half * 128);
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * NT + half * (NT / 2));
+            uint4 drop = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            float sc = 1.0f;
+            if (HIDDEN && p.nk.training && row < p.nrows) {
+                int site, b;
+                uint32_t sample;
+                p.nr.decode(row, site, b, sample);
+                // NT = 128: the tile is exactly one 128-bit Philox block of this row's mask at this layer
+                drop = noise_block(p.nk, (uint32_t)(site + p.layer), (uint32_t)nt, (uint32_t)b, sample);
+                sc = 2.0f;
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < NT / 2; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tbase + c0, r);
-                if (row < p.nrows) {
-                    // GEMM column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel
+                if (row >= p.nrows) continue;
+                const int n0 = nt * NT + half * (NT / 2) + c0;
+                if (!HIDDEN) {
+                    // FC4 column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel
                     // 8*kc + e.  A 256-column tile is one group of 4 pixels x 64 channels and the 32 columns loaded here
                     // are 4 pixels x 8 channels of one kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores.
-                    const int n0 = nt * 256 + half * 128 + c0;
+                    const size_t plane = (size_t)p.nrows * 16384;
                     const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
-                    const float sc = p.mask ? 2.0f : 1.0f;
+                    const float s2 = p.mask ? 2.0f : 1.0f;
                     const int kc = (n0 >> 5) & 7;
                     uint32_t hi[4][4], lo[4][4];
 #pragma unroll
@@ -681,13 +706,29 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
                         for (int e = 0; e < 4; ++e) {
                             const int j0 = pl * 8 + 2 * e, j1 = j0 + 1;
                             split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
-                                   ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[pl][e], lo[pl][e]);
+                                   ((mw >> j0) & 1u) ? s2 : 0.0f, ((mw >> j1) & 1u) ? s2 : 0.0f, hi[pl][e], lo[pl][e]);
                         }
                     const size_t o = (((size_t)row * 8 + kc) * 256 + nt * 4) * 8;
                     st_global_256(p.out + o, hi[0], hi[1]);
                     st_global_256(p.out + o + 16, hi[2], hi[3]);
                     st_global_256(p.out + plane + o, lo[0], lo[1]);
                     st_global_256(p.out + plane + o + 16, lo[2], lo[3]);
+                } else {
+                    const int wsel = (half * (NT / 2) + c0) >> 5;       // which 32-bit word of the Philox block
+                    const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j0 = q * 8 + 2 * e, j1 = j0 + 1;
+                            split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
+                                   ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[e], lo[e]);
+                        }
+                        const size_t o = (size_t)((n0 >> 3) + q) * p.out_kc_stride + (size_t)row * 8;
+                        *reinterpret_cast<uint4*>(p.out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(p.out + p.out_plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
                 }
             }
             tc_fence_before();
@@ -697,7 +738,7 @@ __global__ void __launch_bounds__(FC4_THREADS, 1) k_tc_fc4(const Fc4Params p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * NT);
 }
 
 using CfgCt1 = Cfg<TrCt1>;   // 144 KB of weights + 3 x 22.5 KB halo planes
@@ -718,6 +759,9 @@ struct LayerPack {
 struct TcImpl {
     LayerPack ct1, ct2, ct3, qc2, qc3;
     float w4[288];               // po_net.19.weight as [c][tap]
+    uint8_t* dense_w[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // TC_PS1 .. TC_QS2
+    float* dense_b[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int dense_k[7] = {0, 0, 0, 0, 0, 0, 0}, dense_n[7] = {0, 0, 0, 0, 0, 0, 0};
     uint8_t* fc4_wpack = nullptr;
     float* fc4_bias = nullptr;     // po_net.9.bias in the tensor-core FC4's column order
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -921,6 +965,37 @@ int tc_from_blocked(const void* blocked, int rows, int hw, int C, float* nhwc, c
     return 1;
 }
 
+namespace {
+// torch Linear weight (N,K) -> [n_tile = N/128][k_chunk = K/64] blocks of [plane hi|lo][kc 8][128][8] bf16.
+// kperm (optional) maps the GEMM's k index to the reference's input index.
+int pack_dense(TcImpl* im, int which, const std::vector<float>& W, const std::vector<float>& bias, int N, int K, const int* kperm,
+               std::vector<void*>* allocs, std::string* err) {
+    const int ntn = N / 128, kch = K / 64;
+    const size_t blk = (size_t)2 * 8 * 128 * 8;              // elements per block
+    std::vector<uint16_t> host((size_t)ntn * kch * blk);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            const float v = W[(size_t)n * K + (kperm ? kperm[k] : k)];
+            const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+            const size_t o = ((size_t)(n / 128) * kch + k / 64) * blk + ((size_t)((k >> 3) & 7) * 128 + (n & 127)) * 8 + (k & 7);
+            host[o] = hi;
+            host[o + (size_t)8 * 128 * 8] = lo;
+        }
+    void* d = nullptr;
+    if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(dense weights)"; return -1; }
+    allocs->push_back(d);
+    if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(dense weights)"; return -1; }
+    void* db = nullptr;
+    if (cudaMalloc(&db, (size_t)N * 4) != cudaSuccess) { *err = "cudaMalloc(dense bias)"; return -1; }
+    allocs->push_back(db);
+    if (cudaMemcpy(db, bias.data(), (size_t)N * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(dense bias)"; return -1; }
+    im->dense_w[which] = static_cast<uint8_t*>(d);
+    im->dense_b[which] = static_cast<float*>(db);
+    im->dense_k[which] = K; im->dense_n[which] = N;
+    return 0;
+}
+}  // namespace
+
 int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
                     std::string* err) {
     TcImpl* im = static_cast<TcImpl*>(out->impl);
@@ -940,7 +1015,8 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
             cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_fc4, cudaFuncAttributeMaxDynamicSharedMemorySize, FC4_SMEM) != cudaSuccess) {
+            cudaFuncSetAttribute(k_tc_dense<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, false>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dense<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, true>::SMEM) != cudaSuccess) {
             *err = std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(cudaGetLastError());
             return -1;
         }
@@ -949,6 +1025,17 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
     if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, CfgCt1::CONCAT, &im->ct1, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, CfgCt2::CONCAT, &im->ct2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, CfgCt3::CONCAT, &im->ct3, allocs, err) != 0) return -1;
+    {
+        const char* keys[7] = {"ps_net.3", "ps_net.6", "po_net.3", "po_net.6", "qs_net.9", "qs_net.12", "qs_net.15"};
+        const int N[7] = {512, 512, 256, 256, 256, 256, 256}, K[7] = {512, 512, 256, 256, 576, 256, 256};
+        std::vector<int> perm(576);          // encoder FC1: GEMM k = pixel*64 + c (NHWC flatten) <- reference c*9 + pixel
+        for (int px = 0; px < 9; ++px)
+            for (int c = 0; c < 64; ++c) perm[px * 64 + c] = c * 9 + px;
+        for (int i = 0; i < 7; ++i)
+            if (pack_dense(im, i, raw.at(std::string(keys[i]) + ".weight"), raw.at(std::string(keys[i]) + ".bias"), N[i], K[i],
+                           i == TC_QS0 ? perm.data() : nullptr, allocs, err) != 0)
+                return -1;
+    }
     if (build_layer(raw.at("qs_net.2.weight"), 2, 32, 32, false, false, &im->qc2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("qs_net.4.weight"), 2, 32, 64, false, false, &im->qc3, allocs, err) != 0) return -1;
     {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
@@ -967,7 +1054,7 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
                 const float v = W[(size_t)e * 256 + k];
                 const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
                 const int kch = k >> 6, kc = (k >> 3) & 7, ke = k & 7;
-                const size_t blk = ((size_t)nt * 4 + kch) * (FC4_B_BYTES / 2);
+                const size_t blk = ((size_t)nt * 4 + kch) * ((DenseCfg<256, false>::B_BYTES / 2));
                 const size_t o = blk + ((size_t)kc * 256 + nl) * 8 + ke;
                 host[o] = hi;
                 host[o + (size_t)8 * 256 * 8] = lo;
@@ -1008,6 +1095,28 @@ int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer,
     return -1;
 }
 
+// One hidden dense layer (bias + ReLU + keyed dropout) on tensor cores: K-blocked in -> K-blocked out.
+int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* in, void* out, int rows, size_t rows_pad,
+                    const NoiseKey& nk, const NoiseRows& nr, int layer, cudaStream_t st, std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(tw.impl);
+    if (!im || !im->dense_w[which]) { *err = "dense tensor-core weights not packed"; return -1; }
+    const int K = im->dense_k[which], N = im->dense_n[which];
+    DenseParams p{};
+    p.a = static_cast<const __nv_bfloat16*>(in);
+    p.a_kc_stride = rows_pad * 8; p.a_plane = (size_t)(K / 8) * rows_pad * 8;
+    p.wpack = im->dense_w[which]; p.bias = im->dense_b[which];
+    p.nrows = rows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3; p.kchunks = K / 64; p.ntn = N / 128;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.out_kc_stride = rows_pad * 8; p.out_plane = (size_t)(N / 8) * rows_pad * 8;
+    p.nk = nk; p.nr = nr; p.layer = layer;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = ((rows + 127) / 128) * p.ntn;
+    k_tc_dense<128, true><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<128, true>::SMEM, st>>>(p);
+    return 1;
+}
+
 // encoder conv2 + conv3 on tensor cores: c1 = conv1 output in parity-split blocked planes
 // [plane][row][parity 4][kc 4][16][16][8]; c2 = same form of the 15x15x32 map ([..][8][8][8]); c3 = fp32 NHWC (7,7,64)
 int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
@@ -1023,16 +1132,16 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
            const uint32_t* mask, int nrows, void* act0, cudaStream_t st, std::string* err) {
     TcImpl* im = static_cast<TcImpl*>(tw.impl);
     if (!im) { *err = "tensor-core weights not packed"; return -1; }
-    Fc4Params p{};
+    DenseParams p{};
     p.a = static_cast<const __nv_bfloat16*>(h3b) + (size_t)row0 * 8;
     p.a_kc_stride = rows_pad * 8; p.a_plane = 32 * rows_pad * 8;
     p.wpack = im->fc4_wpack; p.bias = im->fc4_bias; p.mask = mask; p.out = static_cast<__nv_bfloat16*>(act0);
-    p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
+    p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3; p.kchunks = 4; p.ntn = 64;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = ((nrows + 127) / 128) * 64;
-    k_tc_fc4<<<ntiles < sms ? ntiles : sms, FC4_THREADS, FC4_SMEM, st>>>(p);
+    k_tc_dense<256, false><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, false>::SMEM, st>>>(p);
     return 1;
 }
 

@@ -42,6 +42,13 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
                      const uint32_t* mask, int nrows, void* act0, void* act1, void* act2, void* act3, const Ct4Args& c4,
                      cudaStream_t st, std::string* err, LayerTimer* timer = nullptr);
 
+// Hidden dense layers served by the tensor-core dense kernel
+enum { TC_PS1 = 0, TC_PS2, TC_PO1, TC_PO2, TC_QS0, TC_QS1, TC_QS2 };
+// bias + ReLU + keyed dropout (site of the row's set + layer); in/out are K-blocked bf16 hi/lo planes
+// [plane][K/8][rows_pad][8].  Returns launches or -1.
+int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* in, void* out, int rows, size_t rows_pad,
+                    const NoiseKey& nk, const NoiseRows& nr, int layer, cudaStream_t st, std::string* err);
+
 // Encoder conv2 (32->32, 31x31->15x15) and conv3 (32->64, 15x15->7x7) on tensor cores.  c1 / c2 are parity-split
 // channel-blocked bf16 hi/lo planes, c3 is fp32 NHWC (rows,7,7,64).  Returns launches or -1.
 int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,

@@ -61,11 +61,69 @@ __global__ void probe(int n, int mode, int iters, long long* out, int a_shift, i
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+__global__ void probe_commit(int n, int per, int ncommit, int tiles, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[8];
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tslot;
+    if (threadIdx.x == 0) {
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + 65536;
+        const uint32_t idesc = umma_idesc(n);
+        const uint64_t a = umma_desc(a0, 2048, 128), b = umma_desc(b0, (uint32_t)n * 16u, 128);
+        const long long t0 = clock64();
+        for (int t = 0; t < tiles; ++t) {
+            for (int i = 0; i < per; ++i) umma(tmem + (uint32_t)((t & 1) * 256), a, b, idesc, i > 0 ? 1u : 0u);
+            for (int c = 0; c < ncommit; ++c)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[c])) : "memory");
+            // barriers complete a phase per commit (count 1): nobody waits on them here
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[7])) : "memory");
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&bars[7])) : "memory");
+        }
+        out[0] = t1 - t0;
+        out[1] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
 int main() {
     long long* d;
-    cudaMalloc(&d, 8);
+    cudaMalloc(&d, 64);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     const int iters = 4096;
+    cudaFuncSetAttribute(probe_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    printf("commit cost: tiles of `per` MMAs (N=64) followed by k commits; cycles per tile (issue loop | until all done)\n");
+    for (int per : {4, 16, 48}) {
+        for (int nc : {0, 1, 3}) {
+            long long h[2];
+            for (int rep = 0; rep < 2; ++rep) {
+                probe_commit<<<1, 128, 160 * 1024>>>(64, per, nc, 256, d);
+                cudaDeviceSynchronize();
+                cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+            }
+            printf("per %3d commits %d: issue %8.1f  total %8.1f   (MMA-only model %d)\n", per, nc, h[0] / 256.0, h[1] / 256.0, per * 48);
+        }
+    }
     printf("all-SM contention: cycles per MMA (max over CTAs) vs grid size\n%5s %6s %12s\n", "N", "grid", "cyc/MMA");
     long long* dd; cudaMalloc(&dd, 8 * 512);
     for (int n : {32, 64, 128, 256}) {
