@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// one lane of a CONVERGED warp (the issue pattern the compiler turns into a single predicated UTCHMMA; issuing from
+// inside `if (lane == 0)` instead costs ~10 extra predicate / branch instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -91,6 +98,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, M = 128, K = 16, bf16 x bf16 -> f32
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one())
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -100,6 +108,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 // arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if (elect_one())
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // this warp's 32 lanes x 32 consecutive fp32 columns
@@ -205,7 +214,8 @@ struct Cfg : T {
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
     static constexpr int W_BYTES = 9 * T::NPH * T::KCIN * 32;  // all 9 taps, hi + lo, resident
     static constexpr int SMEM_A = T::NA * PLANE_A;
-    static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + 1024; // + barriers, tmem slot, bias
+    static constexpr int SMEM_TAIL = T::OUT == OUT_PROJ ? 3072 : 1024;   // barriers, tmem slot, bias (+ projection weights)
+    static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + SMEM_TAIL;
 };
 
 // relu(acc + bias) for two neighbouring channels -> packed bf16 hi pair and lo pair (x = hi + lo)
@@ -227,8 +237,10 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&a)[4], c
 }
 
 // ---------------------------------------------------------------------------------------
-// the kernel: warp 0 = halo TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 = weight loader (once), warps 4..11 = epilogue (TMEM -> registers -> HBM).
+// the kernel: warps 0..7 = epilogue (TMEM -> registers -> HBM; TMEM lane quarter = warp % 4), then
+// warp 8 = halo TMA producer, warp 9 = MMA issuer, warp 10 = TMEM allocator, warp 11 = weight loader (once).
+// The single-thread roles sit in the HIGHEST warp ids on purpose: the warp scheduler favours higher warp ids among
+// eligible warps, and an MMA issuer that loses arbitration to the FFMA-heavy epilogue warps starves the tensor pipe.
 // Per tile the issuer makes two passes over the tap units: pass 1 on the hi plane of the halo
 // (A_hi*B_hi, A_hi*B_lo), pass 2 on the lo plane (A_lo*B_hi); the planes travel through the ring
 // separately so three 20 KB slots are enough to keep the next tile's data in flight.
@@ -246,8 +258,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     uint64_t* w_full = acc_empty + C::NACC;   // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [NPH]
+    float* sw4 = sbias + 64;                                  // ct3 only: [32 c][12] (9 taps + pad), 16-byte rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int W_PROD = C::EPI_WARPS, W_MMA = C::EPI_WARPS + 1, W_ALLOC = C::EPI_WARPS + 2, W_WGT = C::EPI_WARPS + 3;
     const int nplanes = p.nprod == 3 ? 2 : 1;
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -255,15 +269,17 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
         mbar_init(w_full, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
-    if (threadIdx.x >= 128 && threadIdx.x < 128 + C::NPH) sbias[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
+    if (warp == W_ALLOC) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (threadIdx.x < C::NPH) sbias[threadIdx.x] = p.bias[threadIdx.x];
+    if (C::OUT == OUT_PROJ && threadIdx.x < 32)
+        for (int t9 = 0; t9 < 12; ++t9) sw4[threadIdx.x * 12 + t9] = t9 < 9 ? p.w4[threadIdx.x * 9 + t9] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int ntiles = p.nrows * C::TILES;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ===== halo producer: one TMA box per (tile, plane) =====
         if (lane == 0) {
             int cnt = 0;
@@ -280,15 +296,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                 }
             }
         }
-    } else if (warp == 3) {
+    } else if (warp == W_WGT) {
         // ===== weights: all taps, once =====
         if (lane == 0) {
             mbar_expect_tx(w_full, C::W_BYTES);
             for (int off = 0; off < C::W_BYTES; off += 4096) bulk_load(smW + off, p.wpack + off, 4096, w_full);
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+    } else if (warp == W_MMA) {
+        // ===== MMA issuer: the whole warp runs the loop converged, one elected lane issues =====
+        {
             mbar_wait(w_full, 0);
             tc_fence_after();
             int it = 0, cnt = 0;
@@ -354,26 +370,30 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;     // hi -> lo plane of this weight block
                         const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
                         const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
+                        // Descriptors advance along K by adding to their 14-bit address field (shared memory is
+                        // < 256 KB, so no carry leaves the field): a couple of integer adds per MMA keep the issuing
+                        // thread cheap — it shares its scheduler with two FFMA-heavy epilogue warps.
+                        const uint32_t bk = C::CONCAT ? 2u * n * 16u : n * 16u;   // bytes between kc planes of the block
+                        uint64_t a_hi = umma_desc(a_hi_base + a_off, C::KC_STRIDE, C::HX * 16);
+                        uint64_t a_lo = umma_desc(a_lo_base + a_off, C::KC_STRIDE, C::HX * 16);
+                        uint64_t b_hi = umma_desc(w_base, bk, 128);
+                        uint64_t b_lo = umma_desc(w_base + b_plane, bk, 128);
+                        const uint64_t a_step = (uint64_t)((2u * C::KC_STRIDE) >> 4), b_step = (uint64_t)((2u * bk) >> 4);
+                        const uint32_t idesc2 = umma_idesc(2 * un.n);
 #pragma unroll
                         for (int k = 0; k < C::KSTEPS; ++k) {
-                            const uint64_t a_hi = umma_desc(a_hi_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
+                            const uint32_t acc0 = (un.init && k == 0) ? 0u : 1u;
                             if (C::CONCAT && nplanes == 2) {
-                                // block = [kc][2n rows: hi then lo][8]
-                                const uint64_t b_all = umma_desc(w_base + (uint32_t)(2 * k) * 2u * n * 16u, 2u * n * 16u, 128);
-                                const uint64_t a_lo = umma_desc(a_lo_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                                umma_bf16(d, a_hi, b_all, umma_idesc(2 * un.n), (un.init && k == 0) ? 0u : 1u);   // [A_hi*B_hi | A_hi*B_lo]
-                                umma_bf16(d, a_lo, b_all, idesc, 1u);                                            // A_lo*B_hi (first n rows)
+                                umma_bf16(d, a_hi, b_hi, idesc2, acc0);     // [A_hi*B_hi | A_hi*B_lo]  (block = hi rows, lo rows)
+                                umma_bf16(d, a_lo, b_hi, idesc, 1u);        // A_lo*B_hi (first n rows)
                             } else {
-                                const uint32_t kstep = C::CONCAT ? 2u * n * 16u : n * 16u;
-                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * kstep, kstep, 128);
-                                umma_bf16(d, a_hi, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);
+                                umma_bf16(d, a_hi, b_hi, idesc, acc0);
                                 if (nplanes == 2) {
-                                    const uint64_t a_lo = umma_desc(a_lo_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                                    const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
                                     umma_bf16(d, a_lo, b_hi, idesc, 1u);
                                     umma_bf16(d, a_hi, b_lo, idesc, 1u);
                                 }
                             }
+                            a_hi += a_step; a_lo += a_step; b_hi += b_step; b_lo += b_step;
                         }
                     }
                     umma_commit(&a_empty[s0]);
@@ -381,15 +401,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                 }
                 umma_commit(&acc_full[buf]);
             }
-            if (p.counters) {
+            if (p.counters && lane == 0) {
                 long long* c = p.counters + (size_t)blockIdx.x * 8;
                 c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = it;
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < C::EPI_WARPS) {
         // ===== epilogue: lane = pixel of the tile; `half` = which half of the tile's outputs this warp owns =====
         const int ew = warp & 3;                  // the TMEM lane quarter this warp may read
-        const int grp = (warp - 4) >> 2;          // 0..EPI_WARPS/4-1
+        const int grp = warp >> 2;          // 0..EPI_WARPS/4-1
         const int half = grp & 1;
         const int m = ew * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
@@ -470,6 +490,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     uint32_t rl[32], rr[32];
                     tmem_ld32(tbase + slot_l * 32, rl);
                     tmem_ld32(tbase + slot_r * 32, rr);
+                    if (p.dbg & 8) {       // experiment: TMEM loads only
+                        if (rl[0] == 0x12345678u && rr[5] == 0x9abcdef0u) out[o] = 1.0f;
+                    } else
                     if (C::EPI_WARPS == 16 && (grp >> 1) == 1) {
                         float dl[4], dr[4];
 #pragma unroll
@@ -496,15 +519,23 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         for (int c = 0; c < 32; ++c) {
                             const float vl = fmaxf(__uint_as_float(rl[c]) + sbias[c], 0.0f);
                             const float vr = fmaxf(__uint_as_float(rr[c]) + sbias[c], 0.0f);
+                            // the 9 tap weights of channel c: three broadcast 128-bit shared loads
+                            const float4 wa = *reinterpret_cast<const float4*>(sw4 + c * 12);
+                            const float4 wb = *reinterpret_cast<const float4*>(sw4 + c * 12 + 4);
+                            const float4 wc = *reinterpret_cast<const float4*>(sw4 + c * 12 + 8);
+                            const float wv[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
                             for (int t9 = 0; t9 < NT; ++t9) {
-                                dl[t9] = fmaf(vl, p.w4[c * 9 + t9], dl[t9]);
-                                dr[t9] = fmaf(vr, p.w4[c * 9 + t9], dr[t9]);
+                                dl[t9] = fmaf(vl, wv[t9], dl[t9]);
+                                dr[t9] = fmaf(vr, wv[t9], dr[t9]);
                             }
                         }
+                        if ((p.dbg & 4) && dl[0] != 123.456f) {
+                        } else {
 #pragma unroll
                         for (int t9 = 0; t9 < NT; ++t9)
                             *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                        }
                     }
                 } else {
                     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -535,14 +566,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (p.counters && warp == 4 && lane == 0) {
+        if (p.counters && warp == 0 && lane == 0) {
             long long* c = p.counters + (size_t)blockIdx.x * 8;
             c[3] = clock64() - e_begin; c[4] = e_wait;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == W_ALLOC) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -599,7 +630,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 2 * NT);
+    if (warp == 10) tmem_alloc(tmem_slot, 2 * NT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -608,7 +639,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
     const int ntiles = mtiles * p.ntn;
     const int nplanes = p.nprod == 3 ? 2 : 1;
 
-    if (warp == 0) {
+    if (warp == 8) {          // producer (single-thread roles use the highest warp ids: see k_tc_conv)
         if (lane == 0) {
             int cnt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -629,8 +660,8 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == 9) {   // MMA issuer: converged warp, one elected lane issues
+        {
             const uint32_t idesc = umma_idesc(NT);
             int it = 0, cnt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -663,8 +694,8 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                 umma_commit(&acc_full[buf]);
             }
         }
-    } else if (warp >= 4) {
-        const int ew = warp & 3, half = (warp - 4) >> 2;       // lane quarter; column half of the tile
+    } else if (warp < 8) {    // epilogue
+        const int ew = warp & 3, half = warp >> 2;       // lane quarter; column half of the tile
         const int m = ew * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -738,7 +769,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * NT);
+    if (warp == 10) tmem_dealloc(tmem_base, 2 * NT);
 }
 
 using CfgCt1 = Cfg<TrCt1>;   // 144 KB of weights + 3 x 22.5 KB halo planes
