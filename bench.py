@@ -110,6 +110,9 @@ def main():
                          "rollout inside each pair), R*N roots in total [weak]; samples = all ranks split the "
                          "samples of the same R roots [strong]; roots = R independent roots per rank, no collective [weak]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "mcts"],
+                    help="rollout = BASELINE.json configs[1] (default, the bench line); mcts = configs[3]: full planner, "
+                         "30 expansions x N=50 samples x simulation depth 10, reported as decisions/s (extra line, N=1 only)")
     ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -149,6 +152,31 @@ def main():
     model.load_numpy_weights(synthetic.make_weights(0))
     model._sync()
     eng = model._engine
+
+    if args.workload == "mcts":
+        from dai_b200 import mcts as planner
+        prm = planner.MCTS_Params()
+        prm.repeats, prm.threshold, prm.use_means, prm.samples, prm.simulation_depth = 30, 2.0, False, N, T
+        frame = torch.from_numpy(synthetic.make_frames(1, 0))[0, 0]
+        eng.stats(reset=True)
+        times = []
+        for i in range(max(1, args.warmup) + args.steps):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            planner.active_inference_mcts(model, frame, prm, o_shape=(1, 64, 64))
+            torch.cuda.synchronize()
+            if i >= max(1, args.warmup):
+                times.append(time.perf_counter() - t)
+        dt = sum(times) / len(times)
+        print(json.dumps({"metric": "MCTS decisions/sec", "value": 1.0 / dt, "unit": "decisions/s", "n_gpus": 1,
+                          "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "data": "synthetic", "dtype": args.precision,
+                          "expansions_per_s": 31.0 / dt,
+                          "config": {"workload": "full MCTS, 30 expansions x N=%d samples, simulation depth %d "
+                                                 "(BASELINE.json configs[3])" % (N, T), "timing": "host wall clock, "
+                                     "2 host syncs per expansion are inherent in the planner (src/mcts.py:82,188)"},
+                          "gpu_launches": int(eng.stats()["kernel_launches"])}))
+        return
 
     # work split over ranks
     group, frame_seed = None, 0
