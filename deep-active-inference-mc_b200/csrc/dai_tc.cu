@@ -167,7 +167,8 @@ struct ConvParams {
     const uint8_t* wpack;    // packed weights (see pack_layer)
     const float* bias;       // [Cout]
     void* out;               // blocked bf16 planes (ct1, ct2) or projected fp32 planes [row][9][HO][WO] (ct3)
-    float w4[288];           // ct3 only: last deconv's weights [c 32][tap 9] (kernel params = constant bank)
+    float2 w4[288];          // ct3 only: last deconv's weights [c 32][tap 9], each duplicated (w, w) for packed
+                             // fp32x2 FMAs over the (left, right) output pixel pair (kernel params = constant bank)
     int32_t dbg;             // experiments only (env DAI_TC_DBG): 1 = epilogue does no work, 2 = no MMAs issued
     long long* counters;     // experiments only: per CTA {mma_total, mma_wait_acc, mma_wait_a, epi_total, epi_wait, tiles, 0, 0}
 };
@@ -230,6 +231,16 @@ __device__ __forceinline__ void split2(uint32_t r0, uint32_t r1, float b0, float
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// packed fp32x2 FMA (FFMA2): d = a * b + c on both halves
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]),
                  "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
@@ -271,8 +282,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     }
     if (warp == W_ALLOC) tmem_alloc(tmem_slot, C::TMEM_COLS);
     if (threadIdx.x < C::NPH) sbias[threadIdx.x] = p.bias[threadIdx.x];
-    if (C::OUT == OUT_PROJ && threadIdx.x < 32)
-        for (int t9 = 0; t9 < 12; ++t9) sw4[threadIdx.x * 12 + t9] = t9 < 9 ? p.w4[threadIdx.x * 9 + t9] : 0.0f;
+    (void)sw4;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -493,48 +503,25 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     if (p.dbg & 8) {       // experiment: TMEM loads only
                         if (rl[0] == 0x12345678u && rr[5] == 0x9abcdef0u) out[o] = 1.0f;
                     } else
-                    if (C::EPI_WARPS == 16 && (grp >> 1) == 1) {
-                        float dl[4], dr[4];
+                    {
+                        // (left, right) pixel pair per packed fp32x2 FMA: 9 FFMA2 per channel instead of 18 FFMA
+                        unsigned long long acc[9];
 #pragma unroll
-                        for (int t9 = 0; t9 < 4; ++t9) { dl[t9] = 0.0f; dr[t9] = 0.0f; }
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float vl = fmaxf(__uint_as_float(rl[c]) + sbias[c], 0.0f);
-                            const float vr = fmaxf(__uint_as_float(rr[c]) + sbias[c], 0.0f);
-#pragma unroll
-                            for (int t9 = 0; t9 < 4; ++t9) {
-                                dl[t9] = fmaf(vl, p.w4[c * 9 + 5 + t9], dl[t9]);
-                                dr[t9] = fmaf(vr, p.w4[c * 9 + 5 + t9], dr[t9]);
-                            }
-                        }
-#pragma unroll
-                        for (int t9 = 0; t9 < 4; ++t9)
-                            *reinterpret_cast<float2*>(out + (size_t)(5 + t9) * HO * WO + o) = make_float2(dl[t9], dr[t9]);
-                    } else {
-                        constexpr int NT = C::EPI_WARPS == 16 ? 5 : 9;
-                        float dl[NT], dr[NT];
-#pragma unroll
-                        for (int t9 = 0; t9 < NT; ++t9) { dl[t9] = 0.0f; dr[t9] = 0.0f; }
+                        for (int t9 = 0; t9 < 9; ++t9) acc[t9] = 0ull;
+                        const unsigned long long* w4p = reinterpret_cast<const unsigned long long*>(p.w4);
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const float vl = fmaxf(__uint_as_float(rl[c]) + sbias[c], 0.0f);
                             const float vr = fmaxf(__uint_as_float(rr[c]) + sbias[c], 0.0f);
-                            // the 9 tap weights of channel c: three broadcast 128-bit shared loads
-                            const float4 wa = *reinterpret_cast<const float4*>(sw4 + c * 12);
-                            const float4 wb = *reinterpret_cast<const float4*>(sw4 + c * 12 + 4);
-                            const float4 wc = *reinterpret_cast<const float4*>(sw4 + c * 12 + 8);
-                            const float wv[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+                            const unsigned long long v = pack_f32x2(vl, vr);
 #pragma unroll
-                            for (int t9 = 0; t9 < NT; ++t9) {
-                                dl[t9] = fmaf(vl, wv[t9], dl[t9]);
-                                dr[t9] = fmaf(vr, wv[t9], dr[t9]);
-                            }
+                            for (int t9 = 0; t9 < 9; ++t9) acc[t9] = ffma2(v, w4p[c * 9 + t9], acc[t9]);
                         }
-                        if ((p.dbg & 4) && dl[0] != 123.456f) {
+                        if ((p.dbg & 4) && acc[0] == 123ull) {
                         } else {
 #pragma unroll
-                        for (int t9 = 0; t9 < NT; ++t9)
-                            *reinterpret_cast<float2*>(out + (size_t)t9 * HO * WO + o) = make_float2(dl[t9], dr[t9]);
+                        for (int t9 = 0; t9 < 9; ++t9)
+                            *reinterpret_cast<unsigned long long*>(out + (size_t)t9 * HO * WO + o) = acc[t9];
                         }
                     }
                 } else {
@@ -932,7 +919,7 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
     for (int i = 0; i < lp.nunits; ++i) p.units[i] = lp.units[i];
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     p.wpack = lp.wpack; p.bias = bias; p.out = out;
-    if (w4) memcpy(p.w4, w4, sizeof(p.w4));
+    if (w4) for (int i = 0; i < 288; ++i) p.w4[i] = make_float2(w4[i], w4[i]);
     if (const char* e = getenv("DAI_TC_DBG")) p.dbg = atoi(e);
     static long long* dbg_counters = nullptr;
     const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;
