@@ -1071,13 +1071,14 @@ int launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float*
 __device__ __forceinline__ float ent_normal(float lv) { return __fmul_rn(0.5f, __fadd_rn(2.8378770664093453f, lv)); }
 
 __global__ void k_step_finalize(StepFinalizeArgs a) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per (state, action) row b; lanes stride over the MC samples
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= a.B) return;
     const int SB = a.Sl * a.B;
     // per-sample terms are fp32 (as in the reference); their sums over samples / steps / shards are
     // kept in fp64 so that any sample partition adds up to the same value
     double t0 = 0.0, t1 = 0.0, t21 = 0.0, t22 = 0.0;
-    for (int j = 0; j < a.Sl; ++j) {
+    for (int j = lane; j < a.Sl; j += 32) {
         const int r = j * a.B + b;
         t0 += a.reward[r];
         float e = 0.0f;
@@ -1087,16 +1088,24 @@ __global__ void k_step_finalize(StepFinalizeArgs a) {
         t21 += a.hsum[SB + r];
         t22 += a.hsum[2 * SB + r];
     }
-    a.acc[0 * a.B + b] += t0;
-    a.acc[1 * a.B + b] += t1;
-    a.acc[2 * a.B + b] += t21;
-    a.acc[3 * a.B + b] += t22;
-    if (a.carry_src)
-        for (int d = 0; d < S_DIM; ++d) a.carry_dst[b * S_DIM + d] = a.carry_src[b * S_DIM + d];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t21 += __shfl_xor_sync(0xffffffffu, t21, o);
+        t22 += __shfl_xor_sync(0xffffffffu, t22, o);
+    }
+    if (lane == 0) {
+        a.acc[0 * a.B + b] += t0;
+        a.acc[1 * a.B + b] += t1;
+        a.acc[2 * a.B + b] += t21;
+        a.acc[3 * a.B + b] += t22;
+    }
+    if (a.carry_src && lane < S_DIM) a.carry_dst[b * S_DIM + lane] = a.carry_src[b * S_DIM + lane];
 }
 
 int launch_step_finalize(const StepFinalizeArgs& a, cudaStream_t st) {
-    k_step_finalize<<<(a.B + 127) / 128, 128, 0, st>>>(a);
+    k_step_finalize<<<(a.B * 32 + 127) / 128, 128, 0, st>>>(a);
     return 1;
 }
 
