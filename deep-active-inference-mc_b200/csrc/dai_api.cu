@@ -855,6 +855,17 @@ int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use
     return DAI_OK;
 }
 
+int dai_select_actions(dai_handle* h, const float* G, int R, float temperature, float* Ppi, float* logPpi,
+                       int32_t* choice, void* stream) {
+    if (!h) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!G || R <= 0 || !(temperature > 0.0f)) return fail(h, DAI_E_INVALID, "select_actions: bad arguments");
+    const NoiseKey nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    h->launches += launch_select_actions(G, R, temperature, nk, Ppi, logPpi, choice, (cudaStream_t)stream);
+    return post_launch(h, "select_actions");
+}
+
 int dai_profile_begin(dai_handle* h) {
     if (!h) return DAI_E_INVALID;
     for (auto& r : h->timer.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -121,6 +121,8 @@ struct StepFinalizeArgs {
 };
 int  launch_step_finalize(const StepFinalizeArgs& a, cudaStream_t st);
 int  launch_combine(const double* sums, int B, int samples, float* G, float* t0, float* t1, float* t2, cudaStream_t st);
+int  launch_select_actions(const float* G, int R, float temperature, const NoiseKey& nk, float* Ppi, float* logPpi,
+                           int* choice, cudaStream_t st);
 int  launch_reward_only(const float* o, int B, float* r, cudaStream_t st);
 int  launch_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
                    int D, float* G, float* Gmean, cudaStream_t st);

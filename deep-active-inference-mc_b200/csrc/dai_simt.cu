@@ -1127,6 +1127,39 @@ int launch_combine(const double* sums, int B, int samples, float* G, float* t0, 
     return 1;
 }
 
+// softmax_multi_with_log + categorical choice per root (src/util.py:46-53,66-68)
+__global__ void k_select_actions(const float* __restrict__ G, int R, float temperature, NoiseKey nk,
+                                 float* Ppi, float* logPpi, int* choice) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float x[4], e[4], mx = -INFINITY, sum = 0.0f;
+    for (int i = 0; i < 4; ++i) { x[i] = -G[r * 4 + i]; mx = fmaxf(mx, x[i]); }
+    for (int i = 0; i < 4; ++i) { x[i] = x[i] - mx; e[i] = expf(x[i] / temperature); sum = __fadd_rn(sum, e[i]); }
+    const float lse = logf(sum + 1e-20f);
+    float cdf[4], c = 0.0f, p[4];
+    for (int i = 0; i < 4; ++i) {
+        p[i] = e[i] / sum;
+        c = __fadd_rn(c, p[i]);
+        cdf[i] = c;
+        if (Ppi) Ppi[r * 4 + i] = p[i];
+        if (logPpi) logPpi[r * 4 + i] = x[i] - lse;
+    }
+    if (choice) {
+        const float u = noise_uniform24(nk, SITE_CAT, (uint32_t)r, 0);
+        const float thr = __fmul_rn(u, cdf[3]);
+        int a = 3;
+        for (int i = 0; i < 4; ++i) if (thr < cdf[i]) { a = i; break; }
+        choice[r] = a;
+    }
+}
+
+int launch_select_actions(const float* G, int R, float temperature, const NoiseKey& nk, float* Ppi, float* logPpi,
+                          int* choice, cudaStream_t st) {
+    if (R <= 0) return 0;
+    k_select_actions<<<(R + 127) / 128, 128, 0, st>>>(G, R, temperature, nk, Ppi, logPpi, choice);
+    return 1;
+}
+
 // calculate_G_given_trajectory tail (src/torchmodel.py:335-352): rows = depth
 __global__ void k_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
                          int D, float* G, float* Gmean) {

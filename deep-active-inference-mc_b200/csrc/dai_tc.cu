@@ -187,7 +187,12 @@ enum { OUT_BLOCKED = 0, OUT_PROJ = 1, OUT_PARITY = 2, OUT_NHWC_F32 = 3 };
 //            ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times; the hi*lo part lands in a
 //            second column block that the epilogue adds
 struct TrCt1 { static constexpr int MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
-               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = true; };
+               EPI_WARPS = 8, OUT = OUT_BLOCKED;
+#ifdef DAI_CT1_TWO_PASS
+               static constexpr bool TWO_PASS = true, CONCAT = true; };
+#else
+               static constexpr bool TWO_PASS = false, CONCAT = true; };
+#endif
 struct TrCt2 { static constexpr int MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
                EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false; };
 struct TrCt3 { static constexpr int MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 6,
@@ -343,15 +348,20 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 #pragma unroll
                             for (int k = 0; k < C::KSTEPS; ++k) {
                                 const uint64_t a_d = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                const uint32_t bk = C::CONCAT ? 2u * n * 16u : n * 16u;
+                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * bk, bk, 128);
                                 if (pl == 0) {
-                                    umma_bf16(d, a_d, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);      // A_hi * B_hi
-                                    if (nplanes == 2) {
-                                        const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                                        umma_bf16(d, a_d, b_lo, idesc, 1u);                             // A_hi * B_lo
+                                    if (C::CONCAT && nplanes == 2) {
+                                        umma_bf16(d, a_d, b_hi, umma_idesc(2 * un.n), (un.init && k == 0) ? 0u : 1u);   // [A_hi*B_hi | A_hi*B_lo]
+                                    } else {
+                                        umma_bf16(d, a_d, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);      // A_hi * B_hi
+                                        if (nplanes == 2) {
+                                            const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
+                                            umma_bf16(d, a_d, b_lo, idesc, 1u);                             // A_hi * B_lo
+                                        }
                                     }
                                 } else {
-                                    umma_bf16(d, a_d, b_hi, idesc, 1u);                                 // A_lo * B_hi
+                                    umma_bf16(d, a_d, b_hi, idesc, 1u);                                     // A_lo * B_hi
                                 }
                             }
                         }

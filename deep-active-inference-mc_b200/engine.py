@@ -61,6 +61,7 @@ SIGNATURES = {
                                         ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dai_mcts_simulate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                          _vp, _vp, _vp]),
+    "dai_select_actions": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "dai_profile_begin": (ctypes.c_int, [_vp]),
     "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int64), _vp]),
@@ -268,6 +269,15 @@ class Engine:
         self._ck(self.lib.dai_rollout_host(self.h, _p(o_host), _p(pi_host), B, steps, samples, 1 if calc_mean else 0,
                                            1 if four else 0, _p(out_host[0]), _p(out_host[1]), _p(out_host[2]),
                                            _p(out_host[3]), _p(po1_host), self._stream()))
+
+    def select_actions(self, G, temperature=10.0):
+        """G (4R,) -> Ppi (R,4), logPpi (R,4), choice (R,) int32 (src/util.py:46-53,66-68)."""
+        G = self.dev(G).reshape(-1)
+        R = G.shape[0] // 4
+        Ppi, logp = self.new(R, 4), self.new(R, 4)
+        choice = self.new(R, dtype=torch.int32)
+        self._ck(self.lib.dai_select_actions(self.h, _p(G), R, float(temperature), _p(Ppi), _p(logp), _p(choice), self._stream()))
+        return Ppi, logp, choice
 
     def profile_begin(self):
         self._ck(self.lib.dai_profile_begin(self.h))

@@ -253,6 +253,19 @@ class ActiveInferenceModel:
         G, terms = self._finish(out, samples, world)
         return G, terms, out["po1"]
 
+    def select_actions(self, o_roots, steps=1, samples=10, calc_mean=False, temperature=10.0):
+        """Batched many-roots action selection: the model-side core of
+        make_batch_dsprites_active_inference (src/util.py:55-68) with the frames kept on the device.
+        o_roots (R,1,64,64) or (R,64,64,1) -> (pi_choices (R,) int, Ppi (R,4), log_Ppi (R,4), sum_G (4R,), sum_terms)."""
+        self._sync()
+        o = self._engine.dev(o_roots).reshape(-1, 4096)
+        R = o.shape[0]
+        o4 = o.repeat_interleave(4, dim=0)                       # util.py:57  o0.repeat(4, 0)
+        G, terms, _ = self.calculate_G_repeated(o4, torch.eye(4, device=self.device).repeat(R, 1), steps=steps,
+                                                calc_mean=calc_mean, samples=samples)
+        Ppi, logp, choice = self._engine.select_actions(G, temperature)
+        return self._host(choice), self._host(Ppi), self._host(logp), G, terms
+
     def calculate_G_4_repeated(self, o, steps=1, calc_mean=False, samples=10):
         self._sync()
         if calc_mean:       # calculate_G_mean steps have a single sample: nothing to shard

@@ -157,6 +157,14 @@ DAI_API int  dai_rollout_host(dai_handle* h, const float* o_host, const float* p
 DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means,
                        float* G_host, float* pi0, float* qpi, void* stream);
 
+/* ---- next row: batched many-roots action selection -------------------------
+ * The action choice of make_batch_dsprites_active_inference (src/util.py:46-53,66-68) for R roots whose summed EFE
+ * G (4R, row = root*4 + action) is already on the device: per root x = -G - max(-G), e = exp(x / temperature),
+ * Ppi = e / sum(e), logPpi = x - log(sum(e) + 1e-20) (un-tempered, as softmax_multi_with_log returns it), and
+ * choice ~ Categorical(Ppi) drawn from the keyed noise (site CAT, row = root).  1 call index. */
+DAI_API int  dai_select_actions(dai_handle* h, const float* G, int R, float temperature,
+                                float* Ppi, float* logPpi, int32_t* choice, void* stream);
+
 /* ---- per-kernel timing (bench.py's roofline leg) -----------------------------------------
  * Between dai_profile_begin and dai_profile_end every decoder contraction kernel is bracketed by
  * CUDA events on its launch stream.  dai_profile_end waits for the stream and returns, per layer

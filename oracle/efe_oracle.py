@@ -364,6 +364,20 @@ def mcts_step_simulate(W, starting_s, depth, use_means, nz_roll, nz_traj):
     return G, pi0, qpi_ret
 
 
+def select_actions(sum_G, temperature, nz):
+    """The action choice of make_batch_dsprites_active_inference — src/util.py:46-53 (softmax_multi_with_log on
+    -sum_G, including its un-tempered logSM) and :66-68, with the categorical draw taken from the keyed noise
+    (row = root) instead of numpy's global generator."""
+    x = (-sum_G.detach().numpy().astype(np.float32)).reshape(-1, 4)
+    x = x - np.max(x, 1).reshape(-1, 1)
+    e_x = np.exp(x / np.float32(temperature))
+    SM = e_x / e_x.sum(axis=1).reshape(-1, 1)
+    logSM = x - np.log(e_x.sum(axis=1).reshape(-1, 1) + np.float32(1e-20))
+    nz.at(0, 0)
+    choices = np.array([nz.categorical(torch.from_numpy(SM[r]), SITES["CAT"], row=r) for r in range(SM.shape[0])], dtype=np.int32)
+    return SM, logSM, choices
+
+
 # --------------------------------------------------------------------------- reference-shaped model
 
 class _Sub:
@@ -432,6 +446,14 @@ class OracleModel:
 
     def mcts_step_simulate(self, starting_s, depth, use_means=False):
         return mcts_step_simulate(self.W, starting_s, depth, use_means, self._nz(), self._nz())
+
+    def select_actions(self, o_roots, steps=1, samples=10, calc_mean=False, temperature=10.0):
+        o = torch.as_tensor(o_roots).reshape(-1, 1, 64, 64)
+        R = o.shape[0]
+        G, terms, _ = self.calculate_G_repeated(o.repeat_interleave(4, dim=0), torch.eye(4).repeat(R, 1), steps=steps,
+                                                calc_mean=calc_mean, samples=samples)
+        SM, logSM, choices = select_actions(G, temperature, self._nz())
+        return torch.from_numpy(choices), torch.from_numpy(SM), torch.from_numpy(logSM), G, terms
 
     def habitual_net(self, o):
         return qpi_forward(self.W, self.model_down.encoder(o)[0])[1]
