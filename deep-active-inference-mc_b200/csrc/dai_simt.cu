@@ -248,12 +248,20 @@ __global__ void __launch_bounds__(128) k_fc4_mask(RowMap map, NoiseKey nk, int r
                 word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
             }
         } else {                                    // tensor-core FC4 order: column = ((pg*8 + kc)*4 + pl)*8 + ce
-            const int pg = i >> 3, kc = i & 7;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
-                const int e = (kc * 8 + (j & 7)) * 256 + pg * 4 + (j >> 3);
-                word |= ((orig[e >> 5] >> (e & 31)) & 1u) << j;
-            }
+            // bit (pl*8 + ce) <- reference bit e = (kc*8+ce)*256 + pg*4 + pl = nibble (pg & 7) of word (kc*8+ce)*8 + (pg >> 3):
+            // gather the 8 nibbles (ce-major), then transpose the 8x4 bit matrix to 4x8 with three delta swaps
+            const int pg = i >> 3, kc = i & 7, sh = (pg & 7) * 4;
+            uint32_t n = 0;
+#pragma unroll
+            for (int ce = 0; ce < 8; ++ce) n |= ((orig[(kc * 8 + ce) * 8 + (pg >> 3)] >> sh) & 0xfu) << (ce * 4);
+            // n bit (ce*4 + pl) -> word bit (pl*8 + ce)
+            // (index bits c2 c1 c0 p1 p0 -> p1 p0 c2 c1 c0 as four index-bit transpositions)
+            uint32_t t;
+            t = (n ^ (n >> 1)) & 0x22222222u; n ^= t ^ (t << 1);
+            t = (n ^ (n >> 3)) & 0x0a0a0a0au; n ^= t ^ (t << 3);
+            t = (n ^ (n >> 6)) & 0x00cc00ccu; n ^= t ^ (t << 6);
+            t = (n ^ (n >> 12)) & 0x0000f0f0u; n ^= t ^ (t << 12);
+            word = n;
         }
         out[i] = word;
     }
@@ -561,27 +569,37 @@ __global__ void __launch_bounds__(256) k_ct4_gather(DevWeights w, Ct4Args a) {
     const float la_top = logf(d + 1.0f), lb_top = logf(c1 - 1.0f);
     const float la_bot = logf(d + 0.0f), lb_bot = logf(c1 - 0.0f);
     float hacc = 0.0f, racc = 0.0f;
-    for (int i = tid; i < IMG; i += 256) {
-        const int oy = i >> 6, ox = i & 63;
-        float acc = 0.0f;
+    // each thread finishes 4 consecutive pixels: per tap plane one aligned float4 plus the element to its left / right
+    for (int q = tid; q < IMG / 4; q += 256) {
+        const int oy = q >> 4, ox = (q & 15) << 2;
+        float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             const int iy = oy + 1 - kh;
             if (iy < 0 || iy >= 64) continue;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ix = ox + 1 - kw;
-                if (ix < 0 || ix >= 64) continue;
-                acc += __ldg(D + (size_t)(kh * 3 + kw) * IMG + iy * 64 + ix);
-            }
+            const float* rowp = D + (size_t)(kh * 3) * IMG + iy * 64 + ox;
+            // kw = 0 reads ix = ox+1 .. ox+4, kw = 1 reads ox .. ox+3, kw = 2 reads ox-1 .. ox+2
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));                 // plane kw = 0, ix = ox..ox+3
+            const float r0 = ox + 4 < 64 ? __ldg(rowp + 4) : 0.0f;
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp + IMG));           // plane kw = 1
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(rowp + 2 * IMG));       // plane kw = 2
+            const float l2 = ox > 0 ? __ldg(rowp + 2 * IMG - 1) : 0.0f;
+            acc[0] += v0.y + v1.x + l2;
+            acc[1] += v0.z + v1.y + v2.x;
+            acc[2] += v0.w + v1.z + v2.y;
+            acc[3] += r0 + v1.w + v2.z;
         }
-        const float x = acc + bias;
-        const float p = 1.0f / (1.0f + expf(-x));
-        const float q = 1.0f - p;
-        hacc += __fsub_rn(__fmul_rn(-q, logf(c1 - p)), __fmul_rn(p, logf(d + p)));
-        racc += oy < 32 ? __fadd_rn(__fmul_rn(p, la_top), __fmul_rn(q, lb_top))
-                        : __fadd_rn(__fmul_rn(p, la_bot), __fmul_rn(q, lb_bot));
-        if (write_img) a.img[(size_t)r * IMG + i] = p;
+        float pv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float p = 1.0f / (1.0f + expf(-acc[j]));
+            const float qq = 1.0f - p;
+            hacc += __fsub_rn(__fmul_rn(-qq, logf(c1 - p)), __fmul_rn(p, logf(d + p)));
+            racc += oy < 32 ? __fadd_rn(__fmul_rn(p, la_top), __fmul_rn(qq, lb_top))
+                            : __fadd_rn(__fmul_rn(p, la_bot), __fmul_rn(qq, lb_bot));
+            pv[j] = p;
+        }
+        if (write_img) *reinterpret_cast<float4*>(a.img + (size_t)r * IMG + q * 4) = make_float4(pv[0], pv[1], pv[2], pv[3]);
     }
     hacc = warp_sum(hacc); racc = warp_sum(racc);
     if (lane == 0) { red[0][warp] = hacc; red[1][warp] = racc; }
