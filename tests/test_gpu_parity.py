@@ -96,3 +96,51 @@ def test_weight_updates_are_picked_up():
     m.set_rng(5, 0)
     c = m.model_down.decoder(s)
     assert not torch.equal(a, b) and torch.allclose(a, c, atol=1e-6)
+
+
+def test_abi_rejects_bad_arguments_without_crashing():
+    """Every entry point returns a negative code (never throws / aborts) on bad input (include/dai_b200.h)."""
+    import ctypes
+    from dai_b200 import engine
+    m = _model("w0", "bf16x3")
+    m._sync()
+    eng, lib = m._engine, m._engine.lib
+    st = eng._stream()
+    s0 = torch.zeros(4, 10, device="cuda")
+    pi = torch.eye(4, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.dai_calculate_G(eng.h, p(s0), p(pi), 4, 0, 0, 0, None, None, None, None, None, None, None, None, None, st) == -1
+    assert lib.dai_calculate_G(eng.h, p(s0), p(pi), 4, 5, 3, 9, None, None, None, None, None, None, None, None, None, st) == -1
+    assert lib.dai_rollout(eng.h, None, None, 4, 1, 1, 0, 0, 0, 1, None, None, None, None, None, None, st) == -1
+    assert lib.dai_rollout(eng.h, p(torch.zeros(3, 4096, device="cuda")), None, 3, 1, 1, 0, 0, 0, 1, None, None, None, None, None, None, st) == -1
+    assert b"B % 4" in lib.dai_last_error(eng.h)
+    assert lib.dai_set_precision(eng.h, 7) == -1
+    g = ctypes.c_float()
+    assert lib.dai_mcts_simulate(eng.h, p(s0), 0, 0, ctypes.byref(g), p(pi), p(pi), st) == -1
+    with pytest.raises(engine.DaiError):
+        eng.transition(torch.eye(4, device="cuda"), torch.zeros(5, 10, device="cuda"))
+    # a fresh handle without weights refuses to compute
+    fresh = engine.Engine(device="cuda:0")
+    with pytest.raises(engine.DaiError, match="weights"):
+        fresh.decode(torch.zeros(1, 10))
+    fresh.close()
+    # and the handle still works afterwards
+    assert torch.isfinite(m.model_down.decoder(torch.zeros(1, 10))).all()
+
+
+def test_large_batch_and_many_samples_chunking():
+    """More decoder rows than one activation chunk (1024) and more encoder rows than one chunk (2048): chunk
+    boundaries must not change the result — compare a big batched call with the same rows evaluated separately."""
+    m = _model("w0", "bf16x3")
+    eng = m._engine
+    m._sync()
+    s0 = torch.from_numpy(np.random.default_rng(11).standard_normal((8, 10)).astype(np.float32)).cuda()
+    pi = torch.eye(4, device="cuda").repeat(2, 1)
+    eng.set_rng(5, 0)
+    big = eng.calculate_G(s0, pi, 300)             # 3*300*8 = 7200 decoder rows, 2400 encoder rows
+    eng.set_rng(5, 0)
+    a = eng.calculate_G(s0, pi, 300, shard=(0, 100))
+    eng.set_rng(5, 0)
+    b = eng.calculate_G(s0, pi, 300, shard=(100, 300))
+    assert torch.allclose(a["sums"] + b["sums"], big["sums"], rtol=1e-9, atol=1e-6)
+    assert torch.equal(a["ps1"], big["ps1"]) and torch.equal(b["po1"], big["po1"])
