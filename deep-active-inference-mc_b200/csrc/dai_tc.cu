@@ -216,7 +216,9 @@ struct Cfg : T {
     static constexpr int TILES_X = (T::GW + TW - 1) / TW, TILES_Y = (T::GH + TH - 1) / TH;
     static constexpr int TILES = TILES_X * TILES_Y;
     static constexpr int ACC_COLS = (T::MODE == 1 ? 4 * T::NPH : T::NPH) * (T::CONCAT ? 2 : 1);
-    static constexpr int NACC = 2;
+    // accumulator buffers in TMEM: as many as fit (<= 4).  The MMA-complete -> epilogue -> buffer-free round trip is
+    // long compared with a tile's MMA time, so two buffers leave the tensor pipe idle between tiles.
+    static constexpr int NACC = ACC_COLS * 4 <= 512 ? 4 : 2;
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
     static constexpr int W_BYTES = 9 * T::NPH * T::KCIN * 32;  // all 9 taps, hi + lo, resident
     static constexpr int SMEM_A = T::NA * PLANE_A;
