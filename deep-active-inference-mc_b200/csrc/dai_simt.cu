@@ -902,14 +902,24 @@ __global__ void __launch_bounds__(256) k_po_l0(DevWeights w, PoFcArgs a, size_t 
     mlp_l0_row<10, 256>(x, w.po_w0t, w.po_b0, a.nk, a.map.site[set], b, sample, valid, row, rows_pad, out);
 }
 
-// tail: K-blocked hi/lo input [plane][K/8][rows_pad][8] -> 20 outputs per row (bias included)
+// tail: K-blocked hi/lo input [plane][K/8][rows_pad][8] -> 20 outputs per row.
+// A CTA owns TAIL_ROWS rows (lane = row); each of its TAIL_WARPS warps contracts one K slice (the
+// weights of a slice are warp-uniform loads, so they are broadcast from L1 without staging), the
+// slice partials meet in shared memory and are added in slice order (fixed, so the result does not
+// depend on how rows are chunked).  One thread per (row, latent d) then finishes mean/logvar (+ sample).
+constexpr int TAIL_ROWS = 32, TAIL_WARPS = 8, TAIL_NT = TAIL_ROWS * TAIL_WARPS;
+
 template <int K>
-__device__ __forceinline__ void tail20_row(const unsigned short* __restrict__ in, size_t rows_pad, int row,
-                                           const float* ws /*smem [20][K]*/, const float* __restrict__ bias, float (&o)[20]) {
+__device__ __forceinline__ void tail20_partial(const unsigned short* __restrict__ in, size_t rows_pad, int row, int slice,
+                                               const float* __restrict__ W /*[20][K] global*/, float* red /*smem [WARPS][20][ROWS]*/) {
+    constexpr int KC_PER = K / 8 / TAIL_WARPS;
     const size_t plane = (size_t)(K / 8) * rows_pad * 8;
+    float o[20];
 #pragma unroll
-    for (int n = 0; n < 20; ++n) o[n] = __ldg(bias + n);
-    for (int kc = 0; kc < K / 8; ++kc) {
+    for (int n = 0; n < 20; ++n) o[n] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < KC_PER; ++i) {
+        const int kc = slice * KC_PER + i;
         const uint4 h = *reinterpret_cast<const uint4*>(in + ((size_t)kc * rows_pad + row) * 8);
         const uint4 l = *reinterpret_cast<const uint4*>(in + plane + ((size_t)kc * rows_pad + row) * 8);
         const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
@@ -921,32 +931,43 @@ __device__ __forceinline__ void tail20_row(const unsigned short* __restrict__ in
         }
 #pragma unroll
         for (int n = 0; n < 20; ++n) {
-            const float4 w0 = *reinterpret_cast<const float4*>(ws + n * K + kc * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(ws + n * K + kc * 8 + 4);
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + n * K + kc * 8));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + n * K + kc * 8 + 4));
             o[n] = fmaf(x[0], w0.x, o[n]); o[n] = fmaf(x[1], w0.y, o[n]); o[n] = fmaf(x[2], w0.z, o[n]); o[n] = fmaf(x[3], w0.w, o[n]);
             o[n] = fmaf(x[4], w1.x, o[n]); o[n] = fmaf(x[5], w1.y, o[n]); o[n] = fmaf(x[6], w1.z, o[n]); o[n] = fmaf(x[7], w1.w, o[n]);
         }
     }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int n = 0; n < 20; ++n) red[(slice * 20 + n) * TAIL_ROWS + lane] = o[n];
 }
 
-__global__ void __launch_bounds__(128) k_ps_tail(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, const unsigned short* in) {
-    extern __shared__ __align__(16) float tail_ws[];
-    for (int i = threadIdx.x; i < 20 * 512; i += 128) tail_ws[i] = w.ps_w3[i];
-    __syncthreads();
-    const int rows = (a.nA + a.nB) * a.B;
-    const int row = blockIdx.x * 128 + threadIdx.x;
-    if (row >= rows) return;
-    float o[20];
-    tail20_row<512>(in, rows_pad, row, tail_ws, w.ps_b3, o);
-    int site, b;
-    uint32_t sample;
-    nr.decode(row, site, b, sample);
-    const int q = row / a.B;
-    const int set = q < a.nA ? 0 : 1;
-    const int slot = set == 0 ? q : q - a.nA;
+__device__ __forceinline__ float tail20_sum(const float* red, int n, int r, float bias) {
+    float v = bias;
 #pragma unroll
-    for (int d = 0; d < S_DIM; ++d) {
-        const float mean = o[d], lv = o[S_DIM + d];
+    for (int s = 0; s < TAIL_WARPS; ++s) v += red[(s * 20 + n) * TAIL_ROWS + r];
+    return v;
+}
+
+__global__ void __launch_bounds__(TAIL_NT) k_ps_tail(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, const unsigned short* in) {
+    __shared__ float red[TAIL_WARPS * 20 * TAIL_ROWS];
+    const int rows = (a.nA + a.nB) * a.B;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    // rows beyond `rows` lie inside the padded operand (rows_pad >= rows + 128): read, never stored
+    tail20_partial<512>(in, rows_pad, blockIdx.x * TAIL_ROWS + lane, slice, w.ps_w3, red);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TAIL_ROWS * S_DIM; idx += TAIL_NT) {
+        const int r = idx & (TAIL_ROWS - 1), d = idx / TAIL_ROWS;
+        const int row = blockIdx.x * TAIL_ROWS + r;
+        if (row >= rows) continue;
+        const float mean = tail20_sum(red, d, r, __ldg(w.ps_b3 + d));
+        const float lv = tail20_sum(red, S_DIM + d, r, __ldg(w.ps_b3 + S_DIM + d));
+        int site, b;
+        uint32_t sample;
+        nr.decode(row, site, b, sample);
+        const int q = row / a.B;
+        const int set = q < a.nA ? 0 : 1;
+        const int slot = set == 0 ? q : q - a.nA;
         const float eps = noise_normal(a.nk, (uint32_t)(site + 3), (uint32_t)d, (uint32_t)b, sample);
         const float s = reparam(eps, mean, lv);
         const size_t oo = ((size_t)slot * a.B + b) * S_DIM + d;
@@ -960,24 +981,23 @@ __global__ void __launch_bounds__(128) k_ps_tail(DevWeights w, PsArgs a, NoiseRo
     }
 }
 
-__global__ void __launch_bounds__(128) k_qs_tail(DevWeights w, QsArgs a, size_t rows_pad, const unsigned short* in) {
-    extern __shared__ __align__(16) float tail_ws[];
-    for (int i = threadIdx.x; i < 20 * 256; i += 128) tail_ws[i] = w.qf3[i];
+__global__ void __launch_bounds__(TAIL_NT) k_qs_tail(DevWeights w, QsArgs a, size_t rows_pad, const unsigned short* in) {
+    __shared__ float red[TAIL_WARPS * 20 * TAIL_ROWS];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    tail20_partial<256>(in, rows_pad, blockIdx.x * TAIL_ROWS + lane, slice, w.qf3, red);
     __syncthreads();
-    const int row = blockIdx.x * 128 + threadIdx.x;
-    if (row >= a.rows) return;
-    float o[20];
-    tail20_row<256>(in, rows_pad, row, tail_ws, w.qf3_b, o);
-    int set, slot, b;
-    a.map.decode(row, set, slot, b);
-    const uint32_t sample = a.map.sample_of(slot);
-#pragma unroll
-    for (int d = 0; d < S_DIM; ++d) {
-        const float mean = o[d], lv = o[S_DIM + d];
+    for (int idx = threadIdx.x; idx < TAIL_ROWS * S_DIM; idx += TAIL_NT) {
+        const int r = idx & (TAIL_ROWS - 1), d = idx / TAIL_ROWS;
+        const int row = blockIdx.x * TAIL_ROWS + r;
+        if (row >= a.rows) continue;
+        const float mean = tail20_sum(red, d, r, __ldg(w.qf3_b + d));
+        const float lv = tail20_sum(red, S_DIM + d, r, __ldg(w.qf3_b + S_DIM + d));
         const size_t oo = (size_t)row * S_DIM + d;
         a.mean[oo] = mean; a.logvar[oo] = lv;
         if (a.samp) {
-            const float eps = noise_normal(a.nk, (uint32_t)(a.map.site[0] + 3), (uint32_t)d, (uint32_t)b, sample);
+            int set, slot, b;
+            a.map.decode(row, set, slot, b);
+            const float eps = noise_normal(a.nk, (uint32_t)(a.map.site[0] + 3), (uint32_t)d, (uint32_t)b, a.map.sample_of(slot));
             a.samp[oo] = reparam(eps, mean, lv);
         }
     }
@@ -1010,7 +1030,7 @@ int launch_ps_l0(const DevWeights& w, const PsArgs& a, size_t rows_pad, void* ou
 int launch_ps_tail(const DevWeights& w, const PsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
     const int rows = (a.nA + a.nB) * a.B;
     if (rows <= 0) return 0;
-    k_ps_tail<<<(rows + 127) / 128, 128, 20 * 512 * sizeof(float), st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<const unsigned short*>(in));
+    k_ps_tail<<<(rows + TAIL_ROWS - 1) / TAIL_ROWS, TAIL_NT, 0, st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<const unsigned short*>(in));
     return 1;
 }
 
@@ -1023,7 +1043,7 @@ int launch_po_l0(const DevWeights& w, const PoFcArgs& a, size_t rows_pad, void* 
 
 int launch_qs_tail20(const DevWeights& w, const QsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    k_qs_tail<<<(a.rows + 127) / 128, 128, 20 * 256 * sizeof(float), st>>>(w, a, rows_pad, static_cast<const unsigned short*>(in));
+    k_qs_tail<<<(a.rows + TAIL_ROWS - 1) / TAIL_ROWS, TAIL_NT, 0, st>>>(w, a, rows_pad, static_cast<const unsigned short*>(in));
     return 1;
 }
 
@@ -1088,23 +1108,33 @@ int launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float*
 // entropy_normal_from_logvar: 0.5 * (log(2 pi e) + logvar)   (src/torchutils.py:19-20)
 __device__ __forceinline__ float ent_normal(float lv) { return __fmul_rn(0.5f, __fadd_rn(2.8378770664093453f, lv)); }
 
-__global__ void k_step_finalize(StepFinalizeArgs a) {
-    // one warp per (state, action) row b; lanes stride over the MC samples
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (b >= a.B) return;
+constexpr int FIN_NT = 128;
+
+__global__ void __launch_bounds__(FIN_NT) k_step_finalize(StepFinalizeArgs a) {
+    // one CTA per (state, action) row b; threads stride over the MC samples.  All of a sample's 23 inputs are
+    // loaded before any is used (the kernel is pure latency otherwise).
+    __shared__ double red[4][FIN_NT / 32];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int SB = a.Sl * a.B;
     // per-sample terms are fp32 (as in the reference); their sums over samples / steps / shards are
     // kept in fp64 so that any sample partition adds up to the same value
     double t0 = 0.0, t1 = 0.0, t21 = 0.0, t22 = 0.0;
-    for (int j = lane; j < a.Sl; j += 32) {
+    for (int j = threadIdx.x; j < a.Sl; j += FIN_NT) {
         const int r = j * a.B + b;
-        t0 += a.reward[r];
+        float la[S_DIM], lq[S_DIM];
+#pragma unroll
+        for (int d = 0; d < S_DIM; ++d) {
+            la[d] = a.logvarA[(size_t)r * S_DIM + d];
+            lq[d] = a.qs_logvar[(size_t)r * S_DIM + d];
+        }
+        const float rw = a.reward[r], h1 = a.hsum[SB + r], h2 = a.hsum[2 * SB + r];
         float e = 0.0f;
-        for (int d = 0; d < S_DIM; ++d)
-            e += __fadd_rn(ent_normal(a.logvarA[(size_t)r * S_DIM + d]), ent_normal(a.qs_logvar[(size_t)r * S_DIM + d]));
+#pragma unroll
+        for (int d = 0; d < S_DIM; ++d) e += __fadd_rn(ent_normal(la[d]), ent_normal(lq[d]));
+        t0 += rw;
         t1 += -e;
-        t21 += a.hsum[SB + r];
-        t22 += a.hsum[2 * SB + r];
+        t21 += h1;
+        t22 += h2;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1113,17 +1143,21 @@ __global__ void k_step_finalize(StepFinalizeArgs a) {
         t21 += __shfl_xor_sync(0xffffffffu, t21, o);
         t22 += __shfl_xor_sync(0xffffffffu, t22, o);
     }
-    if (lane == 0) {
-        a.acc[0 * a.B + b] += t0;
-        a.acc[1 * a.B + b] += t1;
-        a.acc[2 * a.B + b] += t21;
-        a.acc[3 * a.B + b] += t22;
+    if (lane == 0) { red[0][warp] = t0; red[1][warp] = t1; red[2][warp] = t21; red[3][warp] = t22; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < FIN_NT / 32; ++w) v += red[threadIdx.x][w];
+        a.acc[threadIdx.x * a.B + b] += v;
     }
-    if (a.carry_src && lane < S_DIM) a.carry_dst[b * S_DIM + lane] = a.carry_src[b * S_DIM + lane];
+    if (a.carry_src && threadIdx.x >= 32 && threadIdx.x < 32 + S_DIM)
+        a.carry_dst[b * S_DIM + threadIdx.x - 32] = a.carry_src[b * S_DIM + threadIdx.x - 32];
 }
 
 int launch_step_finalize(const StepFinalizeArgs& a, cudaStream_t st) {
-    k_step_finalize<<<(a.B * 32 + 127) / 128, 128, 0, st>>>(a);
+    if (a.B <= 0) return 0;
+    k_step_finalize<<<a.B, FIN_NT, 0, st>>>(a);
     return 1;
 }
 

@@ -106,6 +106,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (low word in a register, compile-time high word): the high words become uniform-register
+// immediates instead of two more register -> uniform-register moves on the issuing thread
+template <uint32_t A_TOP, uint32_t B_TOP>
+__device__ __forceinline__ void umma_bf16_split(uint32_t lead, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                uint32_t accumulate) {
+    // `lead` = 1 on the one lane elected for the whole tile (the warp stays converged; the MMA is predicated)
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(A_TOP), "n"(B_TOP), "r"(lead)
+        : "memory");
+}
 // arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     if (elect_one())
@@ -169,6 +185,8 @@ struct ConvParams {
     void* out;               // blocked bf16 planes (ct1, ct2) or projected fp32 planes [row][9][HO][WO] (ct3)
     float2 w4[288];          // ct3 only: last deconv's weights [c 32][tap 9], each duplicated (w, w) for packed
                              // fp32x2 FMAs over the (left, right) output pixel pair (kernel params = constant bank)
+    int32_t two_pass;        // 1: per tile all hi-plane MMAs, then all lo-plane MMAs (each ring slot is released as soon
+                             // as its plane is done); 0: both planes waited for, products interleaved per k step
     int32_t dbg;             // experiments only (env DAI_TC_DBG): 1 = epilogue does no work, 2 = no MMAs issued
     long long* counters;     // experiments only: per CTA {mma_total, mma_wait_acc, mma_wait_a, epi_total, epi_wait, tiles, 0, 0}
 };
@@ -181,26 +199,22 @@ enum { OUT_BLOCKED = 0, OUT_PROJ = 1, OUT_PARITY = 2, OUT_NHWC_F32 = 3 };
 //   GH,GW    m-grid the 16x8 tiles cover (output grid for MODE 0/2, input grid for MODE 1); VH,VW its valid part
 //   PH,PW    height/width of one input plane in HBM (MODE 2: of one parity plane)
 //   NA       halo ring slots (one slot = one bf16 plane, hi or lo, of one tile)
-//   TWO_PASS per tile all MMAs on the hi plane first, then all on the lo plane (planes can share a 3-slot ring);
+//   TWO_PASS (default of ConvParams::two_pass; env DAI_TC_TWO_PASS = bit mask over layer IDs overrides it) per tile all
+//            MMAs on the hi plane first, then all on the lo plane, each ring slot released when its plane is done;
 //            otherwise both planes are waited for and the products of one (tap, k) step are issued back to back
 //   CONCAT   (bf16x3) a weight block stores hi rows then lo rows: A_hi*[B_hi;B_lo] is ONE MMA of doubled N — the fixed
 //            ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times; the hi*lo part lands in a
 //            second column block that the epilogue adds
-struct TrCt1 { static constexpr int MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
-               EPI_WARPS = 8, OUT = OUT_BLOCKED;
-#ifdef DAI_CT1_TWO_PASS
-               static constexpr bool TWO_PASS = true, CONCAT = true; };
-#else
-               static constexpr bool TWO_PASS = false, CONCAT = true; };
-#endif
-struct TrCt2 { static constexpr int MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
+struct TrCt1 { static constexpr int ID = 0, MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = true; };
+struct TrCt2 { static constexpr int ID = 1, MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
                EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false; };
-struct TrCt3 { static constexpr int MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 6,
+struct TrCt3 { static constexpr int ID = 2, MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 6,
                EPI_WARPS = 8, OUT = OUT_PROJ; static constexpr bool TWO_PASS = false, CONCAT = false; };
 // encoder: Conv2d 32->32 (31x31 -> 15x15) and 32->64 (15x15 -> 7x7), k3 s2 valid
-struct TrQc2 { static constexpr int MODE = 2, NPH = 32, KCIN = 4, GH = 16, GW = 16, VH = 15, VW = 15, PH = 16, PW = 16, NA = 4,
+struct TrQc2 { static constexpr int ID = 3, MODE = 2, NPH = 32, KCIN = 4, GH = 16, GW = 16, VH = 15, VW = 15, PH = 16, PW = 16, NA = 4,
                EPI_WARPS = 8, OUT = OUT_PARITY; static constexpr bool TWO_PASS = false, CONCAT = false; };
-struct TrQc3 { static constexpr int MODE = 2, NPH = 64, KCIN = 4, GH = 16, GW = 8, VH = 7, VW = 7, PH = 8, PW = 8, NA = 4,
+struct TrQc3 { static constexpr int ID = 4, MODE = 2, NPH = 64, KCIN = 4, GH = 16, GW = 8, VH = 7, VW = 7, PH = 8, PW = 8, NA = 4,
                EPI_WARPS = 8, OUT = OUT_NHWC_F32; static constexpr bool TWO_PASS = false, CONCAT = false; };
 
 template <class T>
@@ -211,6 +225,7 @@ struct Cfg : T {
     static constexpr int HX = T::MODE == 0 ? TW + 2 : TW + 1;
     static constexpr int KPLANES = T::MODE == 2 ? 4 * T::KCIN : T::KCIN;   // 8-channel planes in the halo (x4 parities)
     static constexpr int KSTEPS = T::KCIN / 2;                            // k16 steps per tap
+    static constexpr int NUNITS = T::MODE == 1 ? 4 : 9;                   // MMA groups per tile (unit_at)
     static constexpr int KC_STRIDE = HY * HX * 16;             // bytes of one 8-channel plane of the halo
     static constexpr int PLANE_A = KPLANES * KC_STRIDE;        // one bf16 plane (hi or lo) = one ring slot
     static constexpr int TILES_X = (T::GW + TW - 1) / TW, TILES_Y = (T::GH + TH - 1) / TH;
@@ -225,6 +240,70 @@ struct Cfg : T {
     static constexpr int SMEM_TAIL = T::OUT == OUT_PROJ ? 3072 : 1024;   // barriers, tmem slot, bias (+ projection weights)
     static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + SMEM_TAIL;
 };
+
+// The unit table of a layer as a function of compile-time traits (build_layer packs the weights in this order and
+// checks itself against it).  The MMA issuer unrolls over it, so every per-unit quantity below is an immediate.
+template <class C>
+__host__ __device__ constexpr Unit unit_at(int u) {
+    constexpr int CW = C::NPH * C::KCIN * 32;          // bytes of one tap's weights, hi + lo
+    Unit r{};
+    if (C::MODE == 1) {
+        // grouped sub-pixel phases, TMEM column slots [00, 01, 11, 10]
+        r.oy = (int16_t)(u >> 1); r.ox = (int16_t)(u & 1);
+        r.col = (int16_t)(u == 0 ? 0 : (u == 1 ? C::NPH : 2 * C::NPH));
+        r.n = (int16_t)(u == 0 ? 4 * C::NPH : (u == 3 ? C::NPH : 2 * C::NPH));
+        r.init = (int16_t)(u == 0);
+        r.kc0 = 0;
+        r.woff = (u == 0 ? 0 : (u == 1 ? 4 : (u == 2 ? 6 : 8))) * CW;
+    } else {
+        const int kh = u / 3, kw = u % 3;
+        r.oy = (int16_t)(C::MODE == 0 ? 2 - kh : kh >> 1); r.ox = (int16_t)(C::MODE == 0 ? 2 - kw : kw >> 1);
+        r.col = 0; r.n = (int16_t)C::NPH; r.init = (int16_t)(u == 0);
+        r.kc0 = (int16_t)(C::MODE == 2 ? ((kh & 1) * 2 + (kw & 1)) * C::KCIN : 0);
+        r.woff = u * CW;
+    }
+    return r;
+}
+
+// All MMAs of one tile.  a_hi16 / a_lo16 / w16: shared-memory addresses >> 4 of the two halo planes and of the resident
+// weights; d0: TMEM address of the tile's accumulator block.  SEL 0: the products that read the hi plane, 1: the
+// product that reads the lo plane, 2: all of them, interleaved per k step.  A descriptor is (constant high word,
+// base + immediate low word): one integer add per operand per MMA on the issuing thread, which matters — at N <= 128
+// an MMA takes 46..64 cycles and the issue stream of ONE thread has to stay ahead of that.
+template <class C, int SEL, bool X3>
+__device__ __forceinline__ void issue_tile(uint32_t a_hi16, uint32_t a_lo16, uint32_t w16, uint32_t d0) {
+    constexpr uint32_t A_TOP = (uint32_t)((C::HX * 16) >> 4) | (1u << 14);   // SBO = halo row pitch; descriptor bit 46
+    constexpr uint32_t B_TOP = (uint32_t)(128 >> 4) | (1u << 14);            // SBO = 8 rows x 16 B
+    constexpr uint32_t A_LBO = (uint32_t)(C::KC_STRIDE >> 4) << 16;
+    const uint32_t lead = elect_one() ? 1u : 0u;
+#pragma unroll
+    for (int u = 0; u < C::NUNITS; ++u) {
+        const Unit un = unit_at<C>(u);
+        const uint32_t n = (uint32_t)un.n;
+        const uint32_t bk = C::CONCAT ? 2u * n * 16u : n * 16u;       // bytes between kc planes of the weight block
+        const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;         // hi -> lo plane of a non-concatenated block
+        const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
+        const uint32_t d = d0 + (uint32_t)un.col;
+#pragma unroll
+        for (int k = 0; k < C::KSTEPS; ++k) {
+            const uint32_t acc0 = (un.init && k == 0) ? 0u : 1u;
+            const uint32_t a_imm = ((a_off + (uint32_t)(2 * k) * C::KC_STRIDE) >> 4) + A_LBO;
+            const uint32_t b_imm = (((uint32_t)un.woff + (uint32_t)(2 * k) * bk) >> 4) + ((bk >> 4) << 16);
+            const uint32_t a_hi = a_hi16 + a_imm, a_lo = a_lo16 + a_imm;
+            const uint32_t b_hi = w16 + b_imm, b_lo = w16 + b_imm + (b_plane >> 4);
+            if (!X3) {
+                if (SEL != 1) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_hi, umma_idesc(un.n), acc0);
+            } else if (C::CONCAT) {
+                if (SEL != 1) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_hi, umma_idesc(2 * un.n), acc0);   // [A_hi*B_hi | A_hi*B_lo]
+                if (SEL != 0) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_lo, b_hi, umma_idesc(un.n), 1u);         // A_lo*B_hi (first n rows)
+            } else {
+                if (SEL != 1) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_hi, umma_idesc(un.n), acc0);
+                if (SEL != 0) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_lo, b_hi, umma_idesc(un.n), 1u);
+                if (SEL != 1) umma_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_lo, umma_idesc(un.n), 1u);
+            }
+        }
+    }
+}
 
 // relu(acc + bias) for two neighbouring channels -> packed bf16 hi pair and lo pair (x = hi + lo)
 __device__ __forceinline__ void split2(uint32_t r0, uint32_t r1, float b0, float b1, float scale0, float scale1,
@@ -324,6 +403,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
         {
             mbar_wait(w_full, 0);
             tc_fence_after();
+            const uint32_t w16 = smem_u32(smW) >> 4, a16 = smem_u32(smA) >> 4;
             int it = 0, cnt = 0;
             long long t_begin = clock64(), w_acc = 0, w_a = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -332,94 +412,39 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                 long long tw = clock64();
                 mbar_wait(&acc_empty[buf], aph ^ 1u);
                 w_acc += clock64() - tw;
-                if (C::TWO_PASS) {
-                    for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
-                        const int s = cnt % C::NA;
-                        const uint32_t ph = (uint32_t)(cnt / C::NA) & 1u;
-                        mbar_wait(&a_full[s], ph);
-                        tc_fence_after();
-                        const uint32_t a_base = smem_u32(smA + (size_t)s * C::PLANE_A);
-                        for (int u = 0; u < p.nunits; ++u) {
-                            const Unit un = p.units[u];
-                            const uint32_t n = (uint32_t)un.n;
-                            const uint32_t idesc = umma_idesc(un.n);
-                            const uint32_t w_base = smem_u32(smW + un.woff);
-                            const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;     // hi -> lo plane of this weight block
-                            const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
-                            const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
-#pragma unroll
-                            for (int k = 0; k < C::KSTEPS; ++k) {
-                                const uint64_t a_d = umma_desc(a_base + a_off + (uint32_t)(2 * k) * C::KC_STRIDE, C::KC_STRIDE, C::HX * 16);
-                                const uint32_t bk = C::CONCAT ? 2u * n * 16u : n * 16u;
-                                const uint64_t b_hi = umma_desc(w_base + (uint32_t)(2 * k) * bk, bk, 128);
-                                if (pl == 0) {
-                                    if (C::CONCAT && nplanes == 2) {
-                                        umma_bf16(d, a_d, b_hi, umma_idesc(2 * un.n), (un.init && k == 0) ? 0u : 1u);   // [A_hi*B_hi | A_hi*B_lo]
-                                    } else {
-                                        umma_bf16(d, a_d, b_hi, idesc, (un.init && k == 0) ? 0u : 1u);      // A_hi * B_hi
-                                        if (nplanes == 2) {
-                                            const uint64_t b_lo = umma_desc(w_base + b_plane + (uint32_t)(2 * k) * n * 16u, n * 16u, 128);
-                                            umma_bf16(d, a_d, b_lo, idesc, 1u);                             // A_hi * B_lo
-                                        }
-                                    }
-                                } else {
-                                    umma_bf16(d, a_d, b_hi, idesc, 1u);                                     // A_lo * B_hi
-                                }
-                            }
-                        }
-                        umma_commit(&a_empty[s]);
-                    }
-                } else {
-                    const int s0 = cnt % C::NA;
-                    tw = clock64();
-                    mbar_wait(&a_full[s0], (uint32_t)(cnt / C::NA) & 1u);
-                    ++cnt;
-                    int s1 = s0;
-                    if (nplanes == 2) {
-                        s1 = cnt % C::NA;
-                        mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
-                        ++cnt;
-                    }
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+                const int s0 = cnt % C::NA;
+                tw = clock64();
+                mbar_wait(&a_full[s0], (uint32_t)(cnt / C::NA) & 1u);
+                ++cnt;
+                if (nplanes == 1) {
                     w_a += clock64() - tw;
                     tc_fence_after();
-                    const uint32_t a_hi_base = smem_u32(smA + (size_t)s0 * C::PLANE_A);
-                    const uint32_t a_lo_base = smem_u32(smA + (size_t)s1 * C::PLANE_A);
-                    for (int u = 0; u < ((p.dbg & 2) ? 0 : p.nunits); ++u) {
-                        const Unit un = p.units[u];
-                        const uint32_t n = (uint32_t)un.n;
-                        const uint32_t idesc = umma_idesc(un.n);
-                        const uint32_t w_base = smem_u32(smW + un.woff);
-                        const uint32_t b_plane = (uint32_t)C::KCIN * n * 16u;     // hi -> lo plane of this weight block
-                        const uint32_t a_off = (uint32_t)un.kc0 * C::KC_STRIDE + (uint32_t)(un.oy * C::HX + un.ox) * 16u;
-                        const uint32_t d = tmem_base + (uint32_t)(buf * C::ACC_COLS + un.col);
-                        // Descriptors advance along K by adding to their 14-bit address field (shared memory is
-                        // < 256 KB, so no carry leaves the field): a couple of integer adds per MMA keep the issuing
-                        // thread cheap — it shares its scheduler with two FFMA-heavy epilogue warps.
-                        const uint32_t bk = C::CONCAT ? 2u * n * 16u : n * 16u;   // bytes between kc planes of the block
-                        uint64_t a_hi = umma_desc(a_hi_base + a_off, C::KC_STRIDE, C::HX * 16);
-                        uint64_t a_lo = umma_desc(a_lo_base + a_off, C::KC_STRIDE, C::HX * 16);
-                        uint64_t b_hi = umma_desc(w_base, bk, 128);
-                        uint64_t b_lo = umma_desc(w_base + b_plane, bk, 128);
-                        const uint64_t a_step = (uint64_t)((2u * C::KC_STRIDE) >> 4), b_step = (uint64_t)((2u * bk) >> 4);
-                        const uint32_t idesc2 = umma_idesc(2 * un.n);
-#pragma unroll
-                        for (int k = 0; k < C::KSTEPS; ++k) {
-                            const uint32_t acc0 = (un.init && k == 0) ? 0u : 1u;
-                            if (C::CONCAT && nplanes == 2) {
-                                umma_bf16(d, a_hi, b_hi, idesc2, acc0);     // [A_hi*B_hi | A_hi*B_lo]  (block = hi rows, lo rows)
-                                umma_bf16(d, a_lo, b_hi, idesc, 1u);        // A_lo*B_hi (first n rows)
-                            } else {
-                                umma_bf16(d, a_hi, b_hi, idesc, acc0);
-                                if (nplanes == 2) {
-                                    umma_bf16(d, a_lo, b_hi, idesc, 1u);
-                                    umma_bf16(d, a_hi, b_lo, idesc, 1u);
-                                }
-                            }
-                            a_hi += a_step; a_lo += a_step; b_hi += b_step; b_lo += b_step;
-                        }
-                    }
+                    if (!(p.dbg & 2)) issue_tile<C, 2, false>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
                     umma_commit(&a_empty[s0]);
-                    if (nplanes == 2) umma_commit(&a_empty[s1]);
+                } else if (p.two_pass) {
+                    w_a += clock64() - tw;
+                    tc_fence_after();
+                    if (!(p.dbg & 2)) issue_tile<C, 0, true>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
+                    umma_commit(&a_empty[s0]);
+                    const int s1 = cnt % C::NA;
+                    tw = clock64();
+                    mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
+                    ++cnt;
+                    w_a += clock64() - tw;
+                    tc_fence_after();
+                    if (!(p.dbg & 2)) issue_tile<C, 1, true>(0u, a16 + (uint32_t)s1 * (C::PLANE_A >> 4), w16, d0);
+                    umma_commit(&a_empty[s1]);
+                } else {
+                    const int s1 = cnt % C::NA;
+                    mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
+                    ++cnt;
+                    w_a += clock64() - tw;
+                    tc_fence_after();
+                    if (!(p.dbg & 2))
+                        issue_tile<C, 2, true>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), a16 + (uint32_t)s1 * (C::PLANE_A >> 4), w16, d0);
+                    umma_commit(&a_empty[s0]);
+                    umma_commit(&a_empty[s1]);
                 }
                 umma_commit(&acc_full[buf]);
             }
@@ -932,6 +957,16 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     p.wpack = lp.wpack; p.bias = bias; p.out = out;
     if (w4) for (int i = 0; i < 288; ++i) p.w4[i] = make_float2(w4[i], w4[i]);
+    for (int i = 0; i < C::NUNITS; ++i) {
+        const Unit a = lp.units[i], b = unit_at<C>(i);
+        if (lp.nunits != C::NUNITS || a.oy != b.oy || a.ox != b.ox || a.col != b.col || a.n != b.n || a.init != b.init ||
+            a.kc0 != b.kc0 || a.woff != b.woff) {
+            *err = "tensor-core layer: packed unit table differs from the compile-time table";
+            return -1;
+        }
+    }
+    static const int env_two_pass = getenv("DAI_TC_TWO_PASS") ? atoi(getenv("DAI_TC_TWO_PASS")) : -1;
+    p.two_pass = env_two_pass >= 0 ? ((env_two_pass >> C::ID) & 1) : (C::TWO_PASS ? 1 : 0);
     if (const char* e = getenv("DAI_TC_DBG")) p.dbg = atoi(e);
     static long long* dbg_counters = nullptr;
     const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;
