@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -57,7 +58,7 @@ const WeightSpec kSpecs[] = {
 };
 constexpr int kNumSpecs = sizeof(kSpecs) / sizeof(kSpecs[0]);
 
-constexpr int kDecChunk = 1024;   // decoder rows per activation chunk (896 KB of activations per row)
+constexpr int kDecChunkDefault = 4800;   // decoder rows per activation chunk (896 KB of activations per row; larger chunks amortise the per-launch ramp: 1024 -> 4800 rows = +7 % rollouts/s)
 constexpr int kQsChunk = 2048;    // encoder rows per chunk (166 KB of conv features per row)
 
 }  // namespace
@@ -73,6 +74,7 @@ struct dai_handle {
     std::vector<void*> wallocs;
     uint64_t seed = 1234, call = 0;
     uint64_t launches = 0, calls = 0;
+    int dec_chunk = kDecChunkDefault;   // env DAI_DEC_CHUNK (tuning only)
     // workspaces (grow-only)
     DevBuf mlpA, mlpB, ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
         pi_eye, traj, root, stage_in, stage_out, scratch;
@@ -306,7 +308,9 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
     const size_t rows_pad = ((size_t)rows + 127) / 128 * 128 + 128;      // the tensor-core FC4 reads whole 128-row tiles
     RET(reserve(h, h->h3, tc ? rows_pad * 256 * 2 * sizeof(unsigned short) : (size_t)rows * 256 * sizeof(float)));
-    const int ch = std::min(rows, kDecChunk);
+    // equal chunks (a short last chunk leaves most SMs idle for a whole pass): ceil(rows / nchunks), 32-row granular
+    const int nchunks = (rows + h->dec_chunk - 1) / h->dec_chunk;
+    const int ch = std::min(rows, ((rows + nchunks - 1) / nchunks + 31) / 32 * 32);
     const size_t esz = sizeof(float);   // fp32 planes, or bf16 hi+lo planes: 4 bytes per element either way
     RET(reserve(h, h->mask, (size_t)ch * 512 * sizeof(uint32_t)));
     RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
@@ -573,6 +577,10 @@ int dai_create(const dai_config* cfg, int device, dai_handle** out) {
     if (!h) return DAI_E_NOMEM;
     h->cfg = *cfg;
     h->device = device;
+    if (const char* e = getenv("DAI_DEC_CHUNK")) {
+        const int v = atoi(e);
+        if (v >= 32 && v <= 8192) h->dec_chunk = v;
+    }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DAI_E_CUDA; }
     if (cudaMallocHost(&h->pinned, 4096) != cudaSuccess) { delete h; return DAI_E_NOMEM; }
     h->pinned_cap = 4096;

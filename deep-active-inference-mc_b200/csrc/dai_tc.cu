@@ -206,10 +206,10 @@ enum { OUT_BLOCKED = 0, OUT_PROJ = 1, OUT_PARITY = 2, OUT_NHWC_F32 = 3 };
 //            ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times; the hi*lo part lands in a
 //            second column block that the epilogue adds
 struct TrCt1 { static constexpr int ID = 0, MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
-               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = true; };
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = true, CONCAT = true; };
 struct TrCt2 { static constexpr int ID = 1, MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
                EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false; };
-struct TrCt3 { static constexpr int ID = 2, MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 6,
+struct TrCt3 { static constexpr int ID = 2, MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 7,
                EPI_WARPS = 8, OUT = OUT_PROJ; static constexpr bool TWO_PASS = false, CONCAT = false; };
 // encoder: Conv2d 32->32 (31x31 -> 15x15) and 32->64 (15x15 -> 7x7), k3 s2 valid
 struct TrQc2 { static constexpr int ID = 3, MODE = 2, NPH = 32, KCIN = 4, GH = 16, GW = 16, VH = 15, VW = 15, PH = 16, PW = 16, NA = 4,
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
 
 using CfgCt1 = Cfg<TrCt1>;   // 144 KB of weights + 3 x 22.5 KB halo planes
 using CfgCt2 = Cfg<TrCt2>;   // 144 KB of weights + 4 x 19.1 KB halo planes (2 tiles in flight)
-using CfgCt3 = Cfg<TrCt3>;   //  72 KB of weights + 6 x 19.1 KB halo planes (3 tiles in flight)
+using CfgCt3 = Cfg<TrCt3>;   //  72 KB of weights + 7 x 19.1 KB halo planes (3.5 tiles in flight)
 using CfgQc2 = Cfg<TrQc2>;   //  36 KB of weights + 4 x 38.3 KB halo planes (4 parities x 4 kc)
 using CfgQc3 = Cfg<TrQc3>;   //  72 KB of weights + 4 x 38.3 KB halo planes
 
