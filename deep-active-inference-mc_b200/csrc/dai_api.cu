@@ -761,12 +761,9 @@ int dai_calculate_G_mean(dai_handle* h, const float* s0, const float* pi0, int B
     return finish_outputs(h, st, B, 1, nullptr, G, t0, t1, t2);
 }
 
-int dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, const float* ps1_mean,
-                           const float* ps1_logvar, const float* pi0, int D, float* G, void* stream) {
-    RET(check_ready(h));
-    if (!s0 || !ps1 || !ps1_mean || !ps1_logvar || !pi0 || D <= 0 || D > 256)
-        return fail(h, DAI_E_INVALID, "G_given_trajectory: bad arguments (1 <= depth <= 256)");
-    cudaStream_t st = (cudaStream_t)stream;
+// calculate_G_given_trajectory over D rows = D / depth trajectories of `depth` rows; G (D) and Gmean (D / depth) device.
+static int trajectory_impl(dai_handle* h, cudaStream_t st, const float* s0, const float* ps1, const float* ps1_mean,
+                           const float* ps1_logvar, const float* pi0, int D, int depth, float* G, float* Gmean) {
     const NoiseKey nk = make_key(h, h->call++, 0);
     ++h->calls;
     const size_t slab = (size_t)D * S_DIM;
@@ -789,10 +786,17 @@ int dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, con
     float* qs_mean = ptr<float>(h->qs_out);
     float* qs_logvar = qs_mean + slab;
     RET(run_encoder(h, st, ptr<float>(h->img), D, 1, 0, SITE_QS_A, nk, qs_mean, qs_logvar, nullptr));
-    RET(reserve(h, h->scratch, 16 * sizeof(float)));
-    h->launches += launch_traj_G(ptr<float>(h->reward), ptr<float>(h->hsum), ps1_logvar, qs_logvar, D, G,
-                                 ptr<float>(h->scratch), st);
+    h->launches += launch_traj_G(ptr<float>(h->reward), ptr<float>(h->hsum), ps1_logvar, qs_logvar, D, depth, G, Gmean, st);
     return post_launch(h, "trajectory G");
+}
+
+int dai_G_given_trajectory(dai_handle* h, const float* s0, const float* ps1, const float* ps1_mean,
+                           const float* ps1_logvar, const float* pi0, int D, float* G, void* stream) {
+    RET(check_ready(h));
+    if (!s0 || !ps1 || !ps1_mean || !ps1_logvar || !pi0 || D <= 0 || D > 256)
+        return fail(h, DAI_E_INVALID, "G_given_trajectory: bad arguments (1 <= depth <= 256)");
+    RET(reserve(h, h->scratch, 16 * sizeof(float)));
+    return trajectory_impl(h, (cudaStream_t)stream, s0, ps1, ps1_mean, ps1_logvar, pi0, D, D, G, ptr<float>(h->scratch));
 }
 
 int dai_rollout(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples, int calc_mean, int four,
@@ -839,28 +843,41 @@ int dai_rollout_host(dai_handle* h, const float* o_host, const float* pi_host, i
     return DAI_OK;
 }
 
-int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means, float* G_host, float* pi0,
-                      float* qpi, void* stream) {
+int dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int depth, int use_means, float* G_host,
+                            float* pi0, float* qpi, void* stream) {
     RET(check_ready(h));
-    if (!starting_s || !G_host || !pi0 || !qpi || depth <= 0 || depth > 256)
-        return fail(h, DAI_E_INVALID, "mcts_simulate: bad arguments (1 <= depth <= 256)");
+    if (!starting_s || !G_host || !pi0 || !qpi || K <= 0 || K > 4096 || depth <= 0 || depth > 256)
+        return fail(h, DAI_E_INVALID, "mcts_simulate: bad arguments (1 <= K <= 4096, 1 <= depth <= 256)");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t slab = (size_t)depth * S_DIM;
+    const size_t slab = (size_t)K * depth * S_DIM;
     RET(reserve(h, h->traj, 4 * slab * sizeof(float)));
+    RET(reserve(h, h->scratch, (size_t)std::max(K, 16) * sizeof(float)));
+    if ((size_t)K * sizeof(float) > h->pinned_cap) {
+        float* np = nullptr;
+        CK(cudaMallocHost(&np, (size_t)K * sizeof(float)));
+        cudaFreeHost(h->pinned);
+        h->pinned = np; h->pinned_cap = (size_t)K * sizeof(float);
+    }
     float* s0 = ptr<float>(h->traj);
     SimArgs sa{};
-    sa.start = starting_s; sa.depth = depth; sa.use_means = use_means;
+    sa.start = starting_s; sa.K = K; sa.depth = depth; sa.use_means = use_means;
     sa.s0 = s0; sa.ps1 = s0 + slab; sa.mean = s0 + 2 * slab; sa.logvar = s0 + 3 * slab;
     sa.pi0 = pi0; sa.qpi = qpi;
     sa.nk = make_key(h, h->call++, 0);
     h->launches += launch_sim_rollout(h->w, sa, st);
     RET(post_launch(h, "simulate rollout"));
-    // calculate_G_given_trajectory over the depth rows (next call index), mean -> host (src/torchmodel.py:392)
-    RET(dai_G_given_trajectory(h, sa.s0, sa.ps1, sa.mean, sa.logvar, pi0, depth, nullptr, stream));
-    CK(cudaMemcpyAsync(h->pinned, h->scratch.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+    // calculate_G_given_trajectory over the K*depth rows (next call index), per-trajectory mean -> host
+    // (src/torchmodel.py:392)
+    RET(trajectory_impl(h, st, sa.s0, sa.ps1, sa.mean, sa.logvar, pi0, K * depth, depth, nullptr, ptr<float>(h->scratch)));
+    CK(cudaMemcpyAsync(h->pinned, h->scratch.p, (size_t)K * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    *G_host = h->pinned[0];
+    for (int k = 0; k < K; ++k) G_host[k] = h->pinned[k];
     return DAI_OK;
+}
+
+int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means, float* G_host, float* pi0,
+                      float* qpi, void* stream) {
+    return dai_mcts_simulate_batch(h, starting_s, 1, depth, use_means, G_host, pi0, qpi, stream);
 }
 
 int dai_select_actions(dai_handle* h, const float* G, int R, float temperature, float* Ppi, float* logPpi,

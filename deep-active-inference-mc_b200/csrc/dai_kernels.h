@@ -125,14 +125,14 @@ int  launch_select_actions(const float* G, int R, float temperature, const Noise
                            int* choice, cudaStream_t st);
 int  launch_reward_only(const float* o, int B, float* r, cudaStream_t st);
 int  launch_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
-                   int D, float* G, float* Gmean, cudaStream_t st);
+                   int D, int depth, float* G, float* Gmean, cudaStream_t st);
 
 // habit-policy rollout of mcts_step_simulate: `depth` sequential (Qpi -> categorical -> Ps) steps
 struct SimArgs {
-    const float* start;    // [10]
-    int32_t depth, use_means;
-    float *s0, *ps1, *mean, *logvar, *pi0;   // [depth][10|4]
-    float* qpi;            // [4]
+    const float* start;    // [K][10]
+    int32_t K, depth, use_means;
+    float *s0, *ps1, *mean, *logvar, *pi0;   // [K*depth][10|4], row = k*depth + t
+    float* qpi;            // [K][4]
     NoiseKey nk;
 };
 int  launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st);

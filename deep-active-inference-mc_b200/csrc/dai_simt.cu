@@ -1212,38 +1212,40 @@ int launch_select_actions(const float* G, int R, float temperature, const NoiseK
     return 1;
 }
 
-// calculate_G_given_trajectory tail (src/torchmodel.py:335-352): rows = depth
+// calculate_G_given_trajectory tail (src/torchmodel.py:335-352).  D rows in all = gridDim.x trajectories of `depth`
+// rows each (one CTA per trajectory); Gmean[k] = mean over the rows of trajectory k (src/torchmodel.py:392).
 __global__ void k_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
-                         int D, float* G, float* Gmean) {
+                         int D, int depth, float* G, float* Gmean) {
     __shared__ float gs[256];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, r = blockIdx.x * depth + t;
     float g = 0.0f;
-    if (t < D) {
+    if (t < depth) {
         float e = 0.0f;
         for (int d = 0; d < S_DIM; ++d)
-            e += __fadd_rn(ent_normal(lv_traj[t * S_DIM + d]), ent_normal(qs_logvar[t * S_DIM + d]));
-        const float term0 = reward[t], term1 = -e, term2 = hsum[D + t] - hsum[2 * D + t];
+            e += __fadd_rn(ent_normal(lv_traj[r * S_DIM + d]), ent_normal(qs_logvar[r * S_DIM + d]));
+        const float term0 = reward[r], term1 = -e, term2 = hsum[D + r] - hsum[2 * D + r];
         g = -term0 + term1 + term2;
-        if (G) G[t] = g;
+        if (G) G[r] = g;
     }
     gs[t] = g;
     __syncthreads();
     if (t == 0 && Gmean) {
         float s = 0.0f;
-        for (int i = 0; i < D; ++i) s += gs[i];
-        *Gmean = s / (float)D;
+        for (int i = 0; i < depth; ++i) s += gs[i];
+        Gmean[blockIdx.x] = s / (float)depth;
     }
 }
 
 int launch_traj_G(const float* reward, const float* hsum, const float* lv_traj, const float* qs_logvar,
-                  int D, float* G, float* Gmean, cudaStream_t st) {
-    k_traj_G<<<1, 256, 0, st>>>(reward, hsum, lv_traj, qs_logvar, D, G, Gmean);
+                  int D, int depth, float* G, float* Gmean, cudaStream_t st) {
+    k_traj_G<<<D / depth, 256, 0, st>>>(reward, hsum, lv_traj, qs_logvar, D, depth, G, Gmean);
     return 1;
 }
 
 // ======================================================================================
 // mcts_step_simulate rollout (src/torchmodel.py:354-388): depth sequential B=1 steps of
-// Qpi -> categorical -> Ps, one CTA, the carry never leaves shared memory.
+// Qpi -> categorical -> Ps, one CTA per starting state (blockIdx.x = k, which is also the noise row of
+// everything it draws, so K = 1 is the reference's call), the carry never leaves shared memory.
 // ======================================================================================
 __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
     __shared__ __align__(16) float s_cur[12];
@@ -1254,10 +1256,11 @@ __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
     __shared__ float out[20];
     __shared__ float lg[4];
     __shared__ int act;
-    const int tid = threadIdx.x;
-    if (tid < 12) s_cur[tid] = tid < S_DIM ? a.start[tid] : 0.0f;
+    const int tid = threadIdx.x, kq = blockIdx.x;
+    const size_t r0 = (size_t)kq * a.depth;               // first trajectory row of this leaf
+    if (tid < 12) s_cur[tid] = tid < S_DIM ? a.start[kq * S_DIM + tid] : 0.0f;
     __syncthreads();
-    int rsite[1] = {SITE_PS_A}, rb[1] = {0};
+    int rsite[1] = {SITE_PS_A}, rb[1] = {kq};
     uint32_t rsample[1] = {0};
     for (int t = 0; t < a.depth; ++t) {
         NoiseKey nk = a.nk;
@@ -1284,15 +1287,15 @@ __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
             ok = ok && c > 0.0f;
             int choice = 0;
             if (ok) {
-                const float u = noise_uniform24(nk, SITE_CAT, 0, 0);
+                const float u = noise_uniform24(nk, SITE_CAT, (uint32_t)kq, 0);
                 const float thr = __fmul_rn(u, cdf[3]);
                 choice = 3;
                 for (int i = 0; i < 4; ++i) if (thr < cdf[i]) { choice = i; break; }
             }
             act = choice;
-            for (int i = 0; i < 4; ++i) a.pi0[t * 4 + i] = (i == choice) ? 1.0f : 0.0f;
-            if (t == 0) for (int i = 0; i < 4; ++i) a.qpi[i] = ok ? q[i] : (i == 0 ? 1.0f : 0.0f);
-            for (int d = 0; d < S_DIM; ++d) a.s0[t * S_DIM + d] = s_cur[d];
+            for (int i = 0; i < 4; ++i) a.pi0[(r0 + t) * 4 + i] = (i == choice) ? 1.0f : 0.0f;
+            if (t == 0) for (int i = 0; i < 4; ++i) a.qpi[kq * 4 + i] = ok ? q[i] : (i == 0 ? 1.0f : 0.0f);
+            for (int d = 0; d < S_DIM; ++d) a.s0[(r0 + t) * S_DIM + d] = s_cur[d];
         }
         __syncthreads();
         if (tid < 16) x0[tid] = tid < 4 ? (tid == act ? 1.0f : 0.0f) : (tid < 14 ? s_cur[tid - 4] : 0.0f);
@@ -1313,9 +1316,9 @@ __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
         __syncthreads();
         if (tid < S_DIM) {
             const float mean = out[tid], lv = out[S_DIM + tid];
-            const float eps = noise_normal(nk, SITE_PS_A + 3, (uint32_t)tid, 0, 0);
+            const float eps = noise_normal(nk, SITE_PS_A + 3, (uint32_t)tid, (uint32_t)kq, 0);
             const float s = reparam(eps, mean, lv);
-            a.ps1[t * S_DIM + tid] = s; a.mean[t * S_DIM + tid] = mean; a.logvar[t * S_DIM + tid] = lv;
+            a.ps1[(r0 + t) * S_DIM + tid] = s; a.mean[(r0 + t) * S_DIM + tid] = mean; a.logvar[(r0 + t) * S_DIM + tid] = lv;
             s_cur[tid] = a.use_means ? mean : s;
         }
         __syncthreads();
@@ -1323,7 +1326,7 @@ __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
 }
 
 int launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st) {
-    k_sim_rollout<<<1, 512, 0, st>>>(w, a);
+    k_sim_rollout<<<a.K, 512, 0, st>>>(w, a);
     return 1;
 }
 

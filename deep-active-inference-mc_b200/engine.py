@@ -61,6 +61,8 @@ SIGNATURES = {
                                         ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dai_mcts_simulate": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float),
                                          _vp, _vp, _vp]),
+    "dai_mcts_simulate_batch": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.POINTER(ctypes.c_float), _vp, _vp, _vp]),
     "dai_select_actions": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "dai_profile_begin": (ctypes.c_int, [_vp]),
     "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
@@ -306,3 +308,14 @@ class Engine:
         self._ck(self.lib.dai_mcts_simulate(self.h, _p(s), depth, 1 if use_means else 0, ctypes.byref(G), _p(pi0),
                                             _p(qpi), self._stream()))
         return float(G.value), pi0, qpi
+
+    def mcts_simulate_batch(self, starting_s, depth, use_means=False):
+        """K habit-policy rollouts + one trajectory evaluation (include/dai_b200.h dai_mcts_simulate_batch).
+        starting_s (K,10) -> G (K,) host float32 tensor, pi0 (K,depth,4), qpi (K,4) on the device."""
+        s = self.dev(starting_s).reshape(-1, 10)
+        K = s.shape[0]
+        pi0, qpi = self.new(K, depth, 4), self.new(K, 4)
+        G = (ctypes.c_float * K)()
+        self._ck(self.lib.dai_mcts_simulate_batch(self.h, _p(s), K, depth, 1 if use_means else 0, G, _p(pi0), _p(qpi),
+                                                  self._stream()))
+        return torch.tensor(list(G), dtype=torch.float32), pi0, qpi

@@ -96,6 +96,64 @@ class Tree:
         for a in range(self.pi_dim):
             self.child[i, a] = self.add(nxt[a])
 
+    # ---- batched leaves -------------------------------------------------------------------
+    def select_batch(self, root, k):
+        """Up to k DISTINCT leaves for one batched expansion.  Descents are made one after the other with the
+        reference's argmax rule (selection_scores); after each, the edges of its path get one virtual visit (N + 1 with
+        the edge's mean W/N kept, so only the C/N exploration bonus shrinks) and the claimed leaf is blocked — as is
+        any node whose children are all blocked — so the next descent goes elsewhere.  With k = 1 nothing virtual is
+        ever read: the selection is the reference's.  Returns [(nodes, actions)], statistics restored."""
+        picks, blocked = [], set()
+        W0, N0 = self.W.clone(), self.N.clone()
+        parent = {}
+        while len(picks) < k and root not in blocked:
+            nodes, actions, cur = [], [], root
+            while True:
+                sc = self.selection_scores(cur).clone()
+                for a in range(self.pi_dim):
+                    if int(self.child[cur, a]) in blocked:
+                        sc[a] = -float("inf")
+                a = int(torch.argmax(sc))
+                nxt = int(self.child[cur, a])
+                parent[nxt] = cur
+                actions.append(a)
+                nodes.append(nxt)
+                cur = nxt
+                if self.is_leaf(cur):
+                    break
+            picks.append((nodes, actions))
+            blocked.add(cur)
+            up = cur
+            while up != root:                       # a node with no unblocked child is exhausted for this batch
+                up = parent[up]
+                if all(int(c) in blocked for c in self.child[up]):
+                    blocked.add(up)
+                else:
+                    break
+            for i, a in zip([root] + nodes[:-1], actions):
+                q = self.W[i, a] / self.N[i, a]
+                self.N[i, a] += 1.0
+                self.W[i, a] = q * self.N[i, a]
+        self.W, self.N = W0, N0
+        return picks
+
+    def expand_batch(self, leaves, model, use_means, samples):
+        """expand() for several leaves with ONE model call: rows = leaf*4 + action (the calculate_G_repeated layout,
+        src/util.py:57-60)."""
+        pi_hot = model.pi_one_hot if self.pi_dim == 4 else model.pi_one_hot_3
+        s = torch.stack([self.state[i] for i in leaves for _ in range(self.pi_dim)])
+        pi = torch.as_tensor(pi_hot).repeat(len(leaves), 1)
+        if use_means:
+            G, _, nxt, _ = model.calculate_G_mean(s, pi)
+        else:
+            G, _, nxt, _, _ = model.calculate_G(s, pi, samples=samples)
+        G = G.detach().to("cpu").reshape(len(leaves), self.pi_dim)
+        for j, i in enumerate(leaves):
+            self.W[i] -= G[j]
+            self.N[i] += 1.0
+            for a in range(self.pi_dim):
+                self.child[i, a] = self.add(nxt[j * self.pi_dim + a])
+
     def backpropagate(self, nodes, actions, G):
         for i, a in zip(nodes, actions):
             self.W[i, a] -= G
@@ -157,3 +215,45 @@ def active_inference_mcts(model, frame, params, o_shape=(64, 64, 1)):
         all_paths.append(actions)
         all_paths_G.append(sims.mean().item())
     return tree.most_visited_path(root), params.repeats, states_explored, all_paths, all_paths_G
+
+
+def active_inference_mcts_batched(model, frame, params, o_shape=(64, 64, 1), leaves=8):
+    """Batched-leaf variant of active_inference_mcts: every iteration claims up to `leaves` distinct
+    leaves (Tree.select_batch), expands them with ONE EFE evaluation of 4*leaves rows and simulates them with ONE
+    model.mcts_step_simulate_batch pass — two host waits per `leaves` expansions instead of two per expansion, and
+    batches large enough to occupy the GPU.  params.repeats still counts expansions.  leaves = 1 makes the decisions of
+    active_inference_mcts call for call (same model calls, same noise)."""
+    states_explored, all_paths, all_paths_G = 0, [], []
+    if frame is None or (hasattr(frame, "__len__") and len(frame) == 0):
+        return [0], 0, states_explored, all_paths, all_paths_G
+    samples = int(getattr(params, "samples", 1))
+    frame = torch.as_tensor(frame)
+    qs0_mean, _ = model.model_down.encoder(frame.reshape(1, *o_shape))
+    tree = Tree(model.pi_dim, 1 + model.pi_dim * (params.repeats + leaves + 2), params.C, params.using_prior_for_exploration)
+    root = tree.add(qs0_mean[0])
+    tree.Qpi[root] = model.model_top.encode_s(qs0_mean)[1][0].detach().to("cpu")
+    if params.use_habit and calc_threshold(tree.Qpi[root], axis=0) > params.threshold:
+        return [torch.multinomial(tree.Qpi[root], 1).item()], 0, states_explored, all_paths, all_paths_G
+
+    tree.expand(root, model, params.use_means, samples)
+    done = 0
+    while done < params.repeats:
+        if calc_threshold(normalization(tree.N[root]), axis=0) > params.threshold:
+            return tree.most_visited_path(root), done, states_explored, all_paths, all_paths_G
+        picks = tree.select_batch(root, min(leaves, params.repeats - done))
+        ids = [nodes[-1] for nodes, _ in picks]
+        starts = torch.stack([tree.state[i] for i in ids])          # read before the expansion appends children
+        tree.expand_batch(ids, model, params.use_means, samples)
+        sims = torch.zeros(len(picks))
+        for _ in range(params.simulation_repeats):
+            states_explored += params.simulation_depth * len(picks)
+            G, _, qpi = model.mcts_step_simulate_batch(starts, params.simulation_depth, use_means=False)
+            sims += torch.as_tensor(G, dtype=torch.float32).reshape(-1)
+            tree.Qpi[ids] = qpi.detach().to("cpu")
+        sims /= params.simulation_repeats
+        for (nodes, actions), g in zip(picks, sims):
+            tree.backpropagate([root] + nodes[:-1], actions, g)
+            all_paths.append(actions)
+            all_paths_G.append(g.item())
+        done += len(picks)
+    return tree.most_visited_path(root), done, states_explored, all_paths, all_paths_G

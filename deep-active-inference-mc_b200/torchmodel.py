@@ -297,3 +297,10 @@ class ActiveInferenceModel:
         self._sync()
         G, pi0, qpi = self._engine.mcts_simulate(starting_s, depth, use_means)
         return G, self._host(pi0), self._host(qpi)
+
+    def mcts_step_simulate_batch(self, starting_s, depth, use_means=False):
+        """K simulations in one pass: starting_s (K,10) -> (G (K,), pi0 (K,depth,4), Qpi (K,4)),
+        all host tensors; K = 1 equals mcts_step_simulate."""
+        self._sync()
+        G, pi0, qpi = self._engine.mcts_simulate_batch(starting_s, depth, use_means)
+        return G, self._host(pi0), self._host(qpi)

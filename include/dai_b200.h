@@ -157,6 +157,14 @@ DAI_API int  dai_rollout_host(dai_handle* h, const float* o_host, const float* p
 DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means,
                        float* G_host, float* pi0, float* qpi, void* stream);
 
+/* ---- next row: batched-leaf MCTS.  K independent mcts_step_simulate rollouts in ONE pass: the K
+ * habit-policy rollouts run as K CTAs of one launch, the K*depth trajectory rows go through ONE
+ * calculate_G_given_trajectory evaluation (row = k*depth + t) and the K per-trajectory means come back with one
+ * stream wait.  starting_s (K,10) device; pi0 (K*depth,4), qpi (K,4) device; G_host (K) host.  Noise: rollout k draws
+ * with row index k, trajectory row r with row index r, so K = 1 is exactly dai_mcts_simulate.  2 call indices. */
+DAI_API int  dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int depth, int use_means,
+                                     float* G_host, float* pi0, float* qpi, void* stream);
+
 /* ---- next row: batched many-roots action selection -------------------------
  * The action choice of make_batch_dsprites_active_inference (src/util.py:46-53,66-68) for R roots whose summed EFE
  * G (4R, row = root*4 + action) is already on the device: per root x = -G - max(-G), e = exp(x / temperature),

@@ -78,26 +78,27 @@ class PhiloxNoise(_Noise):
         super().__init__(training)
         self.key = int(key)
         self.tape = tape
+        self.row0 = 0          # noise row of batch row 0 (batched simulations: rollout k draws as row k)
 
     def dropout(self, x, site):
         if not self.training:
             return x
         m = torch.from_numpy(philox.dropout_mask(self.key, self.step, self.sample, site,
-                                                 np.arange(x.shape[0]), x.shape[1]))
+                                                 self.row0 + np.arange(x.shape[0]), x.shape[1]))
         if self.tape is not None:
             self.tape.append(("d", m))
         return x * m
 
     def randn_like(self, x, site):
         e = torch.from_numpy(philox.normals(self.key, self.step, self.sample, site,
-                                            np.arange(x.shape[0]), x.shape[1]))
+                                            self.row0 + np.arange(x.shape[0]), x.shape[1]))
         if self.tape is not None:
             self.tape.append(("r", e))
         return e
 
     def categorical(self, q, site, row=0):
         """Inverse-CDF draw in float32: first i with u*total < cumsum_i (fallback last)."""
-        u = philox.uniform24(self.key, self.step, self.sample, site, row)
+        u = philox.uniform24(self.key, self.step, self.sample, site, self.row0 + row)
         c = np.float32(0.0)
         cdf = []
         for v in q.detach().numpy().astype(np.float32):
@@ -336,11 +337,8 @@ def calculate_G_given_trajectory(W, s0_traj, ps1_traj, ps1_mean_traj, ps1_logvar
     return -term0 + term1 + (term2_1 - term2_2)
 
 
-def mcts_step_simulate(W, starting_s, depth, use_means, nz_roll, nz_traj):
-    """src/torchmodel.py:354-393.  Habit-policy rollout of `depth` B=1 transitions (noise
-    cursor: step = t, row 0), then calculate_G_given_trajectory over the depth rows under
-    the next call key.  A categorical draw that cannot be made (NaN / negative / zero-sum
-    probabilities, the reference's bare `except`, :365-367,380-381) falls back to action 0."""
+def _simulate_rollout(W, starting_s, depth, use_means, nz_roll):
+    """The habit-policy rollout of src/torchmodel.py:354-388: `depth` B=1 transitions, noise cursor step = t."""
     s0 = torch.zeros((depth, S_DIM))
     ps1 = torch.zeros((depth, S_DIM))
     ps1_mean = torch.zeros((depth, S_DIM))
@@ -360,8 +358,32 @@ def mcts_step_simulate(W, starting_s, depth, use_means, nz_roll, nz_traj):
         ps1[t], ps1_mean[t], ps1_logvar[t] = new[0], mean[0], logvar[0]
         if t + 1 < depth:
             s0[t + 1] = mean[0] if use_means else new[0]
+    return s0, ps1, ps1_mean, ps1_logvar, pi0, qpi_ret
+
+
+def mcts_step_simulate(W, starting_s, depth, use_means, nz_roll, nz_traj):
+    """src/torchmodel.py:354-393.  Habit-policy rollout of `depth` B=1 transitions (noise
+    cursor: step = t, row 0), then calculate_G_given_trajectory over the depth rows under
+    the next call key.  A categorical draw that cannot be made (NaN / negative / zero-sum
+    probabilities, the reference's bare `except`, :365-367,380-381) falls back to action 0."""
+    s0, ps1, ps1_mean, ps1_logvar, pi0, qpi_ret = _simulate_rollout(W, starting_s, depth, use_means, nz_roll)
     G = torch.mean(calculate_G_given_trajectory(W, s0, ps1, ps1_mean, ps1_logvar, pi0, nz_traj)).item()
     return G, pi0, qpi_ret
+
+
+def mcts_step_simulate_batch(W, starts, depth, use_means, nz_roll, nz_traj):
+    """K simulations in one pass (include/dai_b200.h dai_mcts_simulate_batch): rollout k is the
+    reference's rollout drawn with noise row k; the K*depth trajectory rows (row = k*depth + t) go through ONE
+    calculate_G_given_trajectory call; G[k] = mean over trajectory k.  K = 1 is mcts_step_simulate."""
+    starts = starts.reshape(-1, S_DIM)
+    parts = []
+    for k in range(starts.shape[0]):
+        nz_roll.row0 = k
+        parts.append(_simulate_rollout(W, starts[k], depth, use_means, nz_roll))
+    nz_roll.row0 = 0
+    s0, ps1, mean, logvar, pi0 = (torch.cat([p[i] for p in parts]) for i in range(5))
+    G = calculate_G_given_trajectory(W, s0, ps1, mean, logvar, pi0, nz_traj).reshape(-1, depth).mean(dim=1)
+    return G, pi0.reshape(-1, depth, PI_DIM), torch.stack([p[5] for p in parts])
 
 
 def select_actions(sum_G, temperature, nz):
@@ -446,6 +468,9 @@ class OracleModel:
 
     def mcts_step_simulate(self, starting_s, depth, use_means=False):
         return mcts_step_simulate(self.W, starting_s, depth, use_means, self._nz(), self._nz())
+
+    def mcts_step_simulate_batch(self, starting_s, depth, use_means=False):
+        return mcts_step_simulate_batch(self.W, torch.as_tensor(starting_s), depth, use_means, self._nz(), self._nz())
 
     def select_actions(self, o_roots, steps=1, samples=10, calc_mean=False, temperature=10.0):
         o = torch.as_tensor(o_roots).reshape(-1, 1, 64, 64)
