@@ -79,6 +79,10 @@ struct dai_handle {
     DevBuf mlpA, mlpB, ps, zB, h3, mask, act0, act1, act2, act3, img, hsum, reward, qc1, qc2, qc3, qc4, qs_out, acc, carry,
         pi_eye, traj, root, stage_in, stage_out, scratch;
     LayerTimer timer;
+    // frame producer
+    DevBuf sprites, sprite_stage, frame_flag;
+    long long sprite_count = 0;
+    long long place[6] = {0, 0, 0, 0, 0, 0}, sizes[6] = {0, 0, 0, 0, 0, 0};
     float* pinned = nullptr;   // small host result buffer
     size_t pinned_cap = 0;
 };
@@ -594,7 +598,7 @@ int dai_destroy(dai_handle* h) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
-                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (void* p : h->wallocs) cudaFree(p);
     tc_release(&h->tcw);
@@ -667,7 +671,7 @@ int dai_get_stats(dai_handle* h, dai_stats* out, int reset) {
     size_t total = 0;
     DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
-                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch};
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag};
     for (DevBuf* b : bufs) total += b->cap;
     out->workspace_bytes = total;
     if (reset) { h->launches = 0; h->calls = 0; }
@@ -889,6 +893,57 @@ int dai_select_actions(dai_handle* h, const float* G, int R, float temperature, 
     ++h->calls;
     h->launches += launch_select_actions(G, R, temperature, nk, Ppi, logPpi, choice, (cudaStream_t)stream);
     return post_launch(h, "select_actions");
+}
+
+int dai_frames_set_sprites(dai_handle* h, const uint8_t* imgs_host, int64_t count, const int32_t* latents_sizes, void* stream) {
+    if (!h) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (!imgs_host || !latents_sizes || count <= 0) return fail(h, DAI_E_INVALID, "frames_set_sprites: bad arguments");
+    long long prod = 1;
+    for (int i = 0; i < 6; ++i) {
+        if (latents_sizes[i] <= 0) return fail(h, DAI_E_INVALID, "frames_set_sprites: latents_sizes[%d] = %d", i, latents_sizes[i]);
+        prod *= latents_sizes[i];
+    }
+    if (prod != count) return fail(h, DAI_E_INVALID, "frames_set_sprites: %lld sprites but latents_sizes multiply to %lld", (long long)count, prod);
+    cudaStream_t st = (cudaStream_t)stream;
+    RET(reserve(h, h->sprites, (size_t)count * 512));
+    RET(reserve(h, h->frame_flag, sizeof(int32_t)));
+    const long long chunk = 16384;                              // 64 MB of uint8 pixels per staging pass
+    RET(reserve(h, h->sprite_stage, (size_t)std::min<long long>(chunk, count) * 4096));
+    for (long long first = 0; first < count; first += chunk) {
+        const long long n = std::min<long long>(chunk, count - first);
+        CK(cudaMemcpyAsync(h->sprite_stage.p, imgs_host + first * 4096, (size_t)n * 4096, cudaMemcpyHostToDevice, st));
+        h->launches += launch_pack_sprites(ptr<uint8_t>(h->sprite_stage), n, ptr<uint32_t>(h->sprites), first, st);
+        RET(post_launch(h, "pack sprites"));
+        CK(cudaStreamSynchronize(st));                          // the staging buffer (and pageable host memory) is reused
+    }
+    h->sprite_count = count;
+    long long pv = 1;
+    for (int i = 5; i >= 0; --i) { h->sizes[i] = latents_sizes[i]; h->place[i] = pv; pv *= latents_sizes[i]; }
+    return DAI_OK;
+}
+
+int dai_frames_render(dai_handle* h, const float* s, int s_stride, const float* last_r, int G, int reference_bases,
+                      float* o, int32_t* n_bad_host, void* stream) {
+    if (!h) return DAI_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (h->sprite_count <= 0) return fail(h, DAI_E_INVALID, "frames_render: no sprite table (dai_frames_set_sprites)");
+    if (!s || !last_r || !o || G <= 0 || s_stride < 6) return fail(h, DAI_E_INVALID, "frames_render: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameArgs a{};
+    a.s = s; a.s_stride = s_stride; a.last_r = last_r; a.bits = ptr<uint32_t>(h->sprites); a.count = h->sprite_count;
+    for (int i = 0; i < 6; ++i) a.base[i] = reference_bases ? h->sizes[i] : h->place[i];
+    a.o = o; a.n_bad = ptr<int32_t>(h->frame_flag);
+    ++h->calls;
+    CK(cudaMemsetAsync(h->frame_flag.p, 0, sizeof(int32_t), st));
+    h->launches += launch_render_frames(a, G, st);
+    RET(post_launch(h, "render frames"));
+    if (n_bad_host) {
+        CK(cudaMemcpyAsync(h->pinned, h->frame_flag.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        *n_bad_host = *reinterpret_cast<int32_t*>(h->pinned);
+    }
+    return DAI_OK;
 }
 
 int dai_profile_begin(dai_handle* h) {

@@ -137,5 +137,19 @@ struct SimArgs {
 };
 int  launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st);
 
+// ---- frame producer (dai_frames.cu; src/game_environment.py:39-66) --------------------------
+struct FrameArgs {
+    const float* s;        // [G][s_stride] latent classes as floats (Game.current_s), first 6 used
+    int32_t s_stride;
+    const float* last_r;   // [G]
+    const uint32_t* bits;  // [count][128] bit-packed sprites
+    long long count;
+    long long base[6];     // index weights
+    float* o;              // [G][4096]
+    int32_t* n_bad;        // games whose index / reward is out of range (frame zeroed)
+};
+int  launch_pack_sprites(const uint8_t* px, long long count, uint32_t* bits, long long first, cudaStream_t st);
+int  launch_render_frames(const FrameArgs& a, int G, cudaStream_t st);
+
 
 }  // namespace dai

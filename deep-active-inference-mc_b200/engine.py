@@ -63,6 +63,9 @@ SIGNATURES = {
                                          _vp, _vp, _vp]),
     "dai_mcts_simulate_batch": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                ctypes.POINTER(ctypes.c_float), _vp, _vp, _vp]),
+    "dai_frames_set_sprites": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), _vp]),
+    "dai_frames_render": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp,
+                                         ctypes.POINTER(ctypes.c_int32), _vp]),
     "dai_select_actions": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "dai_profile_begin": (ctypes.c_int, [_vp]),
     "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
@@ -319,3 +322,25 @@ class Engine:
         self._ck(self.lib.dai_mcts_simulate_batch(self.h, _p(s), K, depth, 1 if use_means else 0, G, _p(pi0), _p(qpi),
                                                   self._stream()))
         return torch.tensor(list(G), dtype=torch.float32), pi0, qpi
+
+    # ------------------------------------------------------------------ frame producer
+    def set_sprites(self, imgs, latents_sizes):
+        """imgs: HOST uint8 (count,64,64[,1]) binary sprite table (dSprites `imgs`); latents_sizes: 6 ints."""
+        imgs = torch.as_tensor(imgs).to(torch.uint8).reshape(-1, 4096).contiguous()
+        if imgs.is_cuda:
+            imgs = imgs.cpu()
+        sizes = (ctypes.c_int32 * 6)(*[int(x) for x in latents_sizes])
+        self._ck(self.lib.dai_frames_set_sprites(self.h, _p(imgs), imgs.shape[0], sizes, self._stream()))
+
+    def render_frames(self, current_s, last_r, reference_bases=False, check=True):
+        """Game.current_frame_all: current_s (G, >=6), last_r (G) -> (G,1,64,64) float32 on the device."""
+        s = self.dev(current_s)
+        r = self.dev(last_r).reshape(-1)
+        G = s.shape[0]
+        o = self.new(G, 1, 64, 64)
+        bad = ctypes.c_int32(0)
+        self._ck(self.lib.dai_frames_render(self.h, _p(s), s.shape[1], _p(r), G, 1 if reference_bases else 0, _p(o),
+                                            ctypes.byref(bad) if check else None, self._stream()))
+        if check and bad.value:
+            raise ValueError("Error: %d game(s) with a sprite index outside the table or a reward outside [-1, 1]" % bad.value)
+        return o

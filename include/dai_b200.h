@@ -173,6 +173,21 @@ DAI_API int  dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int
 DAI_API int  dai_select_actions(dai_handle* h, const float* G, int R, float temperature,
                                 float* Ppi, float* logPpi, int32_t* choice, void* stream);
 
+/* ---- next row: the frame producer in front of the path ------------------------------------
+ * Game.current_frame_all / s_to_o (src/game_environment.py:39-66) for G games in one kernel instead of a Python loop.
+ * dai_frames_set_sprites uploads the dSprites `imgs` table (HOST uint8 (count,64,64), binary) once and keeps it
+ * bit-packed in HBM (512 B per sprite); latents_sizes[6] = metadata['latents_sizes'] ([1,3,6,40,32,32]) must multiply
+ * to count.  dai_frames_render: s (G, s_stride >= 6) = Game.current_s (latent classes as floats), last_r (G), both on
+ * the device -> o (G,4096) float32: sprite[index] with the reward bar on rows 0..2 (r in [0,1]: columns 0..31 = r;
+ * r in [-1,0): columns 32..63 = -r).  index = sum_i trunc(s_i) * base_i with base = the mixed-radix place values of
+ * latents_sizes, or — reference_bases != 0 — the reference's s_bases as shipped (= latents_sizes).
+ * Where the reference raises (index outside the table, reward outside [-1,1]) the frame is zeroed and counted: if
+ * n_bad_host is not NULL the call waits for the stream and stores the count there.  No noise, 0 call indices. */
+DAI_API int  dai_frames_set_sprites(dai_handle* h, const uint8_t* imgs_host, int64_t count, const int32_t* latents_sizes,
+                                    void* stream);
+DAI_API int  dai_frames_render(dai_handle* h, const float* s, int s_stride, const float* last_r, int G, int reference_bases,
+                               float* o, int32_t* n_bad_host, void* stream);
+
 /* ---- per-kernel timing (bench.py's roofline leg) -----------------------------------------
  * Between dai_profile_begin and dai_profile_end every decoder contraction kernel is bracketed by
  * CUDA events on its launch stream.  dai_profile_end waits for the stream and returns, per layer
