@@ -320,7 +320,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act1, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act2, (size_t)ch * 65536 * esz));
-    RET(reserve(h, h->act3, (size_t)ch * 131072 * esz));
+    RET(reserve(h, h->act3, tc ? (size_t)ch * PROJ_ROW_FLOATS * sizeof(float) : (size_t)ch * 131072 * esz));
     fc.h3 = tc ? nullptr : ptr<float>(h->h3);
     fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
     fc.rows_pad = rows_pad;
@@ -932,7 +932,8 @@ int dai_frames_render(dai_handle* h, const float* s, int s_stride, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     FrameArgs a{};
     a.s = s; a.s_stride = s_stride; a.last_r = last_r; a.bits = ptr<uint32_t>(h->sprites); a.count = h->sprite_count;
-    for (int i = 0; i < 6; ++i) a.base[i] = reference_bases ? h->sizes[i] : h->place[i];
+    static const long long kReferenceBases[6] = {1, 3, 6, 40, 32, 32};     // Game.s_bases, src/game_environment.py:25
+    for (int i = 0; i < 6; ++i) a.base[i] = reference_bases ? kReferenceBases[i] : h->place[i];
     a.o = o; a.n_bad = ptr<int32_t>(h->frame_flag);
     ++h->calls;
     CK(cudaMemsetAsync(h->frame_flag.p, 0, sizeof(int32_t), st));
@@ -987,13 +988,15 @@ int dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, in
     RET(reserve(h, h->act1, (size_t)nrows * hw_out * 64 * 4));
     h->launches += tc_to_blocked(in, nrows, hw_in, 64, h->act0.p, st);
     std::string terr;
-    void* dst = layer == 3 ? (void*)out : h->act1.p;
+    if (layer == 3) RET(reserve(h, h->act3, (size_t)nrows * PROJ_ROW_FLOATS * sizeof(float)));
+    void* dst = layer == 3 ? h->act3.p : h->act1.p;
     h->timer.begin(layer, nrows, st);
     const int nl = tc_layer(h->tcw, h->w, precision, layer, h->act0.p, dst, nrows, st, &terr);
     if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core layer: %s", terr.c_str());
     h->timer.end(st);
     h->launches += nl;
     if (layer != 3) h->launches += tc_from_blocked(h->act1.p, nrows, hw_out, 64, out, st);
+    else h->launches += launch_proj_rows(ptr<float>(h->act3), nrows, out, st);
     return post_launch(h, "debug layer (tc)");
 }
 

@@ -68,6 +68,12 @@ int  launch_ct3_simt(const DevWeights& w, const float* act2, int nrows, float* a
 
 // last deconv + sigmoid + EFE pixel terms.  Per row: hsum = sum_px H_bernoulli(p),
 // reward = check_reward(p).  Rows of set 0 (r < img_rows) also write the image.
+// Output of the tensor-core ct3 layer per image: 3 row planes e[kh][64][64] of the last deconv (its channel and kw sums
+// done), then the tile-border terms [kh 3][oy 64][tile x 4][2] (dai_tc.cu, OUT_PROJ epilogue).
+constexpr int PROJ_TILES_X = 4;
+constexpr int PROJ_EDGE = 3 * 64 * PROJ_TILES_X * 2;
+constexpr int PROJ_ROW_FLOATS = 3 * 4096 + PROJ_EDGE;
+
 struct Ct4Args {
     const float* act3;     // [nrows][64][64][32]
     int32_t row0, nrows;   // global row offset of this chunk
@@ -77,8 +83,10 @@ struct Ct4Args {
     float* reward;         // [rows]
 };
 int  launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st);
-// same, from the 9 tap projections [nrows][9][64][64] the tensor-core ct3 epilogue writes into act3
+// same, from the row planes + border terms [nrows][PROJ_ROW_FLOATS] the tensor-core ct3 epilogue writes into act3
 int  launch_ct4_gather(const DevWeights& w, const Ct4Args& a, cudaStream_t st);
+// test hook: the finished row planes e[kh] (border terms added), [nrows][3][4096]
+int  launch_proj_rows(const float* act3, int nrows, float* out, cudaStream_t st);
 
 // ---- encoder -------------------------------------------------------------------------
 struct QsArgs {

@@ -562,32 +562,30 @@ __global__ void __launch_bounds__(256) k_ct4_gather(DevWeights w, Ct4Args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rl = blockIdx.x;
     const int r = a.row0 + rl;
-    const float* D = a.act3 + (size_t)rl * 9 * IMG;
+    const float* D = a.act3 + (size_t)rl * PROJ_ROW_FLOATS;          // e[kh][64][64], then the tile-border terms
+    const float* E = D + 3 * IMG;                                      // [kh][iy][tile x][0: first column's d[kh,0], 1: last column's d[kh,2]]
     const float bias = __ldg(w.ct4_b);
     const bool write_img = r < a.img_rows;
     const float d = 0.00001f, c1 = 1.00001f;
     const float la_top = logf(d + 1.0f), lb_top = logf(c1 - 1.0f);
     const float la_bot = logf(d + 0.0f), lb_bot = logf(c1 - 0.0f);
     float hacc = 0.0f, racc = 0.0f;
-    // each thread finishes 4 consecutive pixels: per tap plane one aligned float4 plus the element to its left / right
+    // each thread finishes 4 consecutive pixels: x[oy][ox] = b + sum_kh e[kh][oy+1-kh][ox]; a pixel in the first / last
+    // column of a ct3 tile (16 output columns) also takes the term its neighbour tile exported
     for (int q = tid; q < IMG / 4; q += 256) {
         const int oy = q >> 4, ox = (q & 15) << 2;
+        const int tile = ox >> 4;
+        const bool first = (ox & 15) == 0 && ox > 0, last = (ox & 15) == 12 && ox + 3 < 63;
         float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             const int iy = oy + 1 - kh;
             if (iy < 0 || iy >= 64) continue;
-            const float* rowp = D + (size_t)(kh * 3) * IMG + iy * 64 + ox;
-            // kw = 0 reads ix = ox+1 .. ox+4, kw = 1 reads ox .. ox+3, kw = 2 reads ox-1 .. ox+2
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(rowp));                 // plane kw = 0, ix = ox..ox+3
-            const float r0 = ox + 4 < 64 ? __ldg(rowp + 4) : 0.0f;
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(rowp + IMG));           // plane kw = 1
-            const float4 v2 = __ldg(reinterpret_cast<const float4*>(rowp + 2 * IMG));       // plane kw = 2
-            const float l2 = ox > 0 ? __ldg(rowp + 2 * IMG - 1) : 0.0f;
-            acc[0] += v0.y + v1.x + l2;
-            acc[1] += v0.z + v1.y + v2.x;
-            acc[2] += v0.w + v1.z + v2.y;
-            acc[3] += r0 + v1.w + v2.z;
+            float4 v = __ldg(reinterpret_cast<const float4*>(D + (size_t)kh * IMG + iy * 64 + ox));
+            const float* e = E + ((size_t)kh * 64 + iy) * (PROJ_TILES_X * 2);
+            if (first) v.x += __ldg(e + (tile - 1) * 2 + 1);
+            if (last) v.w += __ldg(e + (tile + 1) * 2);
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
         }
         float pv[4];
 #pragma unroll
@@ -610,6 +608,26 @@ __global__ void __launch_bounds__(256) k_ct4_gather(DevWeights w, Ct4Args a) {
         a.hsum[r] = hs;
         a.reward[r] = rs * (1.0f / 4096.0f) * 10.0f;
     }
+}
+
+// test hook: finished row planes out[n][kh][4096] = e[kh] + the neighbour tiles' border terms
+__global__ void k_proj_rows(const float* __restrict__ act3, int nrows, float* __restrict__ out) {
+    const size_t n = (size_t)nrows * 3 * IMG;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(i & 63), iy = (int)((i >> 6) & 63), kh = (int)((i >> 12) % 3);
+        const size_t row = i / (3 * IMG);
+        const float* D = act3 + row * PROJ_ROW_FLOATS;
+        const float* e = D + 3 * IMG + ((size_t)kh * 64 + iy) * (PROJ_TILES_X * 2);
+        float v = D[(size_t)kh * IMG + iy * 64 + ox];
+        if ((ox & 15) == 0 && ox > 0) v += e[((ox >> 4) - 1) * 2 + 1];
+        if ((ox & 15) == 15 && ox < 63) v += e[((ox >> 4) + 1) * 2];
+        out[i] = v;
+    }
+}
+
+int launch_proj_rows(const float* act3, int nrows, float* out, cudaStream_t st) {
+    k_proj_rows<<<512, 256, 0, st>>>(act3, nrows, out);
+    return 1;
 }
 
 int launch_ct4_gather(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {

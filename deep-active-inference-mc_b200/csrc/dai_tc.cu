@@ -182,7 +182,7 @@ struct ConvParams {
     int32_t nprod;           // 3: bf16x3, 1: bf16x1
     const uint8_t* wpack;    // packed weights (see pack_layer)
     const float* bias;       // [Cout]
-    void* out;               // blocked bf16 planes (ct1, ct2) or projected fp32 planes [row][9][HO][WO] (ct3)
+    void* out;               // blocked bf16 planes (ct1, ct2) or the last deconv's row planes + border terms [row][PROJ_ROW_FLOATS] (ct3)
     float2 w4[288];          // ct3 only: last deconv's weights [c 32][tap 9], each duplicated (w, w) for packed
                              // fp32x2 FMAs over the (left, right) output pixel pair (kernel params = constant bank)
     int32_t two_pass;        // 1: per tile all hi-plane MMAs, then all lo-plane MMAs (each ring slot is released as soon
@@ -530,9 +530,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     // Last tensor-core layer.  The next layer (ConvT 32->1, k3 s1 p1) is linear in this output,
                     // so its channel contraction is done here, in registers, per output pixel:
                     //   d[t] = sum_c relu(acc[c] + b[c]) * w4[c][t],  t = kh*3+kw
-                    // and only the 9 projections leave the SM ([row][t][HO][WO] fp32, 36 B/pixel instead of 128).
-                    // With 16 epilogue warps the 9 taps are split 5 + 4 between two warps of the same (quarter, py).
-                    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * 9 * HO * WO;
+                    // and its kw sum too, across the lanes of a tile row (lane = tx + 8*ty_local):
+                    //   e[kh][oy][ox] = d[kh,0][oy][ox+1] + d[kh,1][oy][ox] + d[kh,2][oy][ox-1]
+                    // Only the 3 row planes leave the SM ([row][3][HO][WO] fp32, 12 B/pixel instead of 128), plus,
+                    // per tile row, the two terms that cross the tile's left / right border (PROJ_EDGE floats per
+                    // image after the planes: [kh][oy][tile x][0: d[kh,0] of the tile's first column, wanted by the
+                    // tile to the left; 1: d[kh,2] of its last column, wanted by the tile to the right]).  The pixel
+                    // kernel (k_ct4_rows) adds them and finishes sum over kh, sigmoid, entropy, reward.
+                    float* out = reinterpret_cast<float*>(p.out) + (size_t)row * PROJ_ROW_FLOATS;
                     const size_t o = (size_t)oy * WO + ox;
                     uint32_t rl[32], rr[32];
                     tmem_ld32(tbase + slot_l * 32, rl);
@@ -556,9 +561,22 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         }
                         if ((p.dbg & 4) && acc[0] == 123ull) {
                         } else {
+                            const int txl = lane & 7;
+                            float* edge = out + 3 * HO * WO + ((size_t)oy * C::TILES_X + (t % C::TILES_X)) * 2;
 #pragma unroll
-                        for (int t9 = 0; t9 < 9; ++t9)
-                            *reinterpret_cast<unsigned long long*>(out + (size_t)t9 * HO * WO + o) = acc[t9];
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const float dl0 = __uint_as_float((uint32_t)acc[kh * 3 + 0]), dr0 = __uint_as_float((uint32_t)(acc[kh * 3 + 0] >> 32));
+                                const float dl1 = __uint_as_float((uint32_t)acc[kh * 3 + 1]), dr1 = __uint_as_float((uint32_t)(acc[kh * 3 + 1] >> 32));
+                                const float dl2 = __uint_as_float((uint32_t)acc[kh * 3 + 2]), dr2 = __uint_as_float((uint32_t)(acc[kh * 3 + 2] >> 32));
+                                const float from_left = __shfl_up_sync(0xffffffffu, dr2, 1, 8);     // d[kh,2] of pixel ox-1
+                                const float from_right = __shfl_down_sync(0xffffffffu, dl0, 1, 8);  // d[kh,0] of pixel ox+2
+                                float2 e;
+                                e.x = (dr0 + dl1) + (txl > 0 ? from_left : 0.0f);
+                                e.y = (dr1 + dl2) + (txl < 7 ? from_right : 0.0f);
+                                *reinterpret_cast<float2*>(out + (size_t)kh * HO * WO + o) = e;
+                                if (txl == 0) edge[(size_t)kh * HO * C::TILES_X * 2] = dl0;
+                                if (txl == 7) edge[(size_t)kh * HO * C::TILES_X * 2 + 1] = dr2;
+                            }
                         }
                     }
                 } else {
@@ -1229,7 +1247,7 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
         n += rc;
     }
     Ct4Args c4 = c4in;
-    c4.act3 = static_cast<const float*>(act3);     // projected planes [row][9][64][64]
+    c4.act3 = static_cast<const float*>(act3);     // row planes + border terms [row][PROJ_ROW_FLOATS]
     T.begin(4, nrows, st);
     n += launch_ct4_gather(w, c4, st);
     T.end(st);

@@ -29,7 +29,7 @@ class FrameProducer:
         for n in reversed(self.latents_sizes):
             out.append(pv)
             pv *= n
-        self.s_bases = torch.tensor(self.latents_sizes if self.reference_bases else out[::-1])
+        self.s_bases = torch.tensor([1, 3, 6, 40, 32, 32] if self.reference_bases else out[::-1])
         self.engine.set_sprites(imgs, self.latents_sizes)
 
     @classmethod

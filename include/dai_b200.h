@@ -180,7 +180,7 @@ DAI_API int  dai_select_actions(dai_handle* h, const float* G, int R, float temp
  * to count.  dai_frames_render: s (G, s_stride >= 6) = Game.current_s (latent classes as floats), last_r (G), both on
  * the device -> o (G,4096) float32: sprite[index] with the reward bar on rows 0..2 (r in [0,1]: columns 0..31 = r;
  * r in [-1,0): columns 32..63 = -r).  index = sum_i trunc(s_i) * base_i with base = the mixed-radix place values of
- * latents_sizes, or — reference_bases != 0 — the reference's s_bases as shipped (= latents_sizes).
+ * latents_sizes, or — reference_bases != 0 — the reference's s_bases as shipped ([1,3,6,40,32,32]).
  * Where the reference raises (index outside the table, reward outside [-1,1]) the frame is zeroed and counted: if
  * n_bad_host is not NULL the call waits for the stream and stores the count there.  No noise, 0 call indices. */
 DAI_API int  dai_frames_set_sprites(dai_handle* h, const uint8_t* imgs_host, int64_t count, const int32_t* latents_sizes,
@@ -200,7 +200,9 @@ DAI_API int  dai_profile_end(dai_handle* h, float ms[5], int64_t launches[5], in
  * One decoder contraction layer in isolation (layer 1: ConvT 64->64 s1 16x16; 2: ConvT 64->64 s2
  * 16x16->32x32; 3: ConvT 64->32 s2 32x32->64x64; src/torchmodel.py:120-124), bias + ReLU included,
  * fp32 NHWC in and out, in the given DAI_PREC_* arithmetic.  Used by tests to compare the tcgen05
- * kernels with the fp32 CUDA-core kernels layer by layer. */
+ * kernels with the fp32 CUDA-core kernels layer by layer.  Exception: layer 3 in a tensor-core precision returns what
+ * that kernel hands to the pixel kernel — the last deconv's channel and kw sums, out (nrows,3,4096):
+ * e[kh][oy][ox] = sum_kw sum_c relu(ct3)[oy][ox+1-kw][c] * w4[c][kh][kw]. */
 DAI_API int  dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, int nrows, float* out, void* stream);
 
 #ifdef __cplusplus

@@ -26,9 +26,14 @@ def test_tc_layer_matches_fp32(eng, layer, rows):
     x = x * (torch.rand(rows, hw_in, 64, device="cuda", generator=g) < 0.5) * 2.0
     ref = eng.debug_layer(layer, "fp32_simt", x)
     if layer == 3:
-        # the tensor-core ct3 epilogue emits <relu(out), w4[:, t]> for the 9 taps of the last deconv
+        # the tensor-core ct3 epilogue emits the last deconv's channel and kw sums:
+        # e[kh][oy][ox] = sum_kw <relu(out)[oy][ox+1-kw], w4[:, kh, kw]>
         w4 = torch.from_numpy(cases.weights_for("w0")["po_net.19.weight"]).cuda().reshape(32, 9)
-        ref = torch.einsum("npc,ct->ntp", ref.double(), w4.double()).float()
+        d = torch.einsum("npc,ct->ntp", ref.double(), w4.double()).reshape(rows, 3, 3, 64, 64)
+        e = d[:, :, 1].clone()
+        e[..., :-1] += d[:, :, 0][..., 1:]
+        e[..., 1:] += d[:, :, 2][..., :-1]
+        ref = e.reshape(rows, 3, 4096).float()
     got = eng.debug_layer(layer, "bf16x3", x)
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
