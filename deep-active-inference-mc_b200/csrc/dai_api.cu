@@ -406,7 +406,10 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
             RET(reserve(h, h->mlpA, rp * 576 * 2 * sizeof(unsigned short)));
             RET(reserve(h, h->mlpB, rp * 576 * 2 * sizeof(unsigned short)));
             const NoiseRows nr = map_noise_rows(a.map);
-            h->launches += launch_qs_conv4_kblocked(h->w, a.c3, n, rp, h->mlpA.p, st);
+            RET(reserve(h, h->qc4, tc_qs_conv4_scratch_bytes(n)));
+            const int n4 = tc_qs_conv4(h->tcw, h->cfg.precision, a.c3, n, h->qc4.p, rp, h->mlpA.p, st, &terr);
+            if (n4 < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder conv4: %s", terr.c_str());
+            h->launches += n4;
             int n0 = tc_dense_hidden(h->tcw, TC_QS0, h->cfg.precision, h->mlpA.p, h->mlpB.p, n, rp, nk, nr, 0, st, &terr);
             int n1 = n0 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_QS1, h->cfg.precision, h->mlpB.p, h->mlpA.p, n, rp, nk, nr, 1, st, &terr);
             int n2 = n1 < 0 ? -1 : tc_dense_hidden(h->tcw, TC_QS2, h->cfg.precision, h->mlpA.p, h->mlpB.p, n, rp, nk, nr, 2, st, &terr);

@@ -645,9 +645,11 @@ struct DenseParams {
     int32_t layer;               // dropout site = nr.site[set] + layer
 };
 
-template <int NT, bool HIDDEN>
+enum { EPI_FC4 = 0, EPI_HIDDEN = 1, EPI_CONV4 = 2 };
+
+template <int NT, int EPI>
 struct DenseCfg {
-    static constexpr int NS = NT == 256 ? 2 : 3;            // pipeline stages
+    static constexpr int NS = NT == 256 ? 2 : (NT == 128 ? 3 : 4);   // pipeline stages
     static constexpr int A_BYTES = 2 * 8 * 128 * 16;        // 32 KB: hi+lo, 8 kc, 128 rows
     static constexpr int B_BYTES = 2 * 8 * NT * 16;         // hi+lo, 8 kc, NT columns
     static constexpr int STAGE = A_BYTES + B_BYTES;
@@ -655,9 +657,9 @@ struct DenseCfg {
     static constexpr int THREADS = 128 + 256;               // 8 epilogue warps
 };
 
-template <int NT, bool HIDDEN>
+template <int NT, int EPI>
 __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
-    using D = DenseCfg<NT, HIDDEN>;
+    using D = DenseCfg<NT, EPI>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + D::NS * D::STAGE);
     uint64_t* full = bars;                 // [NS]
@@ -750,7 +752,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * NT + half * (NT / 2));
             uint4 drop = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             float sc = 1.0f;
-            if (HIDDEN && p.nk.training && row < p.nrows) {
+            if (EPI == EPI_HIDDEN && p.nk.training && row < p.nrows) {
                 int site, b;
                 uint32_t sample;
                 p.nr.decode(row, site, b, sample);
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                 tmem_ld32(tbase + c0, r);
                 if (row >= p.nrows) continue;
                 const int n0 = nt * NT + half * (NT / 2) + c0;
-                if (!HIDDEN) {
+                if (EPI == EPI_FC4) {
                     // FC4 column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel
                     // 8*kc + e.  A 256-column tile is one group of 4 pixels x 64 channels and the 32 columns loaded here
                     // are 4 pixels x 8 channels of one kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores.
@@ -798,7 +800,11 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                             split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
                                    ((mw >> j0) & 1u) ? sc : 0.0f, ((mw >> j1) & 1u) ? sc : 0.0f, hi[e], lo[e]);
                         }
-                        const size_t o = (size_t)((n0 >> 3) + q) * p.out_kc_stride + (size_t)row * 8;
+                        // HIDDEN: output k = column, row = row.  CONV4: GEMM row = image * 9 + output pixel, column = channel
+                        // -> the encoder FC1's operand, k = pixel * 64 + channel (NHWC flatten), row = image
+                        const int img = EPI == EPI_CONV4 ? row / 9 : row;
+                        const int kc_out = EPI == EPI_CONV4 ? (row - img * 9) * 8 + (n0 >> 3) + q : (n0 >> 3) + q;
+                        const size_t o = (size_t)kc_out * p.out_kc_stride + (size_t)img * 8;
                         *reinterpret_cast<uint4*>(p.out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(p.out + p.out_plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
@@ -832,9 +838,9 @@ struct LayerPack {
 struct TcImpl {
     LayerPack ct1, ct2, ct3, qc2, qc3;
     float w4[288];               // po_net.19.weight as [c][tap]
-    uint8_t* dense_w[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // TC_PS1 .. TC_QS2
-    float* dense_b[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int dense_k[7] = {0, 0, 0, 0, 0, 0, 0}, dense_n[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint8_t* dense_w[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // TC_PS1 .. TC_QS2, TC_QC4
+    float* dense_b[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int dense_k[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dense_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t* fc4_wpack = nullptr;
     float* fc4_bias = nullptr;     // po_net.9.bias in the tensor-core FC4's column order
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -1049,20 +1055,20 @@ int tc_from_blocked(const void* blocked, int rows, int hw, int C, float* nhwc, c
 }
 
 namespace {
-// torch Linear weight (N,K) -> [n_tile = N/128][k_chunk = K/64] blocks of [plane hi|lo][kc 8][128][8] bf16.
+// torch Linear weight (N,K) -> [n_tile = N/NT][k_chunk = K/64] blocks of [plane hi|lo][kc 8][NT][8] bf16.
 // kperm (optional) maps the GEMM's k index to the reference's input index.
 int pack_dense(TcImpl* im, int which, const std::vector<float>& W, const std::vector<float>& bias, int N, int K, const int* kperm,
-               std::vector<void*>* allocs, std::string* err) {
-    const int ntn = N / 128, kch = K / 64;
-    const size_t blk = (size_t)2 * 8 * 128 * 8;              // elements per block
+               std::vector<void*>* allocs, std::string* err, int NT = 128) {
+    const int ntn = N / NT, kch = K / 64;
+    const size_t blk = (size_t)2 * 8 * NT * 8;               // elements per block
     std::vector<uint16_t> host((size_t)ntn * kch * blk);
     for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) {
             const float v = W[(size_t)n * K + (kperm ? kperm[k] : k)];
             const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
-            const size_t o = ((size_t)(n / 128) * kch + k / 64) * blk + ((size_t)((k >> 3) & 7) * 128 + (n & 127)) * 8 + (k & 7);
+            const size_t o = ((size_t)(n / NT) * kch + k / 64) * blk + ((size_t)((k >> 3) & 7) * NT + (n % NT)) * 8 + (k & 7);
             host[o] = hi;
-            host[o + (size_t)8 * 128 * 8] = lo;
+            host[o + (size_t)8 * NT * 8] = lo;
         }
     void* d = nullptr;
     if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(dense weights)"; return -1; }
@@ -1098,8 +1104,9 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
             cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_dense<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, false>::SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_dense<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, true>::SMEM) != cudaSuccess) {
+            cudaFuncSetAttribute(k_tc_dense<256, EPI_FC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, EPI_FC4>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dense<128, EPI_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, EPI_HIDDEN>::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_dense<64, EPI_CONV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<64, EPI_CONV4>::SMEM) != cudaSuccess) {
             *err = std::string("cudaFuncSetAttribute(max dynamic smem): ") + cudaGetErrorString(cudaGetLastError());
             return -1;
         }
@@ -1119,6 +1126,14 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
                            i == TC_QS0 ? perm.data() : nullptr, allocs, err) != 0)
                 return -1;
     }
+    {   // encoder conv4 (Conv2d 64->64, k3 s2, 7x7 -> 3x3) as a GEMM over im2col rows: B[n = co][k = (kh*3+kw)*64 + ci]
+        const std::vector<float>& W = raw.at("qs_net.6.weight");          // (Cout, Cin, 3, 3)
+        std::vector<float> B((size_t)64 * 576);
+        for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < 64; ++ci)
+                for (int t = 0; t < 9; ++t) B[(size_t)co * 576 + t * 64 + ci] = W[((size_t)co * 64 + ci) * 9 + t];
+        if (pack_dense(im, TC_QC4, B, raw.at("qs_net.6.bias"), 64, 576, nullptr, allocs, err, 64) != 0) return -1;
+    }
     if (build_layer(raw.at("qs_net.2.weight"), 2, 32, 32, false, false, &im->qc2, allocs, err) != 0) return -1;
     if (build_layer(raw.at("qs_net.4.weight"), 2, 32, 64, false, false, &im->qc3, allocs, err) != 0) return -1;
     {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
@@ -1137,7 +1152,7 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
                 const float v = W[(size_t)e * 256 + k];
                 const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
                 const int kch = k >> 6, kc = (k >> 3) & 7, ke = k & 7;
-                const size_t blk = ((size_t)nt * 4 + kch) * ((DenseCfg<256, false>::B_BYTES / 2));
+                const size_t blk = ((size_t)nt * 4 + kch) * ((DenseCfg<256, EPI_FC4>::B_BYTES / 2));
                 const size_t o = blk + ((size_t)kc * 256 + nl) * 8 + ke;
                 host[o] = hi;
                 host[o + (size_t)8 * 256 * 8] = lo;
@@ -1196,8 +1211,35 @@ int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = ((rows + 127) / 128) * p.ntn;
-    k_tc_dense<128, true><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<128, true>::SMEM, st>>>(p);
+    k_tc_dense<128, EPI_HIDDEN><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<128, EPI_HIDDEN>::SMEM, st>>>(p);
     return 1;
+}
+
+// im2col of the encoder's conv4 (k3 s2 valid, 7x7x64 -> 3x3): c3 fp32 NHWC (rows,7,7,64) -> GEMM operand, K-blocked bf16
+// hi/lo [plane][kc 72][m_pad][8] with row m = image*9 + oy*3+ox and k = (kh*3+kw)*64 + ci.  One thread per (kc, m).
+__global__ void __launch_bounds__(256) k_conv4_im2col(const float* __restrict__ c3, int M, size_t m_pad, __nv_bfloat16* __restrict__ out) {
+    const size_t n = (size_t)M * 72;
+    const size_t plane = 72 * m_pad * 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i % M), kc = (int)(i / M);
+        const int img = m / 9, px = m - img * 9, oy = px / 3, ox = px - oy * 3;
+        const int tap = kc >> 3, kh = tap / 3, kw = tap - kh * 3, c0 = (kc & 7) * 8;
+        const float* src = c3 + (((size_t)img * 7 + 2 * oy + kh) * 7 + 2 * ox + kw) * 64 + c0;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * e], h0, l0);
+            split_bf16(v[2 * e + 1], h1, l1);
+            hi[e] = pack_bf16(h0, h1);
+            lo[e] = pack_bf16(l0, l1);
+        }
+        const size_t o = ((size_t)kc * m_pad + m) * 8;
+        *reinterpret_cast<uint4*>(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
 }
 
 // encoder conv2 + conv3 on tensor cores: c1 = conv1 output in parity-split blocked planes
@@ -1208,6 +1250,36 @@ int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const v
     if (!im) { *err = "tensor-core weights not packed"; return -1; }
     if (launch_conv<CfgQc2>(im, im->qc2, w.qc2_b, precision, c1, c2, rows, st, err) < 0) return -1;
     if (launch_conv<CfgQc3>(im, im->qc3, w.qc3_b, precision, c2, c3, rows, st, err) < 0) return -1;
+    return 2;
+}
+
+// encoder conv4 on tensor cores: c3 fp32 NHWC (rows,7,7,64) -> im2col (scratch: (rows*9 padded) x 576 x 2 planes bf16) ->
+// GEMM 576 -> 64 with bias + ReLU -> the K-blocked operand of the encoder's FC1 (k = pixel*64 + c), rows_pad rows
+size_t tc_qs_conv4_scratch_bytes(int rows) {
+    const size_t m_pad = ((size_t)rows * 9 + 127) / 128 * 128 + 128;
+    return m_pad * 576 * 2 * sizeof(__nv_bfloat16);
+}
+
+int tc_qs_conv4(const TcWeights& tw, int precision, const float* c3, int rows, void* scratch, size_t rows_pad, void* out,
+                cudaStream_t st, std::string* err) {
+    TcImpl* im = static_cast<TcImpl*>(tw.impl);
+    if (!im || !im->dense_w[TC_QC4]) { *err = "conv4 tensor-core weights not packed"; return -1; }
+    const int M = rows * 9;
+    const size_t m_pad = ((size_t)M + 127) / 128 * 128 + 128;
+    k_conv4_im2col<<<1184, 256, 0, st>>>(c3, M, m_pad, static_cast<__nv_bfloat16*>(scratch));
+    DenseParams p{};
+    p.a = static_cast<const __nv_bfloat16*>(scratch);
+    p.a_kc_stride = m_pad * 8; p.a_plane = 72 * m_pad * 8;
+    p.wpack = im->dense_w[TC_QC4]; p.bias = im->dense_b[TC_QC4];
+    p.nrows = M; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3; p.kchunks = 9; p.ntn = 1;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.out_kc_stride = rows_pad * 8; p.out_plane = 72 * rows_pad * 8;
+    p.nk.training = 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = (M + 127) / 128;
+    k_tc_dense<64, EPI_CONV4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<64, EPI_CONV4>::SMEM, st>>>(p);
     return 2;
 }
 
@@ -1224,7 +1296,7 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = ((nrows + 127) / 128) * 64;
-    k_tc_dense<256, false><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, false>::SMEM, st>>>(p);
+    k_tc_dense<256, EPI_FC4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, EPI_FC4>::SMEM, st>>>(p);
     return 1;
 }
 

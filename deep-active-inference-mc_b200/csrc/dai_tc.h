@@ -43,7 +43,7 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
                      cudaStream_t st, std::string* err, LayerTimer* timer = nullptr);
 
 // Hidden dense layers served by the tensor-core dense kernel
-enum { TC_PS1 = 0, TC_PS2, TC_PO1, TC_PO2, TC_QS0, TC_QS1, TC_QS2 };
+enum { TC_PS1 = 0, TC_PS2, TC_PO1, TC_PO2, TC_QS0, TC_QS1, TC_QS2, TC_QC4 };
 // bias + ReLU + keyed dropout (site of the row's set + layer); in/out are K-blocked bf16 hi/lo planes
 // [plane][K/8][rows_pad][8].  Returns launches or -1.
 int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* in, void* out, int rows, size_t rows_pad,
@@ -52,6 +52,12 @@ int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* i
 // Encoder conv2 (32->32, 31x31->15x15) and conv3 (32->64, 15x15->7x7) on tensor cores.  c1 / c2 are parity-split
 // channel-blocked bf16 hi/lo planes, c3 is fp32 NHWC (rows,7,7,64).  Returns launches or -1.
 int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
+                cudaStream_t st, std::string* err);
+
+// Encoder conv4 (64->64, k3 s2, 7x7 -> 3x3) as im2col + tcgen05 GEMM.  c3 fp32 NHWC (rows,7,7,64); out = the K-blocked
+// bf16 hi/lo operand of the encoder's FC1 ([plane][72][rows_pad][8], k = pixel*64 + c).  Returns launches or -1.
+size_t tc_qs_conv4_scratch_bytes(int rows);
+int tc_qs_conv4(const TcWeights& tw, int precision, const float* c3, int rows, void* scratch, size_t rows_pad, void* out,
                 cudaStream_t st, std::string* err);
 
 // One tensor-core layer (1: ct1, 2: ct2, 3: ct3) on channel-blocked bf16 hi/lo input planes.

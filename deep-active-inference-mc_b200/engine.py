@@ -77,7 +77,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdai_b200.so")
+    """The in-tree build.  DAI_B200_LIB (A/B measurements of two builds only) names another build of the same sources."""
+    return os.environ.get("DAI_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdai_b200.so")
 
 
 def load_library():
