@@ -311,10 +311,11 @@ def main():
                      "step_share_ms": {k: v[0] / min(args.steps, 3) for k, v in layers.items()}})
     line["roofline"] = roof
     if not args.no_cpu_baseline and not args.quick and world == 1:
-        cv, per_call, cores = cpu_reference_run(N, T, 3, 1)
+        ncalls = 24                                   # ~10 s of CPU work on the box's host cores (0.35 s per call)
+        cv, per_call, cores = cpu_reference_run(N, T, ncalls, 2)
         line["cpu_baseline"] = {"value": cv, "unit": "rollouts/s", "cores": cores, "kind": "port",
-                                "sample": "calculate_G_4_repeated(steps=1, samples=%d), 1 root, 3 timed calls "
-                                          "(%.2f s each), scaled by 1/T" % (N, per_call)}
+                                "sample": "calculate_G_4_repeated(steps=1, samples=%d), 1 root, %d timed calls "
+                                          "(%.2f s each), scaled by 1/T" % (N, ncalls, per_call)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -406,6 +406,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             const uint32_t w16 = smem_u32(smW) >> 4, a16 = smem_u32(smA) >> 4;
             int it = 0, cnt = 0;
             long long t_begin = clock64(), w_acc = 0, w_a = 0;
+            unsigned long long ns_begin;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it % C::NACC;
                 const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
@@ -451,6 +453,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             if (p.counters && lane == 0) {
                 long long* c = p.counters + (size_t)blockIdx.x * 8;
                 c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = it;
+                unsigned long long ns_end;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+                c[6] = (long long)(ns_end - ns_begin);
             }
         }
     } else if (warp < C::EPI_WARPS) {
@@ -1010,11 +1015,12 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
         cudaStreamSynchronize(st);
         long long h[8 * 512];
         cudaMemcpy(h, dbg_counters, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-        double a[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < grid; ++i) for (int j = 0; j < 6; ++j) a[j] += (double)h[i * 8 + j] / grid;
+        double a[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < grid; ++i) for (int j = 0; j < 7; ++j) a[j] += (double)h[i * 8 + j] / grid;
         if (printed++ % 23 == 3)
             fprintf(stderr, "[tc counters] mode %d nph %d rows %d: per CTA cycles: mma loop %.0f (wait acc_empty %.0f, wait a_full %.0f) | "
-                    "epilogue loop %.0f (wait acc_full %.0f) | tiles %.1f\n", C::MODE, C::NPH, nrows, a[0], a[1], a[2], a[3], a[4], a[5]);
+                    "epilogue loop %.0f (wait acc_full %.0f) | tiles %.1f | mma loop %.1f us => SM clock %.0f MHz\n", C::MODE, C::NPH, nrows, a[0], a[1], a[2], a[3], a[4], a[5],
+                    a[6] * 1e-3, a[6] > 0 ? a[0] / a[6] * 1e3 : 0.0);
     }
     return 1;
 }

@@ -144,3 +144,74 @@ def test_large_batch_and_many_samples_chunking():
     b = eng.calculate_G(s0, pi, 300, shard=(100, 300))
     assert torch.allclose(a["sums"] + b["sums"], big["sums"], rtol=1e-9, atol=1e-6)
     assert torch.equal(a["ps1"], big["ps1"]) and torch.equal(b["po1"], big["po1"])
+
+
+# ---- BASELINE.json configs at full size ----------------------------------------------------------------------
+
+def _frames4(seed):
+    import dai_b200.synthetic as syn
+    return torch.from_numpy(syn.make_frames(1, seed)).repeat(4, 1, 1, 1)
+
+
+def test_config2_full_size_matches_the_oracle():
+    """configs[1]: N=50 samples, T=10 steps, one root (4 action rows), against the CPU oracle on the same keyed noise."""
+    m = _model("w0", "bf16x3")
+    m.set_rng(cases.SEED, 0)
+    got = cases._g4(m, "cuda:0", 10, 50, False, 21)
+    ora = _oracle("w0")
+    ora.set_rng(cases.SEED, 0)
+    with torch.no_grad():
+        ref = cases._g4(ora, "cpu", 10, 50, False, 21)
+    got = {k: v.detach().cpu().numpy() for k, v in got.items()}
+    ref = {k: v.detach().cpu().numpy() for k, v in ref.items()}
+    assert cases.compare("config2", got, ref) == []
+
+
+def test_config3_many_samples_slice_matches_the_oracle_and_full_size_is_shard_additive():
+    """configs[2]: N=200, T=10.  Parity with the oracle on a T=2 slice (the oracle needs ~6 s per step at N=200); at the
+    full horizon the size-independent property: sample shards add up to the unsharded rollout, bit-equal carries."""
+    m = _model("w0", "bf16x3")
+    m.set_rng(cases.SEED, 0)
+    got = cases._g4(m, "cuda:0", 2, 200, False, 22)
+    ora = _oracle("w0")
+    ora.set_rng(cases.SEED, 0)
+    with torch.no_grad():
+        ref = cases._g4(ora, "cpu", 2, 200, False, 22)
+    assert cases.compare("config3", {k: v.detach().cpu().numpy() for k, v in got.items()},
+                         {k: v.detach().cpu().numpy() for k, v in ref.items()}) == []
+    eng = m._engine
+    o = _frames4(23).cuda()
+    eng.set_rng(9, 0)
+    full = eng.rollout(o, None, 10, 200, four=True)
+    sums = torch.zeros_like(full["sums"])
+    for j0, j1 in ((0, 70), (70, 71), (71, 200)):
+        eng.set_rng(9, 0)
+        part = eng.rollout(o, None, 10, 200, four=True, shard=(j0, j1))
+        sums += part["sums"]
+        assert torch.equal(part["po1"], full["po1"])
+    assert torch.allclose(sums, full["sums"], rtol=1e-9, atol=1e-6)
+    eng.set_rng(9, 0)
+    again = eng.rollout(o, None, 10, 200, four=True)
+    assert torch.equal(again["G"], full["G"]) and torch.equal(again["sums"], full["sums"])       # deterministic
+
+
+def test_config5_eight_sample_shards_add_up():
+    """configs[4]: N=800 samples over 8 ranks (100 each), T=15: the eight partial sums — what the one all-reduce adds —
+    equal the unsharded evaluation."""
+    from dai_b200.sharding import shard_range
+    m = _model("w0", "bf16x3")
+    eng = m._engine
+    m._sync()
+    o = _frames4(24).cuda()
+    eng.set_rng(3, 0)
+    full = eng.rollout(o, None, 15, 800, four=True)
+    sums = torch.zeros_like(full["sums"])
+    for r in range(8):
+        eng.set_rng(3, 0)
+        part = eng.rollout(o, None, 15, 800, four=True, shard=shard_range(800, r, 8))
+        sums += part["sums"]
+        assert torch.equal(part["po1"], full["po1"])
+    assert torch.allclose(sums, full["sums"], rtol=1e-9, atol=1e-6)
+    G, t0, t1, t2 = eng.combine(sums, 800)
+    assert torch.allclose(G, full["G"], rtol=1e-6, atol=1e-5)
+    assert torch.isfinite(G).all() and float(G.min()) > 0
