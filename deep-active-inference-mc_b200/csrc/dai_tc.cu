@@ -76,13 +76,6 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -237,7 +230,7 @@ struct Cfg : T {
     static constexpr int TMEM_COLS = ACC_COLS * NACC < 32 ? 32 : ACC_COLS * NACC;
     static constexpr int W_BYTES = 9 * T::NPH * T::KCIN * 32;  // all 9 taps, hi + lo, resident
     static constexpr int SMEM_A = T::NA * PLANE_A;
-    static constexpr int SMEM_TAIL = T::OUT == OUT_PROJ ? 3072 : 1024;   // barriers, tmem slot, bias (+ projection weights)
+    static constexpr int SMEM_TAIL = 1024;                     // barriers, tmem slot, bias
     static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + SMEM_TAIL;
 };
 
@@ -355,7 +348,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     uint64_t* w_full = acc_empty + C::NACC;   // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 2);   // [NPH]
-    float* sw4 = sbias + 64;                                  // ct3 only: [32 c][12] (9 taps + pad), 16-byte rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_PROD = C::EPI_WARPS, W_MMA = C::EPI_WARPS + 1, W_ALLOC = C::EPI_WARPS + 2, W_WGT = C::EPI_WARPS + 3;
@@ -368,7 +360,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     }
     if (warp == W_ALLOC) tmem_alloc(tmem_slot, C::TMEM_COLS);
     if (threadIdx.x < C::NPH) sbias[threadIdx.x] = p.bias[threadIdx.x];
-    (void)sw4;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -659,7 +650,6 @@ struct DenseCfg {
     static constexpr int B_BYTES = 2 * 8 * NT * 16;         // hi+lo, 8 kc, NT columns
     static constexpr int STAGE = A_BYTES + B_BYTES;
     static constexpr int SMEM = NS * STAGE + 1024;
-    static constexpr int THREADS = 128 + 256;               // 8 epilogue warps
 };
 
 template <int NT, int EPI>
