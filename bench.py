@@ -115,6 +115,8 @@ def main():
                          "30 expansions x N=50 samples x simulation depth 10, reported as decisions/s (extra line, N=1 only)")
     ap.add_argument("--leaves", type=int, default=1, help="--workload mcts: leaves expanded per batch (1 = the "
                     "reference's sequential search; >1 = batched-leaf planner, SURVEY.md §8 f2)")
+    ap.add_argument("--device-tree", action="store_true", help="--workload mcts: search tree resident on the GPU "
+                    "(dai_mcts_plan), one host wait per decision")
     ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu legs (never a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -165,7 +167,9 @@ def main():
         for i in range(max(1, args.warmup) + args.steps):
             torch.cuda.synchronize()
             t = time.perf_counter()
-            if args.leaves > 1:
+            if args.device_tree:
+                planner.active_inference_mcts_device(model, frame, prm, o_shape=(1, 64, 64), leaves=args.leaves)
+            elif args.leaves > 1:
                 planner.active_inference_mcts_batched(model, frame, prm, o_shape=(1, 64, 64), leaves=args.leaves)
             else:
                 planner.active_inference_mcts(model, frame, prm, o_shape=(1, 64, 64))
@@ -178,7 +182,7 @@ def main():
                           "higher_is_better": True, "data": "synthetic", "dtype": args.precision,
                           "expansions_per_s": 31.0 / dt,
                           "config": {"workload": "full MCTS, 30 expansions x N=%d samples, simulation depth %d "
-                                                 "(BASELINE.json configs[3])" % (N, T), "leaves_per_batch": args.leaves,
+                                                 "(BASELINE.json configs[3])" % (N, T), "leaves_per_batch": args.leaves, "tree": "device" if args.device_tree else "host",
                                      "timing": "host wall clock, "
                                      "2 host syncs per expansion are inherent in the planner (src/mcts.py:82,188)"},
                           "gpu_launches": int(eng.stats()["kernel_launches"])}))

@@ -83,6 +83,10 @@ struct dai_handle {
     DevBuf sprites, sprite_stage, frame_flag;
     long long sprite_count = 0;
     long long place[6] = {0, 0, 0, 0, 0, 0}, sizes[6] = {0, 0, 0, 0, 0, 0};
+    // device-resident planner
+    DevBuf plan_tree, plan_picks, plan_rows, plan_out, plan_pi0;
+    int32_t* plan_stop_host = nullptr;   // mapped pinned flag: the search's threshold test fired
+    int32_t* plan_stop_dev = nullptr;
     float* pinned = nullptr;   // small host result buffer
     size_t pinned_cap = 0;
 };
@@ -601,11 +605,12 @@ int dai_destroy(dai_handle* h) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
-                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag};
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag, &h->plan_tree, &h->plan_picks, &h->plan_rows, &h->plan_out, &h->plan_pi0};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (void* p : h->wallocs) cudaFree(p);
     tc_release(&h->tcw);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->plan_stop_host) cudaFreeHost(h->plan_stop_host);
     delete h;
     return DAI_OK;
 }
@@ -674,7 +679,7 @@ int dai_get_stats(dai_handle* h, dai_stats* out, int reset) {
     size_t total = 0;
     DevBuf* bufs[] = {&h->mlpA, &h->mlpB, &h->ps, &h->zB, &h->h3, &h->mask, &h->act0, &h->act1, &h->act2, &h->act3, &h->img, &h->hsum,
                       &h->reward, &h->qc1, &h->qc2, &h->qc3, &h->qc4, &h->qs_out, &h->acc, &h->carry, &h->pi_eye,
-                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag};
+                      &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag, &h->plan_tree, &h->plan_picks, &h->plan_rows, &h->plan_out, &h->plan_pi0};
     for (DevBuf* b : bufs) total += b->cap;
     out->workspace_bytes = total;
     if (reset) { h->launches = 0; h->calls = 0; }
@@ -850,21 +855,12 @@ int dai_rollout_host(dai_handle* h, const float* o_host, const float* pi_host, i
     return DAI_OK;
 }
 
-int dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int depth, int use_means, float* G_host,
-                            float* pi0, float* qpi, void* stream) {
-    RET(check_ready(h));
-    if (!starting_s || !G_host || !pi0 || !qpi || K <= 0 || K > 4096 || depth <= 0 || depth > 256)
-        return fail(h, DAI_E_INVALID, "mcts_simulate: bad arguments (1 <= K <= 4096, 1 <= depth <= 256)");
-    cudaStream_t st = (cudaStream_t)stream;
+// K rollouts + one trajectory evaluation, enqueued only: the K per-trajectory means are left in h->scratch (device)
+static int simulate_batch_enqueue(dai_handle* h, cudaStream_t st, const float* starting_s, int K, int depth, int use_means,
+                                  float* pi0, float* qpi) {
     const size_t slab = (size_t)K * depth * S_DIM;
     RET(reserve(h, h->traj, 4 * slab * sizeof(float)));
     RET(reserve(h, h->scratch, (size_t)std::max(K, 16) * sizeof(float)));
-    if ((size_t)K * sizeof(float) > h->pinned_cap) {
-        float* np = nullptr;
-        CK(cudaMallocHost(&np, (size_t)K * sizeof(float)));
-        cudaFreeHost(h->pinned);
-        h->pinned = np; h->pinned_cap = (size_t)K * sizeof(float);
-    }
     float* s0 = ptr<float>(h->traj);
     SimArgs sa{};
     sa.start = starting_s; sa.K = K; sa.depth = depth; sa.use_means = use_means;
@@ -873,9 +869,23 @@ int dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int d
     sa.nk = make_key(h, h->call++, 0);
     h->launches += launch_sim_rollout(h->w, sa, st);
     RET(post_launch(h, "simulate rollout"));
-    // calculate_G_given_trajectory over the K*depth rows (next call index), per-trajectory mean -> host
-    // (src/torchmodel.py:392)
-    RET(trajectory_impl(h, st, sa.s0, sa.ps1, sa.mean, sa.logvar, pi0, K * depth, depth, nullptr, ptr<float>(h->scratch)));
+    // calculate_G_given_trajectory over the K*depth rows (next call index), per-trajectory mean (src/torchmodel.py:392)
+    return trajectory_impl(h, st, sa.s0, sa.ps1, sa.mean, sa.logvar, pi0, K * depth, depth, nullptr, ptr<float>(h->scratch));
+}
+
+int dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int depth, int use_means, float* G_host,
+                            float* pi0, float* qpi, void* stream) {
+    RET(check_ready(h));
+    if (!starting_s || !G_host || !pi0 || !qpi || K <= 0 || K > 4096 || depth <= 0 || depth > 256)
+        return fail(h, DAI_E_INVALID, "mcts_simulate: bad arguments (1 <= K <= 4096, 1 <= depth <= 256)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((size_t)K * sizeof(float) > h->pinned_cap) {
+        float* np = nullptr;
+        CK(cudaMallocHost(&np, (size_t)K * sizeof(float)));
+        cudaFreeHost(h->pinned);
+        h->pinned = np; h->pinned_cap = (size_t)K * sizeof(float);
+    }
+    RET(simulate_batch_enqueue(h, st, starting_s, K, depth, use_means, pi0, qpi));
     CK(cudaMemcpyAsync(h->pinned, h->scratch.p, (size_t)K * sizeof(float), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int k = 0; k < K; ++k) G_host[k] = h->pinned[k];
@@ -885,6 +895,112 @@ int dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int d
 int dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth, int use_means, float* G_host, float* pi0,
                       float* qpi, void* stream) {
     return dai_mcts_simulate_batch(h, starting_s, 1, depth, use_means, G_host, pi0, qpi, stream);
+}
+
+int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, const dai_mcts_params* prm,
+                  dai_mcts_result* res, int32_t* path_host, int32_t* all_paths_host, int32_t* all_len_host,
+                  float* all_G_host, void* stream) {
+    RET(check_ready(h));
+    if ((!frame && !qs0_mean_in) || !prm || !res || !path_host)
+        return fail(h, DAI_E_INVALID, "mcts_plan: bad arguments");
+    const int K = prm->leaves, R = prm->repeats, depth = prm->simulation_depth, nrep = prm->simulation_repeats;
+    if (K < 1 || K > PLAN_MAX_K || R < 0 || R > 100000 || depth < 1 || depth > 256 || nrep < 1 || prm->samples < 1)
+        return fail(h, DAI_E_INVALID, "mcts_plan: 1 <= leaves <= %d, repeats >= 0, 1 <= simulation_depth <= 256, "
+                    "simulation_repeats >= 1, samples >= 1", PLAN_MAX_K);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->plan_stop_host) {
+        CK(cudaHostAlloc(&h->plan_stop_host, 64, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&h->plan_stop_dev, h->plan_stop_host, 0));
+    }
+    *(volatile int32_t*)h->plan_stop_host = 0;      // the previous decision ended with a stream wait: no kernel writes it now
+    // ---- carve the tree, the picks and the row buffers
+    const int cap = 1 + PI_DIM * (R + K + 2), log_cap = std::max(R, 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t oW = take((size_t)cap * PI_DIM * 4), oN = take((size_t)cap * PI_DIM * 4), oQ = take((size_t)cap * PI_DIM * 4),
+                 oC = take((size_t)cap * PI_DIM * 4), oS = take((size_t)cap * S_DIM * 4), oB = take((size_t)cap),
+                 oCtl = take(PLAN_NCTL * 4), oLa = take((size_t)log_cap * PLAN_MAX_DEPTH * 4), oLl = take((size_t)log_cap * 4),
+                 oLg = take((size_t)log_cap * 4);
+    RET(reserve(h, h->plan_tree, off));
+    uint8_t* tb = ptr<uint8_t>(h->plan_tree);
+    PlanTree t{};
+    t.W = (float*)(tb + oW); t.N = (float*)(tb + oN); t.Qpi = (float*)(tb + oQ); t.child = (int32_t*)(tb + oC);
+    t.state = (float*)(tb + oS); t.blocked = tb + oB; t.ctl = (int32_t*)(tb + oCtl); t.host_stop = h->plan_stop_dev;
+    t.cap = cap; t.use_prior = prm->using_prior_for_exploration ? 1 : 0; t.C = prm->C;
+    t.log_actions = (int32_t*)(tb + oLa); t.log_len = (int32_t*)(tb + oLl); t.log_G = (float*)(tb + oLg); t.log_cap = log_cap;
+    off = 0;
+    const size_t pLeaf = take(K * 4), pLen = take(K * 4), pNodes = take((size_t)K * PLAN_MAX_DEPTH * 4),
+                 pActs = take((size_t)K * PLAN_MAX_DEPTH * 4), pCnt = take(4), pScr = take((size_t)K * (PLAN_MAX_DEPTH + 1) * 4);
+    RET(reserve(h, h->plan_picks, off));
+    uint8_t* pb = ptr<uint8_t>(h->plan_picks);
+    PlanPicks pk{};
+    pk.leaf = (int32_t*)(pb + pLeaf); pk.len = (int32_t*)(pb + pLen); pk.nodes = (int32_t*)(pb + pNodes);
+    pk.actions = (int32_t*)(pb + pActs); pk.count = (int32_t*)(pb + pCnt); pk.scratch = (int32_t*)(pb + pScr);
+    // rows: s_rows (4K,10), starts (K,10), G (4K), nxt (4K,10), sims (K), qpi (K,4), root mean/logvar (10 each), root qpi (4)
+    off = 0;
+    const size_t rS = take((size_t)4 * K * S_DIM * 4), rSt = take((size_t)K * S_DIM * 4), rG = take((size_t)4 * K * 4),
+                 rNx = take((size_t)4 * K * S_DIM * 4), rSim = take((size_t)K * 4), rQ = take((size_t)K * PI_DIM * 4),
+                 rM = take(S_DIM * 4), rLv = take(S_DIM * 4), rRq = take(PI_DIM * 4), rPi = take((size_t)4 * K * PI_DIM * 4);
+    RET(reserve(h, h->plan_rows, off));
+    uint8_t* rb = ptr<uint8_t>(h->plan_rows);
+    float *s_rows = (float*)(rb + rS), *starts = (float*)(rb + rSt), *Gd = (float*)(rb + rG), *nxt = (float*)(rb + rNx),
+          *sims = (float*)(rb + rSim), *qpi = (float*)(rb + rQ), *m0 = (float*)(rb + rM), *lv0 = (float*)(rb + rLv),
+          *rootq = (float*)(rb + rRq), *pi_eye = (float*)(rb + rPi);
+    RET(reserve(h, h->plan_pi0, (size_t)K * depth * PI_DIM * 4));
+    RET(reserve(h, h->plan_out, (size_t)(1 + PLAN_MAX_DEPTH) * 4));
+    k_fill_eye<<<(4 * K * 4 + 255) / 256, 256, 0, st>>>(pi_eye, 4 * K);
+    ++h->launches;
+
+    // ---- root: qs0 = encoder mean (src/mcts.py:158), habit prior (:164), first expansion (:172)
+    const float* root_mean = qs0_mean_in;
+    if (!root_mean) {
+        RET(dai_encode(h, frame, 1, m0, lv0, nullptr, stream));
+        root_mean = m0;
+    }
+    RET(dai_habit(h, root_mean, 1, nullptr, rootq, nullptr, stream));
+    h->launches += launch_plan_init(t, root_mean, rootq, st);
+    auto expand = [&](int kv) -> int {          // kv <= 0: the root itself
+        const int rows = PI_DIM * std::max(kv, 1);
+        h->launches += launch_plan_select(t, kv, prm->threshold, pk, s_rows, starts, st);
+        if (prm->use_means) RET(dai_calculate_G_mean(h, s_rows, pi_eye, rows, Gd, nullptr, nullptr, nullptr, nxt, nullptr, stream));
+        else RET(dai_calculate_G(h, s_rows, pi_eye, rows, prm->samples, 0, prm->samples, nullptr, Gd, nullptr, nullptr, nullptr,
+                                 nxt, nullptr, nullptr, nullptr, stream));
+        h->launches += launch_plan_expand(t, pk, Gd, nxt, st);
+        return post_launch(h, "planner expansion");
+    };
+    RET(expand(0));
+    int done = 0, leaves_now = PI_DIM;
+    while (done < R) {
+        if (*(volatile int32_t*)h->plan_stop_host) break;       // the device's threshold test fired (src/mcts.py:176)
+        const int kv = std::min(std::min(K, leaves_now), R - done);
+        RET(expand(kv));
+        for (int r = 0; r < nrep; ++r) {
+            RET(simulate_batch_enqueue(h, st, starts, kv, depth, 0, ptr<float>(h->plan_pi0), qpi));
+            h->launches += launch_plan_accumulate(ptr<float>(h->scratch), sims, kv, r == 0, st);
+        }
+        h->launches += launch_plan_backprop(t, pk, sims, nrep, qpi, st);
+        RET(post_launch(h, "planner back-propagation"));
+        done += kv; leaves_now += 3 * kv;
+    }
+    // ---- result: one wait per decision
+    h->launches += launch_plan_finish(t, ptr<int32_t>(h->plan_out), st);
+    RET(post_launch(h, "planner finish"));
+    int32_t out[1 + PLAN_MAX_DEPTH], ctl[PLAN_NCTL];
+    CK(cudaMemcpyAsync(out, h->plan_out.p, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctl, t.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ctl[PLAN_ERR]) return fail(h, DAI_E_UNSUPPORTED, "mcts_plan: %s", ctl[PLAN_ERR] == 1 ? "search path deeper than 64 edges" : "tree capacity exceeded");
+    res->path_len = out[0]; res->repeats_done = ctl[PLAN_DONE]; res->stopped = ctl[PLAN_STOP]; res->logged = ctl[PLAN_LOGGED];
+    if (out[0] > PLAN_MAX_DEPTH) return fail(h, DAI_E_UNSUPPORTED, "mcts_plan: decision path deeper than 64 edges");
+    for (int i = 0; i < out[0]; ++i) path_host[i] = out[1 + i];
+    const int nlog = std::min(ctl[PLAN_LOGGED], log_cap);
+    if (nlog > 0 && all_paths_host && all_len_host && all_G_host) {
+        CK(cudaMemcpyAsync(all_paths_host, t.log_actions, (size_t)nlog * PLAN_MAX_DEPTH * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(all_len_host, t.log_len, (size_t)nlog * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(all_G_host, t.log_G, (size_t)nlog * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return DAI_OK;
 }
 
 int dai_select_actions(dai_handle* h, const float* G, int R, float temperature, float* Ppi, float* logPpi,

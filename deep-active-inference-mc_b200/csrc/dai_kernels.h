@@ -145,6 +145,37 @@ struct SimArgs {
 };
 int  launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st);
 
+// ---- device-resident search tree (dai_planner.cu; src/mcts.py:11-128) -----------------------
+constexpr int PLAN_MAX_K = 32;        // leaves per batch
+constexpr int PLAN_MAX_DEPTH = 64;    // edges on one root-to-leaf path
+enum { PLAN_SIZE = 0, PLAN_DONE = 1, PLAN_STOP = 2, PLAN_ERR = 3, PLAN_LOGGED = 4, PLAN_NCTL = 8 };
+struct PlanTree {
+    float *W, *N, *Qpi;       // [cap][4]
+    int32_t* child;           // [cap][4], -1 = none
+    float* state;             // [cap][10]
+    uint8_t* blocked;         // [cap] scratch of one selection round
+    int32_t* ctl;             // [PLAN_NCTL]: nodes, expansions done, stop (threshold reached), error, paths logged
+    int32_t* host_stop;       // mapped pinned flag the host polls between iterations
+    int32_t cap, use_prior;
+    float C;
+    // log of every expansion's path (all_paths / all_paths_G of the reference's return tuple)
+    int32_t* log_actions;     // [log_cap][PLAN_MAX_DEPTH]
+    int32_t* log_len;         // [log_cap]
+    float* log_G;             // [log_cap]
+    int32_t log_cap;
+};
+struct PlanPicks {
+    int32_t *leaf, *len, *nodes, *actions;   // [K], [K], [K][PLAN_MAX_DEPTH] x2 (edge d of pick j: (nodes, actions)[j][d])
+    int32_t* count;                          // [1]
+    int32_t* scratch;                        // [K * (PLAN_MAX_DEPTH + 1)]
+};
+int  launch_plan_init(const PlanTree& t, const float* qs0_mean, const float* qpi, cudaStream_t st);
+int  launch_plan_select(const PlanTree& t, int k, float threshold, const PlanPicks& p, float* s_rows, float* starts, cudaStream_t st);
+int  launch_plan_expand(const PlanTree& t, const PlanPicks& p, const float* G, const float* nxt, cudaStream_t st);
+int  launch_plan_accumulate(const float* g, float* sims, int n, int first, cudaStream_t st);
+int  launch_plan_backprop(const PlanTree& t, const PlanPicks& p, const float* sims, int nrep, const float* qpi, cudaStream_t st);
+int  launch_plan_finish(const PlanTree& t, int* out, cudaStream_t st);
+
 // ---- frame producer (dai_frames.cu; src/game_environment.py:39-66) --------------------------
 struct FrameArgs {
     const float* s;        // [G][s_stride] latent classes as floats (Game.current_s), first 6 used

@@ -28,6 +28,17 @@ class DaiConfig(ctypes.Structure):
                 ("colour_channels", ctypes.c_int32), ("precision", ctypes.c_int32), ("training", ctypes.c_int32)]
 
 
+class DaiMctsParams(ctypes.Structure):
+    _fields_ = [("C", ctypes.c_float), ("threshold", ctypes.c_float), ("repeats", ctypes.c_int32),
+                ("simulation_repeats", ctypes.c_int32), ("simulation_depth", ctypes.c_int32), ("use_means", ctypes.c_int32),
+                ("using_prior_for_exploration", ctypes.c_int32), ("samples", ctypes.c_int32), ("leaves", ctypes.c_int32)]
+
+
+class DaiMctsResult(ctypes.Structure):
+    _fields_ = [("path_len", ctypes.c_int32), ("repeats_done", ctypes.c_int32), ("stopped", ctypes.c_int32),
+                ("logged", ctypes.c_int32)]
+
+
 class DaiStats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64)]
 
@@ -66,6 +77,9 @@ SIGNATURES = {
     "dai_frames_set_sprites": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), _vp]),
     "dai_frames_render": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp,
                                          ctypes.POINTER(ctypes.c_int32), _vp]),
+    "dai_mcts_plan": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(DaiMctsParams), ctypes.POINTER(DaiMctsResult),
+                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float), _vp]),
     "dai_select_actions": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]),
     "dai_profile_begin": (ctypes.c_int, [_vp]),
     "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
@@ -345,3 +359,21 @@ class Engine:
         if check and bad.value:
             raise ValueError("Error: %d game(s) with a sprite index outside the table or a reward outside [-1, 1]" % bad.value)
         return o
+
+    def mcts_plan(self, frame, params, leaves, qs0_mean=None):
+        """One planning decision with the tree on the device (include/dai_b200.h dai_mcts_plan).  Returns
+        (raw_path, repeats_done, stopped, all_paths, all_paths_G)."""
+        f = None if frame is None else self.dev(frame).reshape(4096)
+        q = None if qs0_mean is None else self.dev(qs0_mean).reshape(10)
+        prm = DaiMctsParams(float(params.C), float(params.threshold), int(params.repeats), int(params.simulation_repeats),
+                            int(params.simulation_depth), 1 if params.use_means else 0,
+                            1 if params.using_prior_for_exploration else 0, int(getattr(params, "samples", 1)), int(leaves))
+        res = DaiMctsResult()
+        n = max(int(params.repeats), 1)
+        path = (ctypes.c_int32 * 64)()
+        all_paths, all_len, all_G = (ctypes.c_int32 * (n * 64))(), (ctypes.c_int32 * n)(), (ctypes.c_float * n)()
+        self._ck(self.lib.dai_mcts_plan(self.h, _p(f), _p(q), ctypes.byref(prm), ctypes.byref(res), path, all_paths, all_len,
+                                        all_G, self._stream()))
+        paths = [[int(all_paths[i * 64 + d]) for d in range(all_len[i])] for i in range(res.logged)]
+        return ([int(path[i]) for i in range(res.path_len)], int(res.repeats_done), bool(res.stopped), paths,
+                [float(all_G[i]) for i in range(res.logged)])

@@ -168,20 +168,25 @@ class Tree:
             cur = int(self.child[cur, a])
             if self.is_leaf(cur):
                 break
-        if self.pi_dim == 4:
-            opposite = {(0, 1), (1, 0), (2, 3), (3, 2)}
-        elif self.pi_dim == 3:
-            opposite = {(1, 2), (2, 1)}
+        return trim_path(path, self.pi_dim)
+
+
+def trim_path(path, pi_dim):
+    """src/mcts.py:108-126: drop pairs of opposite actions (and, as there, the last action of the path)."""
+    if pi_dim == 4:
+        opposite = {(0, 1), (1, 0), (2, 3), (3, 2)}
+    elif pi_dim == 3:
+        opposite = {(1, 2), (2, 1)}
+    else:
+        raise ValueError(f'Error: Unknown number of pi_dim {pi_dim}')
+    out, i = [], 0
+    while i < len(path) - 1:
+        if (path[i], path[i + 1]) in opposite:
+            i += 2
         else:
-            raise ValueError(f'Error: Unknown number of pi_dim {self.pi_dim}')
-        out, i = [], 0
-        while i < len(path) - 1:
-            if (path[i], path[i + 1]) in opposite:
-                i += 2
-            else:
-                out.append(path[i])
-                i += 1
-        return out
+            out.append(path[i])
+            i += 1
+    return out
 
 
 def active_inference_mcts(model, frame, params, o_shape=(64, 64, 1)):
@@ -257,3 +262,24 @@ def active_inference_mcts_batched(model, frame, params, o_shape=(64, 64, 1), lea
             all_paths_G.append(g.item())
         done += len(picks)
     return tree.most_visited_path(root), done, states_explored, all_paths, all_paths_G
+
+
+def active_inference_mcts_device(model, frame, params, o_shape=(64, 64, 1), leaves=8):
+    """active_inference_mcts_batched with the search tree resident on the GPU (dai_mcts_plan): selection, expansion
+    bookkeeping, back-propagation and the final path are kernels between the EFE evaluations and the host waits once
+    per decision.  Same return tuple and — same model calls under the same noise keys — the same decisions as
+    active_inference_mcts_batched(model, ..., leaves) (tests/test_planner.py); `model` must be the CUDA model."""
+    if frame is None or (hasattr(frame, "__len__") and len(frame) == 0):
+        return [0], 0, 0, [], []
+    frame = torch.as_tensor(frame)
+    qs0_mean = None
+    if params.use_habit:                                  # src/mcts.py:166-170: needs the prior on the host first
+        qs0_mean, _ = model.model_down.encoder(frame.reshape(1, *o_shape))
+        qpi = model.model_top.encode_s(qs0_mean)[1][0].detach().to("cpu")
+        if calc_threshold(qpi, axis=0) > params.threshold:
+            return [torch.multinomial(qpi, 1).item()], 0, 0, [], []
+    model._sync()
+    raw, done, _, all_paths, all_G = model._engine.mcts_plan(None if qs0_mean is not None else frame, params, leaves,
+                                                             qs0_mean=None if qs0_mean is None else qs0_mean[0])
+    explored = done * params.simulation_depth * params.simulation_repeats
+    return trim_path(raw, model.pi_dim), done, explored, all_paths, all_G

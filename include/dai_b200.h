@@ -165,6 +165,37 @@ DAI_API int  dai_mcts_simulate(dai_handle* h, const float* starting_s, int depth
 DAI_API int  dai_mcts_simulate_batch(dai_handle* h, const float* starting_s, int K, int depth, int use_means,
                                      float* G_host, float* pi0, float* qpi, void* stream);
 
+/* One whole planning decision — active_inference_mcts (src/mcts.py:150-195) with `leaves` leaves per iteration — with
+ * the search tree resident on the device: selection (the reference's argmax descent, src/mcts.py:39-62, made `leaves`
+ * times with virtual visits so the leaves are distinct), expansion bookkeeping (:64-86), back-propagation (:88-96) and
+ * the most-visited path (:98-106) are kernels between the EFE evaluations; the host enqueues the iterations and waits
+ * ONCE, at the end (plus a poll of a mapped flag for the visit-count threshold of :176).  leaves = 1 is the
+ * reference's search.  frame (4096) device, or qs0_mean (10) device if the caller already encoded it (then no encoder
+ * call is made).  Results (host): path = the most-visited path before the opposite-action trimming of :108-126
+ * (path_host holds 64 entries), all_paths (repeats x 64) / all_len / all_G = every expansion's action path and
+ * simulated G (may be NULL).  Call indices: 1 (encoder, if frame) + 1 (root expansion) + per iteration 1 +
+ * 2 * simulation_repeats — the same as the host-driven planner, so both make the same decisions. */
+typedef struct dai_mcts_params {
+    float   C;                             /* MCTS_Params.C (src/mcts.py:139)            */
+    float   threshold;                     /* .threshold                                 */
+    int32_t repeats;                       /* .repeats: expansions per decision          */
+    int32_t simulation_repeats;            /* .simulation_repeats                        */
+    int32_t simulation_depth;              /* .simulation_depth                          */
+    int32_t use_means;                     /* .use_means: calculate_G_mean expansions    */
+    int32_t using_prior_for_exploration;   /* .using_prior_for_exploration               */
+    int32_t samples;                       /* MC samples per expansion (Node.expand)     */
+    int32_t leaves;                        /* leaves per batch, 1..32                    */
+} dai_mcts_params;
+typedef struct dai_mcts_result {
+    int32_t path_len;                      /* entries in path_host                       */
+    int32_t repeats_done;                  /* expansions made before the search ended    */
+    int32_t stopped;                       /* 1: the visit-count threshold ended it      */
+    int32_t logged;                        /* entries in all_paths / all_len / all_G     */
+} dai_mcts_result;
+DAI_API int  dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean, const dai_mcts_params* prm,
+                           dai_mcts_result* res, int32_t* path_host, int32_t* all_paths_host, int32_t* all_len_host,
+                           float* all_G_host, void* stream);
+
 /* ---- next row: batched many-roots action selection -------------------------
  * The action choice of make_batch_dsprites_active_inference (src/util.py:46-53,66-68) for R roots whose summed EFE
  * G (4R, row = root*4 + action) is already on the device: per root x = -G - max(-G), e = exp(x / temperature),

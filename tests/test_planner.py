@@ -169,3 +169,31 @@ def test_cuda_model_plans_like_the_oracle_with_batched_leaves(use_means):
     po = my_mcts.active_inference_mcts_batched(ora, _frame(), p, o_shape=(1, 64, 64), leaves=4)
     assert pg[0] == po[0] and pg[1] == po[1] and pg[3] == po[3]
     assert np.allclose(pg[4], po[4], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_means,threshold,leaves,repeats", [(True, 2.0, 4, 9), (False, 2.0, 8, 20), (True, 0.5, 2, 40),
+                                                                 (False, 2.0, 1, 5)])
+def test_device_resident_planner_makes_the_host_planners_decisions(use_means, threshold, leaves, repeats):
+    """dai_mcts_plan (tree on the device, one host wait per decision) against the host-driven batched planner on the
+    same CUDA model and noise: same path, same expansions, same simulated G."""
+    from dai_b200 import mcts as my_mcts
+    from dai_b200.torchmodel import ActiveInferenceModel
+    gpu = ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, device="cuda:0").load_numpy_weights(cases.weights_for("w0"))
+    p = _params(my_mcts, repeats, use_means, threshold, depth=3, samples=2)
+    gpu.set_rng(77, 0)
+    host = my_mcts.active_inference_mcts_batched(gpu, _frame(), p, o_shape=(1, 64, 64), leaves=leaves)
+    calls_host = gpu._engine.get_rng()[1]
+    gpu.set_rng(77, 0)
+    dev = my_mcts.active_inference_mcts_device(gpu, _frame(), p, o_shape=(1, 64, 64), leaves=leaves)
+    assert dev[0] == host[0] and dev[1] == host[1] and dev[2] == host[2]
+    assert dev[3] == _ints(host[3])
+    assert np.allclose(dev[4], host[4], rtol=0, atol=1e-6)
+    assert gpu._engine.get_rng()[1] >= calls_host          # a stop by threshold may have enqueued one batch too many
+    if threshold > 1.0:
+        assert gpu._engine.get_rng()[1] == calls_host and dev[1] == repeats
+    # leaves = 1 is the reference's sequential search
+    if leaves == 1:
+        gpu.set_rng(77, 0)
+        seq = my_mcts.active_inference_mcts(gpu, _frame(), p, o_shape=(1, 64, 64))
+        assert dev[0] == seq[0] and dev[3] == _ints(seq[3])
