@@ -641,6 +641,31 @@ struct DenseParams {
     int32_t layer;               // dropout site = nr.site[set] + layer
 };
 
+// FC4 epilogue for 32 accumulator columns of one row: bias + ReLU + MC-dropout bit + hi/lo split + stores.
+// FC4 column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel 8*kc + e.  A
+// 256-column tile is one group of 4 pixels x 64 channels and 32 consecutive columns are 4 pixels x 8 channels of one
+// kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores per plane.
+__device__ __forceinline__ void fc4_store32(const DenseParams& p, const uint32_t (&r)[32], int row, int nt, int n0) {
+    const size_t plane = (size_t)p.nrows * 16384;
+    const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
+    const float s2 = p.mask ? 2.0f : 1.0f;
+    const int kc = (n0 >> 5) & 7;
+    uint32_t hi[4][4], lo[4][4];
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j0 = pl * 8 + 2 * e, j1 = j0 + 1;
+            split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
+                   ((mw >> j0) & 1u) ? s2 : 0.0f, ((mw >> j1) & 1u) ? s2 : 0.0f, hi[pl][e], lo[pl][e]);
+        }
+    const size_t o = (((size_t)row * 8 + kc) * 256 + nt * 4) * 8;
+    st_global_256(p.out + o, hi[0], hi[1]);
+    st_global_256(p.out + o + 16, hi[2], hi[3]);
+    st_global_256(p.out + plane + o, lo[0], lo[1]);
+    st_global_256(p.out + plane + o + 16, lo[2], lo[3]);
+}
+
 enum { EPI_FC4 = 0, EPI_HIDDEN = 1, EPI_CONV4 = 2 };
 
 template <int NT, int EPI>
@@ -762,27 +787,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                 if (row >= p.nrows) continue;
                 const int n0 = nt * NT + half * (NT / 2) + c0;
                 if (EPI == EPI_FC4) {
-                    // FC4 column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel
-                    // 8*kc + e.  A 256-column tile is one group of 4 pixels x 64 channels and the 32 columns loaded here
-                    // are 4 pixels x 8 channels of one kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores.
-                    const size_t plane = (size_t)p.nrows * 16384;
-                    const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
-                    const float s2 = p.mask ? 2.0f : 1.0f;
-                    const int kc = (n0 >> 5) & 7;
-                    uint32_t hi[4][4], lo[4][4];
-#pragma unroll
-                    for (int pl = 0; pl < 4; ++pl)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j0 = pl * 8 + 2 * e, j1 = j0 + 1;
-                            split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
-                                   ((mw >> j0) & 1u) ? s2 : 0.0f, ((mw >> j1) & 1u) ? s2 : 0.0f, hi[pl][e], lo[pl][e]);
-                        }
-                    const size_t o = (((size_t)row * 8 + kc) * 256 + nt * 4) * 8;
-                    st_global_256(p.out + o, hi[0], hi[1]);
-                    st_global_256(p.out + o + 16, hi[2], hi[3]);
-                    st_global_256(p.out + plane + o, lo[0], lo[1]);
-                    st_global_256(p.out + plane + o + 16, lo[2], lo[3]);
+                    fc4_store32(p, r, row, nt, n0);
                 } else {
                     const int wsel = (half * (NT / 2) + c0) >> 5;       // which 32-bit word of the Philox block
                     const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
@@ -1292,6 +1297,9 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = ((nrows + 127) / 128) * 64;
+    // (an A-resident variant — m-tile's A kept in shared memory, B streamed in K = 32 stages through a 3-slot ring — was
+    // measured 11 % SLOWER, 3.46 vs 3.11 ms per rollout: with 96 KB instead of 192 KB of loads in flight the kernel is
+    // bound by load latency x bytes in flight, not by the L2 traffic that variant saves)
     k_tc_dense<256, EPI_FC4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, EPI_FC4>::SMEM, st>>>(p);
     return 1;
 }
