@@ -215,3 +215,81 @@ def test_config5_eight_sample_shards_add_up():
     G, t0, t1, t2 = eng.combine(sums, 800)
     assert torch.allclose(G, full["G"], rtol=1e-6, atol=1e-5)
     assert torch.isfinite(G).all() and float(G.min()) > 0
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+
+def test_ragged_batches_and_single_sample_match_the_oracle():
+    """B not a multiple of 4 (explicit pi), one sample, one step; and eval mode on the tensor-core path."""
+    from oracle import efe_oracle as O
+    m = _model("w0", "bf16x3")
+    rng = np.random.default_rng(5)
+    import dai_b200.synthetic as syn
+    o = torch.from_numpy(syn.make_frames(5, 31))
+    pi = torch.eye(4)[torch.tensor([0, 3, 1, 2, 2])]
+    ora = O.OracleModel(cases.weights_for("w0"), seed=8)
+    m.set_rng(8, 0)
+    G, terms, po1 = m.calculate_G_repeated(o, pi, steps=1, samples=1)
+    with torch.no_grad():
+        Go, to, poo = ora.calculate_G_repeated(o, pi, steps=1, samples=1)
+    got = dict(G=G, t0=terms[0], t1=terms[1], t2=terms[2], po1=po1)
+    ref = dict(G=Go, t0=to[0], t1=to[1], t2=to[2], po1=poo)
+    assert cases.compare("ragged", {k: v.detach().cpu().numpy() for k, v in got.items()},
+                         {k: v.detach().cpu().numpy() for k, v in ref.items()}) == []
+    # eval mode: dropout is identity in all three nets, the normals are still drawn
+    s0 = torch.from_numpy(rng.standard_normal((7, 10)).astype(np.float32))
+    pi7 = torch.eye(4)[torch.tensor([0, 1, 2, 3, 0, 1, 2])]
+    try:
+        for net in (m.model_down, m.model_mid, m.model_top):
+            net.eval()
+        ora_eval = O.OracleModel(cases.weights_for("w0"), seed=8, training=False)
+        m.set_rng(8, 3); ora_eval.set_rng(8, 3)
+        Gg, tg, ps1, mu, po = m.calculate_G(s0, pi7, samples=3)
+        with torch.no_grad():
+            Go, to, ps1o, muo, poo = ora_eval.calculate_G(s0, pi7, samples=3)
+        got = dict(G=Gg, t0=tg[0], t1=tg[1], t2=tg[2], ps1=ps1, mean=mu, po1=po)
+        ref = dict(G=Go, t0=to[0], t1=to[1], t2=to[2], ps1=ps1o, mean=muo, po1=poo)
+        assert cases.compare("eval", {k: v.detach().cpu().numpy() for k, v in got.items()},
+                             {k: v.detach().cpu().numpy() for k, v in ref.items()}) == []
+    finally:
+        for net in (m.model_down, m.model_mid, m.model_top):
+            net.train()
+
+
+def test_new_entry_points_reject_bad_arguments():
+    import ctypes
+    from dai_b200 import engine
+    m = _model("w0", "bf16x3")
+    m._sync()
+    eng, lib = m._engine, m._engine.lib
+    st = eng._stream()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    s = torch.zeros(4, 10, device="cuda")
+    g = (ctypes.c_float * 4)()
+    pi0, qpi = torch.zeros(4 * 3, 4, device="cuda"), torch.zeros(4, 4, device="cuda")
+    assert lib.dai_mcts_simulate_batch(eng.h, p(s), 0, 3, 0, g, p(pi0), p(qpi), st) == -1
+    assert lib.dai_mcts_simulate_batch(eng.h, p(s), 4, 0, 0, g, p(pi0), p(qpi), st) == -1
+    assert lib.dai_mcts_simulate_batch(eng.h, None, 4, 3, 0, g, p(pi0), p(qpi), st) == -1
+    prm = engine.DaiMctsParams(1.0, 2.0, 4, 1, 2, 1, 0, 1, 33)          # leaves > 32
+    res = engine.DaiMctsResult()
+    path = (ctypes.c_int32 * 64)()
+    frame = torch.zeros(4096, device="cuda")
+    assert lib.dai_mcts_plan(eng.h, p(frame), None, ctypes.byref(prm), ctypes.byref(res), path, None, None, None, st) == -1
+    assert b"leaves" in lib.dai_last_error(eng.h)
+    prm.leaves = 4
+    assert lib.dai_mcts_plan(eng.h, None, None, ctypes.byref(prm), ctypes.byref(res), path, None, None, None, st) == -1
+    # repeats = 0: only the root expansion; the decision is the best first action
+    prm.repeats = 0
+    assert lib.dai_mcts_plan(eng.h, p(frame), None, ctypes.byref(prm), ctypes.byref(res), path, None, None, None, st) == 0
+    assert res.repeats_done == 0 and res.path_len == 1 and 0 <= path[0] < 4
+    # frame producer without a sprite table, then with inconsistent sizes
+    fresh = engine.Engine(device="cuda:0")
+    r = torch.zeros(2, device="cuda")
+    s7 = torch.zeros(2, 7, device="cuda")
+    o = torch.zeros(2, 4096, device="cuda")
+    assert lib.dai_frames_render(fresh.h, p(s7), 7, p(r), 2, 0, p(o), None, st) == -1
+    imgs = torch.zeros(6, 4096, dtype=torch.uint8)
+    sizes = (ctypes.c_int32 * 6)(1, 1, 1, 1, 2, 2)                      # multiplies to 4, table has 6
+    assert lib.dai_frames_set_sprites(fresh.h, ctypes.c_void_p(imgs.data_ptr()), 6, sizes, st) == -1
+    fresh.close()
+    assert torch.isfinite(m.model_down.decoder(torch.zeros(1, 10))).all()
