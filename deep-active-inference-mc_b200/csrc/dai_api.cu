@@ -59,7 +59,7 @@ const WeightSpec kSpecs[] = {
 constexpr int kNumSpecs = sizeof(kSpecs) / sizeof(kSpecs[0]);
 
 constexpr int kDecChunkDefault = 4800;   // decoder rows per activation chunk (896 KB of activations per row; larger chunks amortise the per-launch ramp: 1024 -> 4800 rows = +7 % rollouts/s)
-constexpr int kQsChunk = 2048;    // encoder rows per chunk (166 KB of conv features per row)
+constexpr int kQsChunk = 4096;    // encoder rows per chunk (166 KB of conv features per row); chunks are equalised
 
 }  // namespace
 
@@ -376,10 +376,14 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
     const int rows = B * Sl;
     if (rows <= 0) return DAI_OK;
     const int ch = std::min(rows, kQsChunk);
-    // chunks must hold whole slots so the (slot, b) decode stays valid: round down to a multiple of B
+    // chunks must hold whole slots so the (slot, b) decode stays valid: a multiple of B; equal chunks rather than a
+    // full one and a short one (slots per chunk = ceil(Sl / nchunks))
     int chs = ch;
     if (rows > ch) {
-        chs = (ch / B) * B;
+        const int slots_max = ch / B;
+        if (slots_max == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
+        const int nchunks = (Sl + slots_max - 1) / slots_max;
+        chs = ((Sl + nchunks - 1) / nchunks) * B;
         if (chs == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
     }
     const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
