@@ -991,9 +991,10 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
     }
     static const int env_two_pass = getenv("DAI_TC_TWO_PASS") ? atoi(getenv("DAI_TC_TWO_PASS")) : -1;
     p.two_pass = env_two_pass >= 0 ? ((env_two_pass >> C::ID) & 1) : (C::TWO_PASS ? 1 : 0);
-    if (const char* e = getenv("DAI_TC_DBG")) p.dbg = atoi(e);
+    static const int env_dbg = getenv("DAI_TC_DBG") ? atoi(getenv("DAI_TC_DBG")) : 0;      // experiments only
+    p.dbg = env_dbg;
     static long long* dbg_counters = nullptr;
-    const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;
+    static const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;                // experiments only
     if (want_counters) {
         if (!dbg_counters) cudaMalloc(&dbg_counters, 8 * 8 * 512);
         cudaMemsetAsync(dbg_counters, 0, 8 * 8 * 512, st);

@@ -197,3 +197,37 @@ def test_device_resident_planner_makes_the_host_planners_decisions(use_means, th
         gpu.set_rng(77, 0)
         seq = my_mcts.active_inference_mcts(gpu, _frame(), p, o_shape=(1, 64, 64))
         assert dev[0] == seq[0] and dev[3] == _ints(seq[3])
+
+
+def test_select_batch_on_random_trees_claims_distinct_leaves_and_leaves_no_trace():
+    """Property test of the virtual-visit selection on randomly grown trees: k distinct leaves (or all of them),
+    every path ends in its leaf, statistics untouched; the first pick is the sequential rule's pick."""
+    from dai_b200.mcts import Tree
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        t = Tree(4, 400, float(rng.uniform(0.2, 2.0)), bool(trial % 2))
+        root = t.add(torch.zeros(10))
+        leaves = [root]
+        for _ in range(int(rng.integers(1, 25))):                  # expand random leaves
+            i = leaves.pop(int(rng.integers(0, len(leaves))))
+            for a in range(4):
+                c = t.add(torch.zeros(10))
+                t.child[i, a] = c
+                leaves.append(c)
+            t.W[i] = torch.from_numpy(-rng.uniform(40, 60, 4).astype(np.float32))
+            t.N[i] = torch.from_numpy(rng.integers(1, 6, 4).astype(np.float32))
+            t.Qpi[i] = torch.softmax(torch.from_numpy(rng.normal(size=4).astype(np.float32)), 0)
+        W0, N0 = t.W.clone(), t.N.clone()
+        k = int(rng.integers(1, 12))
+        picks = t.select_batch(root, k)
+        ids = [nodes[-1] for nodes, _ in picks]
+        assert len(ids) == min(k, len(leaves)) and len(set(ids)) == len(ids)
+        assert all(t.is_leaf(i) for i in ids)
+        for nodes, actions in picks:
+            cur = root
+            for n, a in zip(nodes, actions):
+                assert int(t.child[cur, a]) == n
+                cur = n
+        assert torch.equal(t.W, W0) and torch.equal(t.N, N0)
+        seq_nodes, seq_actions = t.select(root)
+        assert picks[0][1] == seq_actions and picks[0][0] == seq_nodes
