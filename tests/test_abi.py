@@ -68,3 +68,25 @@ def test_shard_ranges_partition_the_samples():
                 b, e = shard_range(n, r, w)
                 cover += list(range(b, e))
             assert cover == list(range(n))
+
+
+def test_ctypes_signatures_have_the_arity_the_header_declares():
+    """Every binding in engine.SIGNATURES passes as many arguments as the C prototype takes (ABI drift shows up here,
+    on the CPU, rather than as a crash on the GPU box)."""
+    engine = _library()
+    text = open(os.path.join(ROOT, "include", "dai_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"DAI_API\s+(?:const\s+char\*|int)\s+(dai_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(engine.SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        assert n == len(engine.SIGNATURES[name][1]), (name, n, len(engine.SIGNATURES[name][1]))
+    # the two parameter structs mirror the header field for field
+    fields = re.search(r"typedef struct dai_mcts_params \{(.*?)\} dai_mcts_params;", text, flags=re.S).group(1)
+    names = re.findall(r"(?:float|int32_t)\s+(\w+)\s*;", fields)
+    assert names == [f[0] for f in engine.DaiMctsParams._fields_]
+    fields = re.search(r"typedef struct dai_mcts_result \{(.*?)\} dai_mcts_result;", text, flags=re.S).group(1)
+    assert re.findall(r"int32_t\s+(\w+)\s*;", fields) == [f[0] for f in engine.DaiMctsResult._fields_]
+    fields = re.search(r"typedef struct dai_config \{(.*?)\} dai_config;", text, flags=re.S).group(1)
+    assert re.findall(r"int32_t\s+(\w+)\s*;", fields) == [f[0] for f in engine.DaiConfig._fields_]
