@@ -313,6 +313,12 @@ def main():
                      "avg_launch_ms": ms3 / n3, "launches_timed": int(n3), "rows_per_launch": rows3 / n3,
                      "traffic": traffic,
                      "step_share_ms": {k: v[0] / min(args.steps, 3) for k, v in layers.items()}})
+        # the other contraction kernels of the decoder, same accounting (algorithmic MAC per decoder row)
+        macs = {"fc4": 4_194_304, "ct1": 9_437_184, "ct2": 9_437_184, "ct3": MAC_CT3}
+        nprod = 3 if args.precision == "bf16x3" else 1
+        roof["kernels"] = {k: {"alg_tflops": 2.0 * m * layers[k][2] / (layers[k][0] * 1e-3) / 1e12,
+                               "issued_frac": nprod * 2.0 * m * layers[k][2] / (layers[k][0] * 1e-3) / 1e12 / peak_tf}
+                           for k, m in macs.items() if k in layers and layers[k][0] > 0}
     line["roofline"] = roof
     if not args.no_cpu_baseline and not args.quick and world == 1:
         ncalls = 24                                   # ~10 s of CPU work on the box's host cores (0.35 s per call)
