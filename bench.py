@@ -70,29 +70,76 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(samples, horizon, steps, warmup):
-    """The reference's CPU path (oracle port over the same ATen kernels, torch's own RNG draws as in the
-    reference — SURVEY.md §6) timed on this box's host cores.  One step = one bounded sample:
-    calculate_G_4_repeated(o, steps=1, samples=N) for one root; CPU cost is linear in N*T
-    (BASELINE.md §2), so rollouts/s at horizon T = 1 / (T * seconds per 1-step call)."""
+def cpu_reference_run(samples, horizon, steps, warmup, extra_as_shipped=1):
+    """The reference's own CPU path timed on this box's host cores, at the stated config: every timed step is ONE
+    full `calculate_G_4_repeated(o, steps=T, samples=N)` call for one root observation (test_demo.py:150) — a
+    bounded sample (1 root) of the GPU arm's R-root step; roots are independent, so rollouts/s = 1 / seconds per call.
+    Runs the UNMODIFIED reference (staged under baseline/_ref, or /root/reference where mounted; SHIM-1/2 of
+    SURVEY.md §0.1 on the instance) with torch's own RNG; falls back to the oracle port over the same ATen kernels
+    and draw pattern when the reference is absent.  `value` is measured under torch.no_grad() (the faster, i.e.
+    conservative, figure); `extra_as_shipped` more calls are timed with autograd on, as the reference ships."""
     os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")
     import torch
     from dai_b200 import synthetic
     from oracle import efe_oracle as O
+    from oracle import reference_model as RM
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    W = O.to_torch(synthetic.make_weights(0))
+    w = synthetic.make_weights(0)
     o = torch.from_numpy(synthetic.make_frames(1, 0)).repeat(4, 1, 1, 1)
+    if RM.available():
+        ref = RM.load(w)
+        kind, where = "reference", RM.location()
+
+        def call():
+            return ref.calculate_G_4_repeated(o, steps=horizon, samples=samples)
+    else:
+        W = O.to_torch(w)
+        kind, where = "port", "oracle/efe_oracle.py"
+
+        def call():
+            return O.calculate_G_repeated(W, o, None, horizon, False, samples, O.TorchStreamNoise(), four=True)
     torch.manual_seed(0)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t = time.perf_counter()
-            O.calculate_G_repeated(W, o, None, 1, False, samples, O.TorchStreamNoise(), four=True)
+            call()
             if i >= warmup:
                 times.append(time.perf_counter() - t)
+    shipped = []
+    for i in range(extra_as_shipped):
+        t = time.perf_counter()
+        call()
+        shipped.append(time.perf_counter() - t)
     per_call = sum(times) / len(times)
-    return 1.0 / (per_call * horizon), per_call, torch.get_num_threads()
+    return {"value": 1.0 / per_call, "per_call_s": per_call, "cores": torch.get_num_threads(), "kind": kind, "where": where,
+            "as_shipped_value": (len(shipped) / sum(shipped)) if shipped else None}
+
+
+def mcts_decisions(model, N, T, leaves, device_tree, n_timed, n_warm=1):
+    """configs[3]: full planner, 30 expansions x N samples x simulation depth T; seconds per decision (host wall clock:
+    the planner's host syncs are part of a decision)."""
+    import torch
+    from dai_b200 import synthetic
+    from dai_b200 import mcts as planner
+    prm = planner.MCTS_Params()
+    prm.repeats, prm.threshold, prm.use_means, prm.samples, prm.simulation_depth = 30, 2.0, False, N, T
+    frame = torch.from_numpy(synthetic.make_frames(1, 0))[0, 0]
+    times = []
+    for i in range(n_warm + n_timed):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        if device_tree:
+            planner.active_inference_mcts_device(model, frame, prm, o_shape=(1, 64, 64), leaves=leaves)
+        elif leaves > 1:
+            planner.active_inference_mcts_batched(model, frame, prm, o_shape=(1, 64, 64), leaves=leaves)
+        else:
+            planner.active_inference_mcts(model, frame, prm, o_shape=(1, 64, 64))
+        torch.cuda.synchronize()
+        if i >= n_warm:
+            times.append(time.perf_counter() - t)
+    return sum(times) / len(times)
 
 
 def main():
@@ -110,6 +157,7 @@ def main():
                          "rollout inside each pair), R*N roots in total [weak]; samples = all ranks split the "
                          "samples of the same R roots [strong]; roots = R independent roots per rank, no collective [weak]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2..4] legs (`extra` in the JSON line)")
     ap.add_argument("--workload", default="rollout", choices=["rollout", "mcts"],
                     help="rollout = BASELINE.json configs[1] (default, the bench line); mcts = configs[3]: full planner, "
                          "30 expansions x N=50 samples x simulation depth 10, reported as decisions/s (extra line, N=1 only)")
@@ -117,7 +165,7 @@ def main():
                     "reference's sequential search; >1 = batched-leaf planner, SURVEY.md §8 f2)")
     ap.add_argument("--device-tree", action="store_true", help="--workload mcts: search tree resident on the GPU "
                     "(dai_mcts_plan), one host wait per decision")
-    ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu legs (never a bench value)")
+    ap.add_argument("--quick", action="store_true", help="profiling pass: 1 warm-up, no e2e / cpu / extra legs (never a bench value)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -129,16 +177,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        k = max(1, min(args.steps, 20))
-        value, per_call, cores = cpu_reference_run(N, T, k, max(1, min(args.warmup, 2)))
-        sample = "calculate_G_4_repeated(steps=1, samples=%d), 1 root, %d timed calls, scaled by 1/T (cost is linear in N*T)" % (N, k)
+        k, w = max(1, args.steps), max(0, args.warmup)
+        r = cpu_reference_run(N, T, k, w)
+        sample = ("each step = one full calculate_G_4_repeated(o, steps=%d, samples=%d) call for 1 of the %d roots of the "
+                  "GPU arm's step (roots are independent); %d timed + %d warm-up calls under torch.no_grad(), %.2f s each; "
+                  "as shipped (autograd on): %.4f rollouts/s; code: %s" %
+                  (T, N, R, k, w, r["per_call_s"], r["as_shipped_value"] or 0.0, r["where"]))
         print(json.dumps({
-            "impl": "reference", "metric": "EFE rollouts/sec", "value": value, "unit": "rollouts/s",
-            "n_gpus": args.gpus, "steps": k, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": per_call * 1e3,
+            "impl": "reference", "metric": "EFE rollouts/sec", "value": r["value"], "unit": "rollouts/s",
+            "n_gpus": args.gpus, "steps": k, "warmup": w, "ms_per_step": r["per_call_s"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(config, roots_per_step=1, rows_per_step=4),
-            "cpu_baseline": {"value": value, "unit": "rollouts/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "rollouts/s", "cores": r["cores"], "kind": r["kind"], "sample": sample,
+                             "as_shipped_value": r["as_shipped_value"]},
+            "e2e": {"value": r["value"], "unit": "rollouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
 
@@ -158,25 +210,8 @@ def main():
     eng = model._engine
 
     if args.workload == "mcts":
-        from dai_b200 import mcts as planner
-        prm = planner.MCTS_Params()
-        prm.repeats, prm.threshold, prm.use_means, prm.samples, prm.simulation_depth = 30, 2.0, False, N, T
-        frame = torch.from_numpy(synthetic.make_frames(1, 0))[0, 0]
         eng.stats(reset=True)
-        times = []
-        for i in range(max(1, args.warmup) + args.steps):
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            if args.device_tree:
-                planner.active_inference_mcts_device(model, frame, prm, o_shape=(1, 64, 64), leaves=args.leaves)
-            elif args.leaves > 1:
-                planner.active_inference_mcts_batched(model, frame, prm, o_shape=(1, 64, 64), leaves=args.leaves)
-            else:
-                planner.active_inference_mcts(model, frame, prm, o_shape=(1, 64, 64))
-            torch.cuda.synchronize()
-            if i >= max(1, args.warmup):
-                times.append(time.perf_counter() - t)
-        dt = sum(times) / len(times)
+        dt = mcts_decisions(model, N, T, args.leaves, args.device_tree, args.steps, max(1, args.warmup))
         print(json.dumps({"metric": "MCTS decisions/sec", "value": 1.0 / dt, "unit": "decisions/s", "n_gpus": 1,
                           "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": dt * 1e3,
                           "higher_is_better": True, "data": "synthetic", "dtype": args.precision,
@@ -203,32 +238,40 @@ def main():
     else:
         my_roots, shard, scaling = R, (shard_range(N, rank, world) if world > 1 else None), ("strong" if world > 1 else "weak")
         total_roots = R
-    frames = torch.from_numpy(synthetic.make_frames(my_roots, seed=frame_seed))
-    o_host = frames.repeat_interleave(4, dim=0).reshape(4 * my_roots, 4096).contiguous().pin_memory()
-    o_dev = o_host.to(dev)
-    out_host = torch.empty(4, 4 * my_roots).pin_memory()
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)      # > 126 MB L2
 
-    def step_device():
-        out = eng.rollout(o_dev, None, T, N, calc_mean=False, four=False, shard=shard, want_po1=False)
-        if shard is not None:
-            dist.all_reduce(out["sums"], group=group)
-            eng.combine(out["sums"], N)
-        return out
+    def make_steps(roots, n, t, shard_, group_, seed):
+        """(device-resident step, end-to-end step, h2d bytes, d2h bytes) for `roots` roots x 4 actions, n samples, horizon t.
+        Both return what the reference call returns: G, the three terms and po1 of the last step."""
+        frames = torch.from_numpy(synthetic.make_frames(roots, seed=seed))
+        o_host = frames.repeat_interleave(4, dim=0).reshape(4 * roots, 4096).contiguous().pin_memory()
+        o_dev = o_host.to(dev)
+        out_host = torch.empty(4, 4 * roots).pin_memory()
+        po1_host = torch.empty(4 * roots, 4096).pin_memory()
 
-    def step_e2e():
-        if shard is None:
-            eng.rollout_host(o_host, None, T, N, False, False, out_host)
-        else:
-            o = o_host.to(dev, non_blocking=True)
-            out = eng.rollout(o, None, T, N, calc_mean=False, four=False, shard=shard, want_po1=False)
-            dist.all_reduce(out["sums"], group=group)
-            G, t0, t1, t2 = eng.combine(out["sums"], N)
-            out_host[0].copy_(G, non_blocking=True)
-            out_host[1].copy_(t0, non_blocking=True)
-            out_host[2].copy_(t1, non_blocking=True)
-            out_host[3].copy_(t2, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        def step_device():
+            out = eng.rollout(o_dev, None, t, n, calc_mean=False, four=False, shard=shard_, want_po1=True)
+            if shard_ is not None:
+                dist.all_reduce(out["sums"], group=group_)
+                eng.combine(out["sums"], n)
+            return out
+
+        def step_e2e():
+            if shard_ is None:
+                eng.rollout_host(o_host, None, t, n, False, False, out_host, po1_host)
+            else:
+                o = o_host.to(dev, non_blocking=True)
+                out = eng.rollout(o, None, t, n, calc_mean=False, four=False, shard=shard_, want_po1=True)
+                dist.all_reduce(out["sums"], group=group_)
+                G, t0, t1, t2 = eng.combine(out["sums"], n)
+                out_host[0].copy_(G, non_blocking=True)
+                out_host[1].copy_(t0, non_blocking=True)
+                out_host[2].copy_(t1, non_blocking=True)
+                out_host[3].copy_(t2, non_blocking=True)
+                po1_host.copy_(out["po1"].reshape(4 * roots, 4096), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        return step_device, step_e2e, int(o_host.numel() * 4), int((out_host.numel() + po1_host.numel()) * 4)
 
     def timed(fn, k, w):
         for _ in range(w):
@@ -252,6 +295,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / k
 
+    step_device, step_e2e, h2d, d2h = make_steps(my_roots, N, T, shard, group, frame_seed)
     sampler = ClockSampler(local)
     eng.stats(reset=True)
     if rank == 0:
@@ -271,6 +315,43 @@ def main():
         for _ in range(min(args.steps, 3)):
             step_device()
         layers = eng.profile_end()
+
+    # ---- the other BASELINE.json configs, timed in the same run (`extra`) -------------------------------------
+    extra = {}
+    if not args.quick and not args.no_extras:
+        ks = max(2, min(args.steps, 5))
+        if world == 1:
+            # configs[2]: N=200, T=10 (4 roots per step); single-root latency of configs[1] (test_demo.py:150 is R=1)
+            d3, e3, _, _ = make_steps(4, 200, 10, None, None, 1)
+            ms3 = timed(d3, ks, 2)
+            ms3e = timed(e3, ks, 1)
+            extra["c3_rollouts_s"] = {"value": 4 / (ms3 * 1e-3), "e2e": 4 / (ms3e * 1e-3), "unit": "rollouts/s", "ms_per_step": ms3,
+                                      "config": "configs[2]: N=200, T=10, R=4 roots per step",
+                                      "algorithmic_tflops": rollout_flops(200, 10) * 4 / (ms3 * 1e-3) / 1e12}
+            d1, e1, _, _ = make_steps(1, N, T, None, None, 2)
+            ms1 = timed(d1, max(ks, 5), 3)
+            ms1e = timed(e1, max(ks, 5), 1)
+            extra["r1_latency_ms"] = {"value": ms1, "e2e": ms1e, "unit": "ms per rollout", "rollouts_s": 1e3 / ms1,
+                                      "config": "configs[1] with R=1: one root (4 action rows), N=%d, T=%d" % (N, T)}
+            # configs[3]: full MCTS decision (host wall clock)
+            dseq = mcts_decisions(model, 50, 10, 1, False, 3)
+            dtree = mcts_decisions(model, 50, 10, 16, True, 5)
+            extra["c4_decisions_s"] = {"sequential": 1.0 / dseq, "device_tree_leaves16": 1.0 / dtree, "unit": "decisions/s",
+                                       "ms_sequential": dseq * 1e3, "ms_device_tree_leaves16": dtree * 1e3,
+                                       "config": "configs[3]: 30 expansions x N=50 samples x simulation depth 10; sequential = the "
+                                                 "reference's search order, one leaf per expansion (src/mcts.py:150-195); "
+                                                 "device_tree = dai_mcts_plan, 16 leaves per batch"}
+        # configs[4]: N=800 samples sharded over ALL ranks, T=15, one root, ONE all-reduce of the (4,B) f64 term sums over
+        # the world group per rollout (at N=1: the same rollout unsharded, the strong-scaling base)
+        sh5 = shard_range(800, rank, world) if world > 1 else None
+        d5, e5, _, _ = make_steps(1, 800, 15, sh5, None, 3)
+        ms5 = timed(d5, ks, 2)
+        ms5e = timed(e5, ks, 1)
+        extra["c5_sample_sharded"] = {"value": 1.0 / (ms5 * 1e-3), "e2e": 1.0 / (ms5e * 1e-3), "unit": "rollouts/s", "ms_per_step": ms5,
+                                      "n_gpus": world, "scaling": "strong", "samples_per_rank": (sh5[1] - sh5[0]) if sh5 else 800,
+                                      "collective": ("one NCCL all-reduce(sum) of (4,4) float64 over %d ranks per rollout" % world) if world > 1 else "none",
+                                      "config": "configs[4]: N=800 samples, T=15, R=1 root",
+                                      "algorithmic_tflops": rollout_flops(800, 15) / (ms5 * 1e-3) / 1e12}
 
     if rank != 0:
         if world > 1:
@@ -292,10 +373,10 @@ def main():
         "data": "synthetic", "config": dict(config, precision=args.precision, shard=args.shard if world > 1 else "none",
                                             roots_total=total_roots, roots_per_rank=my_roots,
                                             samples_per_rank=(shard[1] - shard[0]) if shard else N,
+                                            returns="G, term0..2 and po1 of the last step, like the reference call",
                                             l2="flushed between timed iterations (160 MB write)"),
         "node_evals_per_s": value * 4 * N * T, "algorithmic_tflops": flops_step / (ms_dev * 1e-3) / 1e12,
-        "e2e": {"value": e2e, "unit": "rollouts/s", "h2d_bytes_per_step": int(o_host.numel() * 4),
-                "d2h_bytes_per_step": int(out_host.numel() * 4)},
+        "e2e": {"value": e2e, "unit": "rollouts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     roof = {"bound": "tensor", "achieved": None, "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None,
@@ -319,13 +400,17 @@ def main():
         roof["kernels"] = {k: {"alg_tflops": 2.0 * m * layers[k][2] / (layers[k][0] * 1e-3) / 1e12,
                                "issued_frac": nprod * 2.0 * m * layers[k][2] / (layers[k][0] * 1e-3) / 1e12 / peak_tf}
                            for k, m in macs.items() if k in layers and layers[k][0] > 0}
+        roof["whole_step"] = {"alg_tflops": flops_step / (ms_dev * 1e-3) / 1e12 / world,
+                              "issued_frac": nprod * flops_step / (ms_dev * 1e-3) / 1e12 / world / peak_tf}
     line["roofline"] = roof
+    if extra:
+        line["extra"] = extra
     if not args.no_cpu_baseline and not args.quick and world == 1:
-        ncalls = 24                                   # ~10 s of CPU work on the box's host cores (0.35 s per call)
-        cv, per_call, cores = cpu_reference_run(N, T, ncalls, 2)
-        line["cpu_baseline"] = {"value": cv, "unit": "rollouts/s", "cores": cores, "kind": "port",
-                                "sample": "calculate_G_4_repeated(steps=1, samples=%d), 1 root, %d timed calls "
-                                          "(%.2f s each), scaled by 1/T" % (N, ncalls, per_call)}
+        r = cpu_reference_run(N, T, 3, 1)            # 4 full calls + 1 as shipped: ~15-20 s of CPU work on the box
+        line["cpu_baseline"] = {"value": r["value"], "unit": "rollouts/s", "cores": r["cores"], "kind": r["kind"],
+                                "as_shipped_value": r["as_shipped_value"],
+                                "sample": "3 timed + 1 warm-up full calculate_G_4_repeated(o, steps=%d, samples=%d) calls for 1 root "
+                                          "under torch.no_grad() (%.2f s each), +1 as shipped; code: %s" % (T, N, r["per_call_s"], r["where"])}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
