@@ -240,9 +240,10 @@ def main():
         total_roots = R
     flush = torch.empty(160 * 1024 * 1024 // 4, device=dev)      # > 126 MB L2
 
-    def make_steps(roots, n, t, shard_, group_, seed):
+    def make_steps(roots, n, t, shard_, group_, seed, native=False):
         """(device-resident step, end-to-end step, h2d bytes, d2h bytes) for `roots` roots x 4 actions, n samples, horizon t.
-        Both return what the reference call returns: G, the three terms and po1 of the last step."""
+        Both return what the reference call returns: G, the three terms and po1 of the last step.  native: the sample
+        shards are combined inside the C ABI (dai_rollout_sharded: the library's own NCCL all-reduce)."""
         frames = torch.from_numpy(synthetic.make_frames(roots, seed=seed))
         o_host = frames.repeat_interleave(4, dim=0).reshape(4 * roots, 4096).contiguous().pin_memory()
         o_dev = o_host.to(dev)
@@ -250,6 +251,8 @@ def main():
         po1_host = torch.empty(4 * roots, 4096).pin_memory()
 
         def step_device():
+            if native:
+                return eng.rollout_sharded(o_dev, None, t, n, calc_mean=False, four=False, want_po1=True)
             out = eng.rollout(o_dev, None, t, n, calc_mean=False, four=False, shard=shard_, want_po1=True)
             if shard_ is not None:
                 dist.all_reduce(out["sums"], group=group_)
@@ -257,13 +260,17 @@ def main():
             return out
 
         def step_e2e():
-            if shard_ is None:
+            if shard_ is None and not native:
                 eng.rollout_host(o_host, None, t, n, False, False, out_host, po1_host)
             else:
                 o = o_host.to(dev, non_blocking=True)
-                out = eng.rollout(o, None, t, n, calc_mean=False, four=False, shard=shard_, want_po1=True)
-                dist.all_reduce(out["sums"], group=group_)
-                G, t0, t1, t2 = eng.combine(out["sums"], n)
+                if native:
+                    out = eng.rollout_sharded(o, None, t, n, calc_mean=False, four=False, want_po1=True)
+                    G, t0, t1, t2 = out["G"], out["t0"], out["t1"], out["t2"]
+                else:
+                    out = eng.rollout(o, None, t, n, calc_mean=False, four=False, shard=shard_, want_po1=True)
+                    dist.all_reduce(out["sums"], group=group_)
+                    G, t0, t1, t2 = eng.combine(out["sums"], n)
                 out_host[0].copy_(G, non_blocking=True)
                 out_host[1].copy_(t0, non_blocking=True)
                 out_host[2].copy_(t1, non_blocking=True)
@@ -344,12 +351,15 @@ def main():
         # configs[4]: N=800 samples sharded over ALL ranks, T=15, one root, ONE all-reduce of the (4,B) f64 term sums over
         # the world group per rollout (at N=1: the same rollout unsharded, the strong-scaling base)
         sh5 = shard_range(800, rank, world) if world > 1 else None
-        d5, e5, _, _ = make_steps(1, 800, 15, sh5, None, 3)
+        if world > 1:
+            model.enable_sample_sharding(native=True)        # dai_comm_init over all ranks: the C ABI owns the all-reduce
+        d5, e5, _, _ = make_steps(1, 800, 15, sh5, None, 3, native=world > 1)
         ms5 = timed(d5, ks, 2)
         ms5e = timed(e5, ks, 1)
         extra["c5_sample_sharded"] = {"value": 1.0 / (ms5 * 1e-3), "e2e": 1.0 / (ms5e * 1e-3), "unit": "rollouts/s", "ms_per_step": ms5,
                                       "n_gpus": world, "scaling": "strong", "samples_per_rank": (sh5[1] - sh5[0]) if sh5 else 800,
-                                      "collective": ("one NCCL all-reduce(sum) of (4,4) float64 over %d ranks per rollout" % world) if world > 1 else "none",
+                                      "collective": ("one ncclAllReduce(sum) of (4,4) float64 over %d ranks per rollout, issued inside "
+                                                     "dai_rollout_sharded (C ABI)" % world) if world > 1 else "none",
                                       "config": "configs[4]: N=800 samples, T=15, R=1 root",
                                       "algorithmic_tflops": rollout_flops(800, 15) / (ms5 * 1e-3) / 1e12}
 

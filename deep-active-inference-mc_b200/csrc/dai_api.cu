@@ -2,6 +2,8 @@
 // the kernels into the reference's EFE evaluators (src/torchmodel.py:210-393).
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -87,6 +89,10 @@ struct dai_handle {
     DevBuf plan_tree, plan_picks, plan_rows, plan_out, plan_pi0;
     int32_t* plan_stop_host = nullptr;   // mapped pinned flag: the search's threshold test fired
     int32_t* plan_stop_dev = nullptr;
+    cudaEvent_t plan_sel_ev = nullptr;   // recorded after every selection kernel: bounds the host's run-ahead to one batch
+    // sample-shard communicator (NCCL, resolved at run time; SURVEY.md §8 e)
+    void* comm = nullptr;      // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
     float* pinned = nullptr;   // small host result buffer
     size_t pinned_cap = 0;
 };
@@ -370,51 +376,59 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     return post_launch(h, "decoder");
 }
 
-// Runs Qs on `rows` images with noise map (B, Sl, sample0, site); outputs [rows][10] each.
+// Runs Qs on `rows` images with noise map (B, Sl, sample0, site); outputs [rows][10] each.  Rows are ordered (slot, b);
+// a launch covers either whole slots (B <= chunk) or a run of rows of ONE slot (B > chunk: noise row = b0 + local row).
 int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl, int sample0, int site,
                 const NoiseKey& nk, float* mean, float* logvar, float* samp) {
     const int rows = B * Sl;
     if (rows <= 0) return DAI_OK;
-    const int ch = std::min(rows, kQsChunk);
-    // chunks must hold whole slots so the (slot, b) decode stays valid: a multiple of B; equal chunks rather than a
-    // full one and a short one (slots per chunk = ceil(Sl / nchunks))
-    int chs = ch;
-    if (rows > ch) {
-        const int slots_max = ch / B;
-        if (slots_max == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
+    // equal chunks rather than a full one and a short one
+    int slots_per = Sl, rows_per = B;                // launch = slots_per whole slots, or rows_per rows of one slot
+    if (B > kQsChunk) {
+        const int nchunks = (B + kQsChunk - 1) / kQsChunk;
+        slots_per = 1; rows_per = (B + nchunks - 1) / nchunks;
+    } else if (rows > kQsChunk) {
+        const int slots_max = kQsChunk / B;
         const int nchunks = (Sl + slots_max - 1) / slots_max;
-        chs = ((Sl + nchunks - 1) / nchunks) * B;
-        if (chs == 0) return fail(h, DAI_E_UNSUPPORTED, "encoder batch %d exceeds the chunk size %d", B, kQsChunk);
+        slots_per = (Sl + nchunks - 1) / nchunks;
     }
+    const int chs = B > kQsChunk ? rows_per : slots_per * B;     // largest launch
     const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
     RET(reserve(h, h->qc1, (size_t)chs * 32768 * sizeof(float)));   // (31,31,32) fp32, or 2 x 4 parities x (16,16,32) bf16
     RET(reserve(h, h->qc2, (size_t)chs * 8192 * sizeof(float)));    // (15,15,32) fp32, or 2 x 4 parities x (8,8,32) bf16
     RET(reserve(h, h->qc3, (size_t)chs * 49 * 64 * sizeof(float)));
-    RET(reserve(h, h->qc4, (size_t)chs * 576 * sizeof(float)));
-    for (int r0 = 0; r0 < rows; r0 += chs) {
-        const int n = std::min(chs, rows - r0);
-        QsArgs a{};
-        a.img = img + (size_t)r0 * IMG; a.rows = n;
-        a.map.B = B; a.map.Sl = (n + B - 1) / B; a.map.sample0 = sample0 + r0 / B; a.map.nsets = 1;
-        a.map.site[0] = site; a.map.site[1] = site; a.map.site[2] = site;
-        a.c1 = ptr<float>(h->qc1); a.c2 = ptr<float>(h->qc2); a.c3 = ptr<float>(h->qc3); a.c4 = ptr<float>(h->qc4);
-        a.mean = mean + (size_t)r0 * S_DIM; a.logvar = logvar + (size_t)r0 * S_DIM;
-        a.samp = samp ? samp + (size_t)r0 * S_DIM : nullptr;
-        a.nk = nk;
-        if (!tc) {
-            h->launches += launch_qs(h->w, a, st);
-        } else {
+    RET(reserve(h, h->qc4, tc ? std::max((size_t)chs * 576 * sizeof(float), tc_qs_conv4_scratch_bytes(chs)) : (size_t)chs * 576 * sizeof(float)));
+    const size_t rp_max = ((size_t)chs + 127) / 128 * 128 + 128;
+    if (tc) {
+        RET(reserve(h, h->mlpA, rp_max * 576 * 2 * sizeof(unsigned short)));
+        RET(reserve(h, h->mlpB, rp_max * 576 * 2 * sizeof(unsigned short)));
+    }
+    for (int s0 = 0; s0 < Sl; s0 += slots_per) {
+        const int ns = std::min(slots_per, Sl - s0);
+        for (int b0 = 0; b0 < B; b0 += rows_per) {
+            const int nb = std::min(rows_per, B - b0);
+            const int r0 = s0 * B + b0;                 // first row of this launch
+            const int n = ns * nb;                      // (rows_per == B) or (ns == 1)
+            QsArgs a{};
+            a.img = img + (size_t)r0 * IMG; a.rows = n;
+            a.map.B = nb; a.map.Sl = ns; a.map.sample0 = sample0 + s0; a.map.nsets = 1; a.map.b0 = b0;
+            a.map.site[0] = site; a.map.site[1] = site; a.map.site[2] = site;
+            a.c1 = ptr<float>(h->qc1); a.c2 = ptr<float>(h->qc2); a.c3 = ptr<float>(h->qc3); a.c4 = ptr<float>(h->qc4);
+            a.mean = mean + (size_t)r0 * S_DIM; a.logvar = logvar + (size_t)r0 * S_DIM;
+            a.samp = samp ? samp + (size_t)r0 * S_DIM : nullptr;
+            a.nk = nk;
+            if (!tc) {
+                h->launches += launch_qs(h->w, a, st);
+                continue;
+            }
             h->launches += launch_qs_conv1(h->w, a.img, n, nullptr, h->qc1.p, st);
             std::string terr;
             const int nl = tc_qs_convs(h->tcw, h->w, h->cfg.precision, h->qc1.p, h->qc2.p, a.c3, n, st, &terr);
             if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder convs: %s", terr.c_str());
             h->launches += nl;
-            // conv4 on CUDA cores -> K-blocked operand; FC1..3 on tensor cores; tail (256 -> 20) on CUDA cores
+            // conv4 as im2col + GEMM -> K-blocked operand; FC1..3 on tensor cores; tail (256 -> 20) on CUDA cores
             const size_t rp = ((size_t)n + 127) / 128 * 128 + 128;
-            RET(reserve(h, h->mlpA, rp * 576 * 2 * sizeof(unsigned short)));
-            RET(reserve(h, h->mlpB, rp * 576 * 2 * sizeof(unsigned short)));
             const NoiseRows nr = map_noise_rows(a.map);
-            RET(reserve(h, h->qc4, tc_qs_conv4_scratch_bytes(n)));
             const int n4 = tc_qs_conv4(h->tcw, h->cfg.precision, a.c3, n, h->qc4.p, rp, h->mlpA.p, st, &terr);
             if (n4 < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder conv4: %s", terr.c_str());
             h->launches += n4;
@@ -575,6 +589,8 @@ int rollout_impl(dai_handle* h, cudaStream_t st, const float* o, const float* pi
 // =======================================================================================
 extern "C" {
 
+int dai_comm_destroy(dai_handle* h);
+
 const char* dai_version(void) { return "dai_b200 0.1 (sm_100a)"; }
 
 int dai_create(const dai_config* cfg, int device, dai_handle** out) {
@@ -615,6 +631,8 @@ int dai_destroy(dai_handle* h) {
     tc_release(&h->tcw);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->plan_stop_host) cudaFreeHost(h->plan_stop_host);
+    if (h->plan_sel_ev) cudaEventDestroy(h->plan_sel_ev);
+    dai_comm_destroy(h);
     delete h;
     return DAI_OK;
 }
@@ -916,6 +934,7 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
         CK(cudaHostAlloc(&h->plan_stop_host, 64, cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer(&h->plan_stop_dev, h->plan_stop_host, 0));
     }
+    if (!h->plan_sel_ev) CK(cudaEventCreateWithFlags(&h->plan_sel_ev, cudaEventDisableTiming));
     *(volatile int32_t*)h->plan_stop_host = 0;      // the previous decision ended with a stream wait: no kernel writes it now
     // ---- carve the tree, the picks and the row buffers
     const int cap = 1 + PI_DIM * (R + K + 2), log_cap = std::max(R, 1);
@@ -966,6 +985,7 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
     auto expand = [&](int kv) -> int {          // kv <= 0: the root itself
         const int rows = PI_DIM * std::max(kv, 1);
         h->launches += launch_plan_select(t, kv, prm->threshold, pk, s_rows, starts, st);
+        CK(cudaEventRecord(h->plan_sel_ev, st));
         if (prm->use_means) RET(dai_calculate_G_mean(h, s_rows, pi_eye, rows, Gd, nullptr, nullptr, nullptr, nxt, nullptr, stream));
         else RET(dai_calculate_G(h, s_rows, pi_eye, rows, prm->samples, 0, prm->samples, nullptr, Gd, nullptr, nullptr, nullptr,
                                  nxt, nullptr, nullptr, nullptr, stream));
@@ -973,9 +993,15 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
         return post_launch(h, "planner expansion");
     };
     RET(expand(0));
+    const uint64_t call_after_root = h->call;
+    const uint64_t calls_per_batch = 1 + 2 * (uint64_t)nrep;    // one EFE evaluation + nrep x (rollout, trajectory)
     int done = 0, leaves_now = PI_DIM;
     while (done < R) {
-        if (*(volatile int32_t*)h->plan_stop_host) break;       // the device's threshold test fired (src/mcts.py:176)
+        // The threshold test of batch i runs in its selection kernel (src/mcts.py:176).  Wait for the PREVIOUS selection
+        // before enqueuing the next batch: the GPU still has that batch's evaluation queued, so it never starves, and the
+        // host is never more than one batch ahead of a stop (the batch whose selection raised it is a no-op on the device).
+        CK(cudaEventSynchronize(h->plan_sel_ev));
+        if (*(volatile int32_t*)h->plan_stop_host) break;
         const int kv = std::min(std::min(K, leaves_now), R - done);
         RET(expand(kv));
         for (int r = 0; r < nrep; ++r) {
@@ -995,6 +1021,13 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
     CK(cudaStreamSynchronize(st));
     if (ctl[PLAN_ERR]) return fail(h, DAI_E_UNSUPPORTED, "mcts_plan: %s", ctl[PLAN_ERR] == 1 ? "search path deeper than 64 edges" : "tree capacity exceeded");
     res->path_len = out[0]; res->repeats_done = ctl[PLAN_DONE]; res->stopped = ctl[PLAN_STOP]; res->logged = ctl[PLAN_LOGGED];
+    {   // the call index after a decision counts only the batches the search used (a batch enqueued behind a stop drew
+        // nothing that was kept), so it equals the host-driven planner's and does not depend on timing
+        int d = 0, lv = PI_DIM;
+        uint64_t nb = 0;
+        while (d < ctl[PLAN_DONE]) { const int kv = std::min(std::min(K, lv), R - d); d += kv; lv += 3 * kv; ++nb; }
+        h->call = call_after_root + nb * calls_per_batch;
+    }
     if (out[0] > PLAN_MAX_DEPTH) return fail(h, DAI_E_UNSUPPORTED, "mcts_plan: decision path deeper than 64 edges");
     for (int i = 0; i < out[0]; ++i) path_host[i] = out[1 + i];
     const int nlog = std::min(ctl[PLAN_LOGGED], log_cap);
@@ -1121,6 +1154,135 @@ int dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, in
     if (layer != 3) h->launches += tc_from_blocked(h->act1.p, nrows, hw_out, 64, out, st);
     else h->launches += launch_proj_rows(ptr<float>(h->act3), nrows, out, st);
     return post_launch(h, "debug layer (tc)");
+}
+
+}  // extern "C"
+
+// =======================================================================================
+// Sample-shard communicator: the ONE collective of a sharded rollout (SURVEY.md §8 e) lives behind the C ABI.
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy already loaded into the process — e.g. torch's — or
+// the system one), so the library has no link-time dependency on it and single-GPU users never touch it.
+// =======================================================================================
+namespace {
+
+struct NcclId { char internal[128]; };          // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return api; }
+    api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(lib, "ncclCommInitRank"));
+    api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(lib, "ncclAllReduce"));
+    api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(lib, "ncclCommDestroy"));
+    api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(lib, "ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    if (!api.ok) api.why = "libnccl.so.2 lacks a required symbol";
+    return api;
+}
+
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;   // nccl.h: ncclFloat64, ncclSum
+
+void shard_of(int samples, int rank, int world, int* j0, int* j1) {
+    // contiguous; the first samples % world ranks hold one more (sharding.shard_range)
+    const int base = samples / world, rem = samples % world;
+    *j0 = rank * base + std::min(rank, rem);
+    *j1 = *j0 + base + (rank < rem ? 1 : 0);
+}
+
+int allreduce_sums(dai_handle* h, double* sums, int B, cudaStream_t st) {
+    if (h->comm_world == 1) return DAI_OK;
+    const int rc = nccl().AllReduce(sums, sums, (size_t)4 * B, kNcclFloat64, kNcclSum, h->comm, st);
+    if (rc != 0) return fail(h, DAI_E_CUDA, "ncclAllReduce: %s", nccl().GetErrorString(rc));
+    return DAI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dai_comm_unique_id(void* id128) {
+    if (!id128) return DAI_E_INVALID;
+    if (!nccl().ok) return DAI_E_UNSUPPORTED;
+    NcclId id;
+    if (nccl().GetUniqueId(&id) != 0) return DAI_E_CUDA;
+    memcpy(id128, &id, sizeof(id));
+    return DAI_OK;
+}
+
+int dai_comm_init(dai_handle* h, const void* id128, int rank, int world) {
+    if (!h || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) return fail(h, DAI_E_INVALID, "comm_init: bad arguments");
+    CK(cudaSetDevice(h->device));
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
+    h->comm_rank = rank; h->comm_world = world;
+    if (world == 1) return DAI_OK;
+    if (!nccl().ok) return fail(h, DAI_E_UNSUPPORTED, "comm_init: NCCL unavailable (%s)", nccl().why.c_str());
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = nccl().CommInitRank(&h->comm, world, id, rank);
+    if (rc != 0) { h->comm = nullptr; h->comm_world = 1; h->comm_rank = 0; return fail(h, DAI_E_CUDA, "ncclCommInitRank: %s", nccl().GetErrorString(rc)); }
+    return DAI_OK;
+}
+
+int dai_comm_destroy(dai_handle* h) {
+    if (!h) return DAI_E_INVALID;
+    if (h->comm) { cudaSetDevice(h->device); nccl().CommDestroy(h->comm); h->comm = nullptr; }
+    h->comm_rank = 0; h->comm_world = 1;
+    return DAI_OK;
+}
+
+int dai_comm_info(const dai_handle* h, int* rank, int* world) {
+    if (!h) return DAI_E_INVALID;
+    if (rank) *rank = h->comm_rank;
+    if (world) *world = h->comm_world;
+    return DAI_OK;
+}
+
+int dai_rollout_sharded(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples, int calc_mean, int four,
+                        float* G, float* t0, float* t1, float* t2, float* po1, void* stream) {
+    RET(check_ready(h));
+    if (!o) return fail(h, DAI_E_INVALID, "rollout_sharded: o is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    int j0 = 0, j1 = samples;
+    const bool sharded = h->comm_world > 1 && !(four && calc_mean);    // calculate_G_mean steps have one sample: nothing to shard
+    if (sharded) shard_of(samples, h->comm_rank, h->comm_world, &j0, &j1);
+    if (!sharded) return rollout_impl(h, st, o, pi, B, steps, samples, calc_mean, four, 0, samples, nullptr, G, t0, t1, t2, po1);
+    RET(rollout_impl(h, st, o, pi, B, steps, samples, calc_mean, four, j0, j1, nullptr, nullptr, nullptr, nullptr, nullptr, po1));
+    RET(allreduce_sums(h, ptr<double>(h->acc), B, st));
+    return finish_outputs(h, st, B, samples, nullptr, G, t0, t1, t2);
+}
+
+int dai_calculate_G_sharded(dai_handle* h, const float* s0, const float* pi0, int B, int samples, float* G, float* t0, float* t1,
+                            float* t2, float* ps1, float* ps1_mean, float* ps1_logvar, float* po1, void* stream) {
+    RET(check_ready(h));
+    if (!s0 || !pi0 || B <= 0 || samples <= 0) return fail(h, DAI_E_INVALID, "calculate_G_sharded: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int j0 = 0, j1 = samples;
+    if (h->comm_world > 1) shard_of(samples, h->comm_rank, h->comm_world, &j0, &j1);
+    RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
+    CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
+    StepSpec sp;
+    sp.s0 = s0; sp.pi = pi0; sp.B = B; sp.samples = samples; sp.j0 = j0; sp.j1 = j1;
+    sp.nk = make_key(h, h->call++, 0);
+    ++h->calls;
+    sp.acc = ptr<double>(h->acc);
+    sp.out_ps1 = ps1; sp.out_mean = ps1_mean; sp.out_logvar = ps1_logvar; sp.out_po1 = po1;
+    RET(run_step(h, st, sp));
+    RET(allreduce_sums(h, ptr<double>(h->acc), B, st));
+    return finish_outputs(h, st, B, samples, nullptr, G, t0, t1, t2);
 }
 
 }  // extern "C"

@@ -66,8 +66,9 @@ struct RowMap {
     int32_t sample0;    // global index of local sample slot 0
     int32_t nsets;
     int32_t site[3];    // noise site base per set
+    int32_t b0;         // row offset of this launch inside the call's batch (encoder row chunks: noise row = b0 + local row)
     __device__ __forceinline__ void decode(int r, int& set, int& slot, int& b) const {
-        b = r % B;
+        b = r % B + b0;
         const int q = r / B;
         slot = q % Sl;
         set = q / Sl;
@@ -85,11 +86,12 @@ struct NoiseRows {
     int32_t sample0;        // global sample of slot 0
     int32_t extra_slot;     // set 0 only: slot that stands for global sample `extra_sample` (or -1)
     int32_t extra_sample;
+    int32_t b0;             // see RowMap::b0
     __device__ __forceinline__ void decode(int r, int& site_out, int& b, uint32_t& sample) const {
         const int set = r < set_end[0] ? 0 : (r < set_end[1] ? 1 : 2);
         const int q = r - (set == 0 ? 0 : set_end[set - 1]);
         const int slot = q / B;
-        b = q - slot * B;
+        b = q - slot * B + b0;
         site_out = site[set];
         sample = (set == 0 && slot == extra_slot) ? (uint32_t)extra_sample : (uint32_t)(sample0 + slot);
     }

@@ -1034,7 +1034,7 @@ NoiseRows map_noise_rows(const RowMap& m) {
     NoiseRows nr{};
     nr.B = m.B;
     for (int i = 0; i < 3; ++i) { nr.set_end[i] = (i < m.nsets ? i + 1 : m.nsets) * m.Sl * m.B; nr.site[i] = m.site[i < m.nsets ? i : m.nsets - 1]; }
-    nr.sample0 = m.sample0; nr.extra_slot = -1; nr.extra_sample = 0;
+    nr.sample0 = m.sample0; nr.extra_slot = -1; nr.extra_sample = 0; nr.b0 = m.b0;
     return nr;
 }
 

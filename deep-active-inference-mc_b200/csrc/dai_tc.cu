@@ -335,7 +335,9 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&a)[4], c
 // (A_hi*B_hi, A_hi*B_lo), pass 2 on the lo plane (A_lo*B_hi); the planes travel through the ring
 // separately so three 20 KB slots are enough to keep the next tile's data in flight.
 // ---------------------------------------------------------------------------------------
-template <class C>
+// DBG = true is the experiments build of the same kernel (in-kernel cycle counters, `p.dbg` switches; env DAI_TC_DBG /
+// DAI_TC_COUNTERS select it at launch); the production instantiation carries none of it.
+template <class C, bool DBG>
 __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant__ CUtensorMap tmapA, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smW = smem;
@@ -396,57 +398,63 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             tc_fence_after();
             const uint32_t w16 = smem_u32(smW) >> 4, a16 = smem_u32(smA) >> 4;
             int it = 0, cnt = 0;
-            long long t_begin = clock64(), w_acc = 0, w_a = 0;
-            unsigned long long ns_begin;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+            long long t_begin = 0, w_acc = 0, w_a = 0, tw = 0;
+            unsigned long long ns_begin = 0;
+            if constexpr (DBG) {
+                t_begin = clock64();
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+            }
+            const bool issue = !DBG || !(p.dbg & 2);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int buf = it % C::NACC;
                 const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
-                long long tw = clock64();
+                if constexpr (DBG) tw = clock64();
                 mbar_wait(&acc_empty[buf], aph ^ 1u);
-                w_acc += clock64() - tw;
+                if constexpr (DBG) w_acc += clock64() - tw;
                 const uint32_t d0 = tmem_base + (uint32_t)(buf * C::ACC_COLS);
                 const int s0 = cnt % C::NA;
-                tw = clock64();
+                if constexpr (DBG) tw = clock64();
                 mbar_wait(&a_full[s0], (uint32_t)(cnt / C::NA) & 1u);
                 ++cnt;
                 if (nplanes == 1) {
-                    w_a += clock64() - tw;
+                    if constexpr (DBG) w_a += clock64() - tw;
                     tc_fence_after();
-                    if (!(p.dbg & 2)) issue_tile<C, 2, false>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
+                    if (issue) issue_tile<C, 2, false>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
                     umma_commit(&a_empty[s0]);
                 } else if (p.two_pass) {
-                    w_a += clock64() - tw;
+                    if constexpr (DBG) w_a += clock64() - tw;
                     tc_fence_after();
-                    if (!(p.dbg & 2)) issue_tile<C, 0, true>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
+                    if (issue) issue_tile<C, 0, true>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), 0u, w16, d0);
                     umma_commit(&a_empty[s0]);
                     const int s1 = cnt % C::NA;
-                    tw = clock64();
+                    if constexpr (DBG) tw = clock64();
                     mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
                     ++cnt;
-                    w_a += clock64() - tw;
+                    if constexpr (DBG) w_a += clock64() - tw;
                     tc_fence_after();
-                    if (!(p.dbg & 2)) issue_tile<C, 1, true>(0u, a16 + (uint32_t)s1 * (C::PLANE_A >> 4), w16, d0);
+                    if (issue) issue_tile<C, 1, true>(0u, a16 + (uint32_t)s1 * (C::PLANE_A >> 4), w16, d0);
                     umma_commit(&a_empty[s1]);
                 } else {
                     const int s1 = cnt % C::NA;
                     mbar_wait(&a_full[s1], (uint32_t)(cnt / C::NA) & 1u);
                     ++cnt;
-                    w_a += clock64() - tw;
+                    if constexpr (DBG) w_a += clock64() - tw;
                     tc_fence_after();
-                    if (!(p.dbg & 2))
+                    if (issue)
                         issue_tile<C, 2, true>(a16 + (uint32_t)s0 * (C::PLANE_A >> 4), a16 + (uint32_t)s1 * (C::PLANE_A >> 4), w16, d0);
                     umma_commit(&a_empty[s0]);
                     umma_commit(&a_empty[s1]);
                 }
                 umma_commit(&acc_full[buf]);
             }
-            if (p.counters && lane == 0) {
-                long long* c = p.counters + (size_t)blockIdx.x * 8;
-                c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = it;
-                unsigned long long ns_end;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
-                c[6] = (long long)(ns_end - ns_begin);
+            if constexpr (DBG) {
+                if (p.counters && lane == 0) {
+                    long long* c = p.counters + (size_t)blockIdx.x * 8;
+                    c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = it;
+                    unsigned long long ns_end;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+                    c[6] = (long long)(ns_end - ns_begin);
+                }
             }
         }
     } else if (warp < C::EPI_WARPS) {
@@ -457,18 +465,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
         const int m = ew * 32 + lane;
         const int ty = m >> 3, tx = m & 7;
         int it = 0;
-        long long e_begin = clock64(), e_wait = 0;
+        long long e_begin = 0, e_wait = 0, ew0 = 0;
+        if constexpr (DBG) e_begin = clock64();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int buf = it % C::NACC;
             const uint32_t aph = (uint32_t)(it / C::NACC) & 1u;
             const int row = tile / C::TILES, t = tile % C::TILES;
             const int y = (t / C::TILES_X) * C::TH + ty, x = (t % C::TILES_X) * C::TW + tx;
-            const long long ew0 = clock64();
+            if constexpr (DBG) ew0 = clock64();
             mbar_wait(&acc_full[buf], aph);
-            e_wait += clock64() - ew0;
+            if constexpr (DBG) e_wait += clock64() - ew0;
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
-            if (p.dbg & 1) {
+            if (DBG && (p.dbg & 1)) {
             } else if (C::MODE != 1) {
                 // 32 of the NPH output channels of this pixel (half = which 32, when NPH = 64)
                 const int c0 = (C::NPH == 64) ? half * 32 : 0;
@@ -538,7 +547,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     uint32_t rl[32], rr[32];
                     tmem_ld32(tbase + slot_l * 32, rl);
                     tmem_ld32(tbase + slot_r * 32, rr);
-                    if (p.dbg & 8) {       // experiment: TMEM loads only
+                    if (DBG && (p.dbg & 8)) {       // experiment: TMEM loads only
                         if (rl[0] == 0x12345678u && rr[5] == 0x9abcdef0u) out[o] = 1.0f;
                     } else
                     {
@@ -555,7 +564,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 #pragma unroll
                             for (int t9 = 0; t9 < 9; ++t9) acc[t9] = ffma2(v, w4p[c * 9 + t9], acc[t9]);
                         }
-                        if ((p.dbg & 4) && acc[0] == 123ull) {
+                        if (DBG && (p.dbg & 4) && acc[0] == 123ull) {
                         } else {
                             const int txl = lane & 7;
                             float* edge = out + 3 * HO * WO + ((size_t)oy * C::TILES_X + (t % C::TILES_X)) * 2;
@@ -604,9 +613,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (p.counters && warp == 0 && lane == 0) {
-            long long* c = p.counters + (size_t)blockIdx.x * 8;
-            c[3] = clock64() - e_begin; c[4] = e_wait;
+        if constexpr (DBG) {
+            if (p.counters && warp == 0 && lane == 0) {
+                long long* c = p.counters + (size_t)blockIdx.x * 8;
+                c[3] = clock64() - e_begin; c[4] = e_wait;
+            }
         }
     }
     tc_fence_before();
@@ -1005,7 +1016,13 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = nrows * C::TILES;
     const int grid = ntiles < sms ? ntiles : sms;
-    k_tc_conv<C><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+    if (env_dbg || want_counters) {
+        static bool attr_dbg = false;
+        if (!attr_dbg) { cudaFuncSetAttribute(k_tc_conv<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); attr_dbg = true; }
+        k_tc_conv<C, true><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+    } else {
+        k_tc_conv<C, false><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+    }
     if (want_counters) {
         static int printed = 0;
         cudaStreamSynchronize(st);
@@ -1101,11 +1118,11 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         im->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     }
     if (!im->attrs_set) {
-        if (cudaFuncSetAttribute(k_tc_conv<CfgCt1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt1::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_conv<CfgCt2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt2::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_conv<CfgCt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_conv<CfgQc2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_conv<CfgQc3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
+        if (cudaFuncSetAttribute(k_tc_conv<CfgCt1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt1::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgCt2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt2::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgCt3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgQc2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgQc3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<256, EPI_FC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, EPI_FC4>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<128, EPI_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, EPI_HIDDEN>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<64, EPI_CONV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<64, EPI_CONV4>::SMEM) != cudaSuccess) {

@@ -81,6 +81,14 @@ SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                      ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float), _vp]),
     "dai_select_actions": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_float, _vp, _vp, _vp, _vp]),
+    "dai_comm_unique_id": (ctypes.c_int, [_vp]),
+    "dai_comm_init": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int]),
+    "dai_comm_destroy": (ctypes.c_int, [_vp]),
+    "dai_comm_info": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "dai_rollout_sharded": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dai_calculate_G_sharded": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _vp]),
     "dai_profile_begin": (ctypes.c_int, [_vp]),
     "dai_profile_end": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64),
                                        ctypes.POINTER(ctypes.c_int64), _vp]),
@@ -124,7 +132,8 @@ class Engine:
         if not torch.cuda.is_available():
             raise DaiError("no CUDA device: the EFE rollout path is CUDA-only (sm_100a), there is no CPU fallback")
         self.lib = load_library()
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        idx = None if device is None else torch.device(device).index      # "cuda" without an index = the current device
+        self.device = torch.device("cuda", torch.cuda.current_device() if idx is None else idx)
         cfg = DaiConfig(10, 4, 64, 1, PRECISIONS[precision] if isinstance(precision, str) else int(precision),
                         1 if training else 0)
         h = _vp()
@@ -274,6 +283,46 @@ class Engine:
         self._ck(self.lib.dai_rollout(self.h, _p(o), _p(pi), B, steps, samples, 1 if calc_mean else 0, 1 if four else 0,
                                       j0, j1, _p(out["sums"]), _p(out["G"]), _p(out["t0"]), _p(out["t1"]),
                                       _p(out["t2"]), _p(out["po1"]), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ sample sharding behind the C ABI
+    def comm_unique_id(self):
+        """128 bytes (ncclUniqueId) from rank 0, to be handed to every rank's comm_init."""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.dai_comm_unique_id(buf)
+        if rc != 0:
+            raise DaiError("dai_comm_unique_id failed with code %d (NCCL not loadable?)" % rc)
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.dai_comm_init(self.h, ctypes.c_char_p(unique_id) if unique_id is not None else None, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w = ctypes.c_int(), ctypes.c_int()
+        self._ck(self.lib.dai_comm_info(self.h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
+
+    def rollout_sharded(self, o, pi, steps, samples, calc_mean=False, four=False, want_po1=True):
+        """dai_rollout_sharded: this rank's sample slice + the library's own all-reduce + finish."""
+        o = self.dev(o).reshape(-1, 4096)
+        B = o.shape[0]
+        pi = None if pi is None else self.dev(pi).reshape(B, 4)
+        out = dict(G=self.new(B), t0=self.new(B), t1=self.new(B), t2=self.new(B),
+                   po1=self.new(B, 1, 64, 64) if want_po1 else None)
+        self._ck(self.lib.dai_rollout_sharded(self.h, _p(o), _p(pi), B, steps, samples, 1 if calc_mean else 0, 1 if four else 0,
+                                              _p(out["G"]), _p(out["t0"]), _p(out["t1"]), _p(out["t2"]), _p(out["po1"]),
+                                              self._stream()))
+        return out
+
+    def calculate_G_sharded(self, s0, pi0, samples, want_po1=True):
+        s0, pi0 = self.dev(s0).reshape(-1, 10), self.dev(pi0).reshape(-1, 4)
+        B = s0.shape[0]
+        out = dict(G=self.new(B), t0=self.new(B), t1=self.new(B), t2=self.new(B), ps1=self.new(B, 10),
+                   ps1_mean=self.new(B, 10), ps1_logvar=self.new(B, 10), po1=self.new(B, 1, 64, 64) if want_po1 else None)
+        self._ck(self.lib.dai_calculate_G_sharded(self.h, _p(s0), _p(pi0), B, samples, _p(out["G"]), _p(out["t0"]), _p(out["t1"]),
+                                                  _p(out["t2"]), _p(out["ps1"]), _p(out["ps1_mean"]), _p(out["ps1_logvar"]),
+                                                  _p(out["po1"]), self._stream()))
         return out
 
     def combine(self, sums, samples):

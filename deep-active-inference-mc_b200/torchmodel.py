@@ -141,10 +141,15 @@ class ActiveInferenceModel:
         self._versions = None
         self._plist = None
         self._group = None          # torch.distributed group for MC-sample sharding
+        self._native_comm = False   # True: the C ABI owns the all-reduce (dai_comm_init)
         self._engine.set_rng(seed, 0)
 
     # ------------------------------------------------------------------ plumbing
     def to(self, device=None, *a, **k):     # D3: train.py:97 / test_demo.py:48 call .to(device)
+        if device is not None and not isinstance(device, torch.dtype):
+            d = torch.device(device)
+            if d.type != "cuda" or (d.index is not None and d.index != self.device.index):
+                raise DaiError("the model lives on %s (one engine handle per device); construct it with device=%s" % (self.device, d))
         return self
 
     def _params(self):
@@ -176,11 +181,21 @@ class ActiveInferenceModel:
     def set_precision(self, precision):
         self._engine.set_precision(precision)
 
-    def enable_sample_sharding(self, group=None):
-        """Shard the MC samples of calculate_G / calculate_G_repeated over the ranks of a
-        torch.distributed group (NCCL): one all-reduce of the (4,B) float64 term sums per call."""
+    def enable_sample_sharding(self, group=None, native=True):
+        """Shard the MC samples of calculate_G / calculate_G_repeated over the ranks of a torch.distributed
+        group: one all-reduce of the (4,B) float64 term sums per call.  native=True (default): the library owns
+        the collective (dai_comm_init / dai_rollout_sharded: its own NCCL communicator, the all-reduce enqueued by
+        the C ABI on the call's stream); torch.distributed only carries the 128-byte unique id from rank 0 to the
+        others.  native=False: the sums come back and torch.distributed.all_reduce adds them."""
         import torch.distributed as dist
         self._group = group if group is not None else dist.group.WORLD
+        self._native_comm = False
+        if native:
+            world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+            box = [self._engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self._group, 0), group=self._group)
+            self._engine.comm_init(box[0], rank, world)
+            self._native_comm = True
         return self
 
     def _host(self, t):
@@ -246,8 +261,14 @@ class ActiveInferenceModel:
         return Qpi
 
     # ------------------------------------------------------------------ EFE evaluators
+    def _hosted(self, out):
+        return self._host(out["G"]), [self._host(out["t0"]), self._host(out["t1"]), self._host(out["t2"])]
+
     def calculate_G_repeated(self, o, pi, steps=1, calc_mean=False, samples=10):
         self._sync()
+        if self._native_comm:
+            out = self._engine.rollout_sharded(o, pi, steps, samples, calc_mean=calc_mean, four=False)
+            return (*self._hosted(out), out["po1"])
         shard, world = self._shard(samples)
         out = self._engine.rollout(o, pi, steps, samples, calc_mean=calc_mean, four=False, shard=shard)
         G, terms = self._finish(out, samples, world)
@@ -268,6 +289,9 @@ class ActiveInferenceModel:
 
     def calculate_G_4_repeated(self, o, steps=1, calc_mean=False, samples=10):
         self._sync()
+        if self._native_comm:
+            out = self._engine.rollout_sharded(o, None, steps, samples, calc_mean=calc_mean, four=True)
+            return (*self._hosted(out), out["po1"])
         if calc_mean:       # calculate_G_mean steps have a single sample: nothing to shard
             shard, world = None, 1
         else:
@@ -278,6 +302,9 @@ class ActiveInferenceModel:
 
     def calculate_G(self, s0, pi0, samples=10):
         self._sync()
+        if self._native_comm:
+            out = self._engine.calculate_G_sharded(s0, pi0, samples)
+            return (*self._hosted(out), out["ps1"], out["ps1_mean"], out["po1"])
         shard, world = self._shard(samples)
         out = self._engine.calculate_G(s0, pi0, samples, shard=shard)
         G, terms = self._finish(out, samples, world)

@@ -219,6 +219,28 @@ DAI_API int  dai_frames_set_sprites(dai_handle* h, const uint8_t* imgs_host, int
 DAI_API int  dai_frames_render(dai_handle* h, const float* s, int s_stride, const float* last_r, int G, int reference_bases,
                                float* o, int32_t* n_bad_host, void* stream);
 
+/* ---- MC-sample sharding over GPUs (SURVEY.md §8 e; shards of src/torchmodel.py:273,287) ------------------------
+ * One process per GPU, one handle per process.  Rank r of W evaluates the contiguous sample slice
+ * [r*N/W ...) of every step (the first N % W ranks hold one more sample) with replicated weights; noise is keyed by
+ * the GLOBAL sample index, the globally last loop-2a transition is recomputed on every rank, and the whole call
+ * needs ONE all-reduce(sum) of the (4,B) float64 term sums — issued by the library itself (NCCL, resolved with
+ * dlopen("libnccl.so.2") at run time: no link-time dependency) on the caller's stream.
+ *   dai_comm_unique_id  rank 0: 128 bytes (ncclUniqueId) to hand to every rank out of band (MPI, a file, torch.distributed)
+ *   dai_comm_init       collective over the W ranks; world = 1 detaches (no NCCL needed)
+ *   dai_rollout_sharded / dai_calculate_G_sharded
+ *                       dai_rollout / dai_calculate_G over this rank's slice + the all-reduce + the finish; every rank
+ *                       receives the full result (G, terms, po1 / ps1 of the last sample).  All ranks must make the
+ *                       same calls in the same order (same seed and call index => same noise keys). */
+DAI_API int  dai_comm_unique_id(void* id128);
+DAI_API int  dai_comm_init(dai_handle* h, const void* id128, int rank, int world);
+DAI_API int  dai_comm_destroy(dai_handle* h);
+DAI_API int  dai_comm_info(const dai_handle* h, int* rank, int* world);
+DAI_API int  dai_rollout_sharded(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples,
+                         int calc_mean, int four, float* G, float* t0, float* t1, float* t2, float* po1, void* stream);
+DAI_API int  dai_calculate_G_sharded(dai_handle* h, const float* s0, const float* pi0, int B, int samples,
+                             float* G, float* t0, float* t1, float* t2,
+                             float* ps1, float* ps1_mean, float* ps1_logvar, float* po1, void* stream);
+
 /* ---- per-kernel timing (bench.py's roofline leg) -----------------------------------------
  * Between dai_profile_begin and dai_profile_end every decoder contraction kernel is bracketed by
  * CUDA events on its launch stream.  dai_profile_end waits for the stream and returns, per layer

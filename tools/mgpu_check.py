@@ -19,12 +19,20 @@ m = ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, device="cuda:%d" % local).load_nu
 o = torch.from_numpy(synthetic.make_frames(2, 3)).repeat_interleave(4, dim=0)
 m.set_rng(99, 0)
 G0, terms0, po0 = m.calculate_G_repeated(o, torch.eye(4).repeat(2, 1), steps=3, samples=7)
-m.enable_sample_sharding()
-m.set_rng(99, 0)
-G1, terms1, po1 = m.calculate_G_repeated(o, torch.eye(4).repeat(2, 1), steps=3, samples=7)
-ok = torch.allclose(G0, G1, rtol=1e-5, atol=1e-4) and torch.allclose(po0, po1, atol=1e-6)
-for a, b in zip(terms0, terms1):
-    ok = ok and torch.allclose(a, b, rtol=1e-5, atol=2e-3)
+s0 = torch.from_numpy(synthetic.make_frames(1, 5)).reshape(-1)[:40].reshape(4, 10)
+m.set_rng(99, 5)
+g0 = m.calculate_G(s0, torch.eye(4), samples=9)
+ok = True
+for native in (False, True):          # torch.distributed all-reduce of the returned sums / the library's own NCCL communicator
+    m.enable_sample_sharding(native=native)
+    m.set_rng(99, 0)
+    G1, terms1, po1 = m.calculate_G_repeated(o, torch.eye(4).repeat(2, 1), steps=3, samples=7)
+    ok = ok and torch.allclose(G0, G1, rtol=1e-5, atol=1e-4) and torch.allclose(po0, po1, atol=1e-6)
+    for a, b in zip(terms0, terms1):
+        ok = ok and torch.allclose(a, b, rtol=1e-5, atol=2e-3)
+    m.set_rng(99, 5)
+    g1 = m.calculate_G(s0, torch.eye(4), samples=9)
+    ok = ok and torch.allclose(g0[0], g1[0], rtol=1e-5, atol=1e-4) and torch.equal(g0[2], g1[2]) and torch.equal(g0[4], g1[4])
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if dist.get_rank() == 0:
