@@ -69,11 +69,19 @@ struct dai_handle {
     dai_config cfg{};
     int device = 0;
     std::string err;
-    std::map<std::string, std::vector<float>> raw;
+    // weights: every state_dict tensor is stored on the device as given (raw_dev, allocated once);
+    // every packed image is a RepackJob that a gather kernel rebuilds when its source tensor is dirty
+    float* raw_dev[64] = {};           // by kSpecs index
+    bool have[64] = {};
+    bool dirty[64] = {};
+    struct DevJob { int spec; uint32_t* map; size_t n; int bf16; void* dst; };
+    std::vector<DevJob> jobs;
+    bool planned = false;
     bool committed = false;
     DevWeights w{};
     TcWeights tcw{};
     std::vector<void*> wallocs;
+    uint64_t repack_launches = 0;      // of the last commit
     uint64_t seed = 1234, call = 0;
     uint64_t launches = 0, calls = 0;
     int dec_chunk = kDecChunkDefault;   // env DAI_DEC_CHUNK (tuning only)
@@ -167,125 +175,144 @@ int post_launch(dai_handle* h, const char* what) {
 
 // ---- weight repacking ----------------------------------------------------------------
 
-int upload(dai_handle* h, const std::vector<float>& v, float** out) {
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float));
-    if (e != cudaSuccess) return fail(h, DAI_E_NOMEM, "cudaMalloc(weights) failed: %s", cudaGetErrorString(e));
-    h->wallocs.push_back(p);
-    CK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
-    *out = static_cast<float*>(p);
-    return DAI_OK;
+int spec_index(const char* key) {
+    for (int i = 0; i < kNumSpecs; ++i)
+        if (strcmp(kSpecs[i].key, key) == 0) return i;
+    return -1;
 }
 
+size_t spec_elems(int i) {
+    size_t n = 1;
+    for (int d = 0; d < kSpecs[i].ndim; ++d) n *= (size_t)kSpecs[i].shape[d];
+    return n;
+}
+
+// gather maps of the CUDA-core (fp32) images; the tensor-core images are planned in dai_tc.cu (tc_plan_weights)
 // torch Linear (N,K) -> [Kpad][N]
-std::vector<float> transpose_pad(const std::vector<float>& W, int N, int K, int Kpad) {
-    std::vector<float> t((size_t)Kpad * N, 0.0f);
+std::vector<uint32_t> map_transpose_pad(int N, int K, int Kpad) {
+    std::vector<uint32_t> t((size_t)Kpad * N, REPACK_NONE);
     for (int n = 0; n < N; ++n)
-        for (int k = 0; k < K; ++k) t[(size_t)k * N + n] = W[(size_t)n * K + k];
+        for (int k = 0; k < K; ++k) t[(size_t)k * N + n] = (uint32_t)((size_t)n * K + k);
     return t;
 }
 
 // ConvTranspose2d (Cin,Cout,3,3) -> [tap][Cin][Cout]
-std::vector<float> pack_convT(const std::vector<float>& W, int Cin, int Cout) {
-    std::vector<float> p((size_t)9 * Cin * Cout);
+std::vector<uint32_t> map_convT(int Cin, int Cout) {
+    std::vector<uint32_t> p((size_t)9 * Cin * Cout);
     for (int ci = 0; ci < Cin; ++ci)
         for (int co = 0; co < Cout; ++co)
-            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = W[((size_t)ci * Cout + co) * 9 + t];
+            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = (uint32_t)(((size_t)ci * Cout + co) * 9 + t);
     return p;
 }
 
 // Conv2d (Cout,Cin,3,3) -> [tap][Cin][Cout]
-std::vector<float> pack_conv(const std::vector<float>& W, int Cout, int Cin) {
-    std::vector<float> p((size_t)9 * Cin * Cout);
+std::vector<uint32_t> map_conv(int Cout, int Cin) {
+    std::vector<uint32_t> p((size_t)9 * Cin * Cout);
     for (int co = 0; co < Cout; ++co)
         for (int ci = 0; ci < Cin; ++ci)
-            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = W[((size_t)co * Cin + ci) * 9 + t];
+            for (int t = 0; t < 9; ++t) p[((size_t)t * Cin + ci) * Cout + co] = (uint32_t)(((size_t)co * Cin + ci) * 9 + t);
     return p;
 }
 
-int commit(dai_handle* h) {
-    for (int i = 0; i < kNumSpecs; ++i)
-        if (!h->raw.count(kSpecs[i].key)) return fail(h, DAI_E_WEIGHTS, "missing weight %s", kSpecs[i].key);
-    for (void* p : h->wallocs) cudaFree(p);
-    h->wallocs.clear();
-    auto& R = h->raw;
+// Describe every packed image once per handle: device buffers + gather maps (uploaded), nothing packed yet.
+int plan_weights(dai_handle* h) {
+    std::vector<RepackJob> jobs;
     DevWeights& w = h->w;
+    auto img = [&](const char* key, std::vector<uint32_t> map, float** dst) {
+        jobs.push_back(RepackJob{key, std::move(map), 0, false, reinterpret_cast<void**>(dst)});
+    };
+    auto same = [&](const char* key, float** dst) {          // used as stored
+        jobs.push_back(RepackJob{key, {}, 0, true, reinterpret_cast<void**>(dst)});
+    };
     // Ps
-    RET(upload(h, transpose_pad(R["ps_net.0.weight"], 512, 14, 16), &w.ps_w0t));
-    RET(upload(h, R["ps_net.0.bias"], &w.ps_b0));
-    RET(upload(h, transpose_pad(R["ps_net.3.weight"], 512, 512, 512), &w.ps_w1t));
-    RET(upload(h, R["ps_net.3.bias"], &w.ps_b1));
-    RET(upload(h, transpose_pad(R["ps_net.6.weight"], 512, 512, 512), &w.ps_w2t));
-    RET(upload(h, R["ps_net.6.bias"], &w.ps_b2));
-    RET(upload(h, R["ps_net.9.weight"], &w.ps_w3));
-    RET(upload(h, R["ps_net.9.bias"], &w.ps_b3));
+    img("ps_net.0.weight", map_transpose_pad(512, 14, 16), &w.ps_w0t);   same("ps_net.0.bias", &w.ps_b0);
+    img("ps_net.3.weight", map_transpose_pad(512, 512, 512), &w.ps_w1t); same("ps_net.3.bias", &w.ps_b1);
+    img("ps_net.6.weight", map_transpose_pad(512, 512, 512), &w.ps_w2t); same("ps_net.6.bias", &w.ps_b2);
+    same("ps_net.9.weight", &w.ps_w3);                                   same("ps_net.9.bias", &w.ps_b3);
     // Po FCs
-    RET(upload(h, transpose_pad(R["po_net.0.weight"], 256, 10, 12), &w.po_w0t));
-    RET(upload(h, R["po_net.0.bias"], &w.po_b0));
-    RET(upload(h, transpose_pad(R["po_net.3.weight"], 256, 256, 256), &w.po_w1t));
-    RET(upload(h, R["po_net.3.bias"], &w.po_b1));
-    RET(upload(h, transpose_pad(R["po_net.6.weight"], 256, 256, 256), &w.po_w2t));
-    RET(upload(h, R["po_net.6.bias"], &w.po_b2));
+    img("po_net.0.weight", map_transpose_pad(256, 10, 12), &w.po_w0t);   same("po_net.0.bias", &w.po_b0);
+    img("po_net.3.weight", map_transpose_pad(256, 256, 256), &w.po_w1t); same("po_net.3.bias", &w.po_b1);
+    img("po_net.6.weight", map_transpose_pad(256, 256, 256), &w.po_w2t); same("po_net.6.bias", &w.po_b2);
     {   // FC4: reference output index e = c*256 + p (Unflatten (64,16,16)) -> NHWC column n' = p*64 + c
-        const std::vector<float>& W = R["po_net.9.weight"];
-        const std::vector<float>& b = R["po_net.9.bias"];
-        std::vector<float> t((size_t)256 * 16384), bp(16384);
+        std::vector<uint32_t> t((size_t)256 * 16384), bp(16384);
         for (int c = 0; c < 64; ++c)
             for (int p = 0; p < 256; ++p) {
                 const int e = c * 256 + p, n = p * 64 + c;
-                bp[n] = b[e];
-                for (int k = 0; k < 256; ++k) t[(size_t)k * 16384 + n] = W[(size_t)e * 256 + k];
+                bp[n] = (uint32_t)e;
+                for (int k = 0; k < 256; ++k) t[(size_t)k * 16384 + n] = (uint32_t)((size_t)e * 256 + k);
             }
-        RET(upload(h, t, &w.po_w3t));
-        RET(upload(h, bp, &w.po_b3));
+        img("po_net.9.weight", std::move(t), &w.po_w3t);
+        img("po_net.9.bias", std::move(bp), &w.po_b3);
     }
-    RET(upload(h, pack_convT(R["po_net.13.weight"], 64, 64), &w.ct1_w));
-    RET(upload(h, R["po_net.13.bias"], &w.ct1_b));
-    RET(upload(h, pack_convT(R["po_net.15.weight"], 64, 64), &w.ct2_w));
-    RET(upload(h, R["po_net.15.bias"], &w.ct2_b));
-    RET(upload(h, pack_convT(R["po_net.17.weight"], 64, 32), &w.ct3_w));
-    RET(upload(h, R["po_net.17.bias"], &w.ct3_b));
-    RET(upload(h, pack_convT(R["po_net.19.weight"], 32, 1), &w.ct4_w));
-    RET(upload(h, R["po_net.19.bias"], &w.ct4_b));
+    img("po_net.13.weight", map_convT(64, 64), &w.ct1_w); same("po_net.13.bias", &w.ct1_b);
+    img("po_net.15.weight", map_convT(64, 64), &w.ct2_w); same("po_net.15.bias", &w.ct2_b);
+    img("po_net.17.weight", map_convT(64, 32), &w.ct3_w); same("po_net.17.bias", &w.ct3_b);
+    img("po_net.19.weight", map_convT(32, 1), &w.ct4_w);  same("po_net.19.bias", &w.ct4_b);
     // Qs
-    RET(upload(h, pack_conv(R["qs_net.0.weight"], 32, 1), &w.qc1_w));
-    RET(upload(h, R["qs_net.0.bias"], &w.qc1_b));
-    RET(upload(h, pack_conv(R["qs_net.2.weight"], 32, 32), &w.qc2_w));
-    RET(upload(h, R["qs_net.2.bias"], &w.qc2_b));
-    RET(upload(h, pack_conv(R["qs_net.4.weight"], 64, 32), &w.qc3_w));
-    RET(upload(h, R["qs_net.4.bias"], &w.qc3_b));
-    RET(upload(h, pack_conv(R["qs_net.6.weight"], 64, 64), &w.qc4_w));
-    RET(upload(h, R["qs_net.6.bias"], &w.qc4_b));
+    img("qs_net.0.weight", map_conv(32, 1), &w.qc1_w);  same("qs_net.0.bias", &w.qc1_b);
+    img("qs_net.2.weight", map_conv(32, 32), &w.qc2_w); same("qs_net.2.bias", &w.qc2_b);
+    img("qs_net.4.weight", map_conv(64, 32), &w.qc3_w); same("qs_net.4.bias", &w.qc3_b);
+    img("qs_net.6.weight", map_conv(64, 64), &w.qc4_w); same("qs_net.6.bias", &w.qc4_b);
     {   // FC1: reference flatten index f = c*9 + h*3 + w -> NHWC flatten f' = (h*3+w)*64 + c
-        const std::vector<float>& W = R["qs_net.9.weight"];
-        std::vector<float> t((size_t)576 * 256);
+        std::vector<uint32_t> t((size_t)576 * 256);
         for (int n = 0; n < 256; ++n)
             for (int c = 0; c < 64; ++c)
-                for (int p = 0; p < 9; ++p) t[(size_t)(p * 64 + c) * 256 + n] = W[(size_t)n * 576 + c * 9 + p];
-        RET(upload(h, t, &w.qf0_t));
+                for (int p = 0; p < 9; ++p) t[(size_t)(p * 64 + c) * 256 + n] = (uint32_t)((size_t)n * 576 + c * 9 + p);
+        img("qs_net.9.weight", std::move(t), &w.qf0_t);
     }
-    RET(upload(h, R["qs_net.9.bias"], &w.qf0_b));
-    RET(upload(h, transpose_pad(R["qs_net.12.weight"], 256, 256, 256), &w.qf1_t));
-    RET(upload(h, R["qs_net.12.bias"], &w.qf1_b));
-    RET(upload(h, transpose_pad(R["qs_net.15.weight"], 256, 256, 256), &w.qf2_t));
-    RET(upload(h, R["qs_net.15.bias"], &w.qf2_b));
-    RET(upload(h, R["qs_net.18.weight"], &w.qf3));
-    RET(upload(h, R["qs_net.18.bias"], &w.qf3_b));
+    same("qs_net.9.bias", &w.qf0_b);
+    img("qs_net.12.weight", map_transpose_pad(256, 256, 256), &w.qf1_t); same("qs_net.12.bias", &w.qf1_b);
+    img("qs_net.15.weight", map_transpose_pad(256, 256, 256), &w.qf2_t); same("qs_net.15.bias", &w.qf2_b);
+    same("qs_net.18.weight", &w.qf3);                                    same("qs_net.18.bias", &w.qf3_b);
     // Qpi
-    RET(upload(h, transpose_pad(R["qpi_net.0.weight"], 128, 10, 12), &w.pi_w0t));
-    RET(upload(h, R["qpi_net.0.bias"], &w.pi_b0));
-    RET(upload(h, transpose_pad(R["qpi_net.2.weight"], 128, 128, 128), &w.pi_w1t));
-    RET(upload(h, R["qpi_net.2.bias"], &w.pi_b1));
-    RET(upload(h, R["qpi_net.4.weight"], &w.pi_w2));
-    RET(upload(h, R["qpi_net.4.bias"], &w.pi_b2));
-    // tensor-core operand planes (bf16 hi/lo, K-major) for the contraction layers
-    {
-        std::vector<void*> extra;
-        std::string terr;
-        const int rc = tc_pack_weights(R, &h->tcw, &extra, &terr);
-        for (void* p : extra) h->wallocs.push_back(p);
-        if (rc != 0) return fail(h, DAI_E_CUDA, "tensor-core weight packing failed: %s", terr.c_str());
+    img("qpi_net.0.weight", map_transpose_pad(128, 10, 12), &w.pi_w0t);   same("qpi_net.0.bias", &w.pi_b0);
+    img("qpi_net.2.weight", map_transpose_pad(128, 128, 128), &w.pi_w1t); same("qpi_net.2.bias", &w.pi_b1);
+    same("qpi_net.4.weight", &w.pi_w2);                                   same("qpi_net.4.bias", &w.pi_b2);
+    // tensor-core operand images (bf16 hi/lo, K-major)
+    std::string terr;
+    if (tc_plan_weights(&h->tcw, &jobs, &terr) != 0) return fail(h, DAI_E_CUDA, "tensor-core weight planning failed: %s", terr.c_str());
+    // device side: buffers + maps
+    for (RepackJob& j : jobs) {
+        const int si = spec_index(j.key.c_str());
+        if (si < 0) return fail(h, DAI_E_INVALID, "internal: repack job for unknown key %s", j.key.c_str());
+        if (j.alias) { *j.dst = h->raw_dev[si]; continue; }
+        const size_t n = j.map.size();
+        void *dmap = nullptr, *ddst = nullptr;
+        if (cudaMalloc(&dmap, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&ddst, std::max<size_t>(n * (j.bf16 ? 2 : 4), 16)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, DAI_E_NOMEM, "cudaMalloc(packed weights for %s) failed", j.key.c_str());
+        }
+        h->wallocs.push_back(dmap); h->wallocs.push_back(ddst);
+        CK(cudaMemcpy(dmap, j.map.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        *j.dst = ddst;
+        h->jobs.push_back(dai_handle::DevJob{si, static_cast<uint32_t*>(dmap), n, j.bf16, ddst});
     }
+    h->planned = true;
+    return DAI_OK;
+}
+
+// Re-pack the images of every dirty tensor on `st` (one gather kernel per image; nothing leaves the device except the
+// 288 floats of po_net.19.weight, which travel as a kernel parameter of ct3).
+int commit(dai_handle* h, cudaStream_t st) {
+    for (int i = 0; i < kNumSpecs; ++i)
+        if (!h->have[i]) return fail(h, DAI_E_WEIGHTS, "missing weight %s", kSpecs[i].key);
+    if (!h->planned) {
+        RET(plan_weights(h));
+        for (int i = 0; i < kNumSpecs; ++i) h->dirty[i] = true;
+    }
+    h->repack_launches = 0;
+    for (const dai_handle::DevJob& j : h->jobs)
+        if (h->dirty[j.spec]) h->repack_launches += launch_repack(h->raw_dev[j.spec], j.map, j.n, j.bf16, j.dst, st);
+    h->launches += h->repack_launches;
+    RET(post_launch(h, "weight repack"));
+    const int i19 = spec_index("po_net.19.weight");
+    if (h->dirty[i19]) {
+        float w19[288];
+        CK(cudaMemcpyAsync(w19, h->raw_dev[i19], sizeof(w19), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tc_set_w4(&h->tcw, w19);
+    }
+    for (int i = 0; i < kNumSpecs; ++i) h->dirty[i] = false;
     h->committed = true;
     return DAI_OK;
 }
@@ -628,6 +655,7 @@ int dai_destroy(dai_handle* h) {
                       &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag, &h->plan_tree, &h->plan_picks, &h->plan_rows, &h->plan_out, &h->plan_pi0};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (void* p : h->wallocs) cudaFree(p);
+    for (float* p : h->raw_dev) if (p) cudaFree(p);
     tc_release(&h->tcw);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->plan_stop_host) cudaFreeHost(h->plan_stop_host);
@@ -639,33 +667,42 @@ int dai_destroy(dai_handle* h) {
 
 const char* dai_last_error(const dai_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-int dai_set_weight(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+static int set_weight_impl(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim, cudaStream_t st, bool wait) {
     if (!h || !key || !data || !shape) return DAI_E_INVALID;
-    for (int i = 0; i < kNumSpecs; ++i) {
-        if (strcmp(kSpecs[i].key, key) != 0) continue;
-        if (ndim != kSpecs[i].ndim) return fail(h, DAI_E_INVALID, "%s: ndim %d, expected %d", key, ndim, kSpecs[i].ndim);
-        size_t n = 1;
-        for (int d = 0; d < ndim; ++d) {
-            if (shape[d] != kSpecs[i].shape[d])
-                return fail(h, DAI_E_INVALID, "%s: dim %d is %lld, expected %lld", key, d, (long long)shape[d],
-                            (long long)kSpecs[i].shape[d]);
-            n *= (size_t)shape[d];
-        }
-        CK(cudaSetDevice(h->device));
-        std::vector<float>& v = h->raw[key];
-        v.resize(n);
-        CK(cudaMemcpy(v.data(), data, n * sizeof(float), cudaMemcpyDefault));
-        h->committed = false;
-        return DAI_OK;
+    const int i = spec_index(key);
+    if (i < 0) return fail(h, DAI_E_INVALID, "unknown weight key %s", key);
+    if (ndim != kSpecs[i].ndim) return fail(h, DAI_E_INVALID, "%s: ndim %d, expected %d", key, ndim, kSpecs[i].ndim);
+    for (int d = 0; d < ndim; ++d)
+        if (shape[d] != kSpecs[i].shape[d])
+            return fail(h, DAI_E_INVALID, "%s: dim %d is %lld, expected %lld", key, d, (long long)shape[d], (long long)kSpecs[i].shape[d]);
+    CK(cudaSetDevice(h->device));
+    const size_t n = spec_elems(i);
+    if (!h->raw_dev[i]) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 4) * sizeof(float));
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(h, DAI_E_NOMEM, "cudaMalloc(%s) failed: %s", key, cudaGetErrorString(e)); }
+        h->raw_dev[i] = static_cast<float*>(p);
     }
-    return fail(h, DAI_E_INVALID, "unknown weight key %s", key);
+    // host or device source (UVA): a device tensor never leaves the device
+    CK(cudaMemcpyAsync(h->raw_dev[i], data, n * sizeof(float), cudaMemcpyDefault, st));
+    if (wait) CK(cudaStreamSynchronize(st));
+    h->have[i] = true; h->dirty[i] = true;
+    h->committed = false;
+    return DAI_OK;
+}
+
+int dai_set_weight(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+    return set_weight_impl(h, key, data, shape, ndim, nullptr, true);
+}
+
+int dai_set_weight_async(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+    return set_weight_impl(h, key, data, shape, ndim, (cudaStream_t)stream, false);
 }
 
 int dai_commit_weights(dai_handle* h, void* stream) {
     if (!h) return DAI_E_INVALID;
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize((cudaStream_t)stream));
-    return commit(h);
+    return commit(h, (cudaStream_t)stream);
 }
 
 int dai_set_rng(dai_handle* h, uint64_t seed, uint64_t call_index) {
@@ -704,6 +741,7 @@ int dai_get_stats(dai_handle* h, dai_stats* out, int reset) {
                       &h->traj, &h->root, &h->stage_in, &h->stage_out, &h->scratch, &h->sprites, &h->sprite_stage, &h->frame_flag, &h->plan_tree, &h->plan_picks, &h->plan_rows, &h->plan_out, &h->plan_pi0};
     for (DevBuf* b : bufs) total += b->cap;
     out->workspace_bytes = total;
+    out->repack_launches = h->repack_launches;
     if (reset) { h->launches = 0; h->calls = 0; }
     return DAI_OK;
 }

@@ -2,6 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <string>
+#include <vector>
+
 #include "dai_common.cuh"
 
 namespace dai {
@@ -23,6 +27,20 @@ struct DevWeights {
     // Qpi: 10->128->128->4 (:19-25)
     float *pi_w0t, *pi_b0, *pi_w1t, *pi_b1, *pi_w2, *pi_b2;
 };
+
+// ---- weight repacking on the device --------------------------------------
+// Every packed weight image is described by a gather map over its destination elements: map[i] = index of the fp32
+// source element of the state_dict tensor `key` (REPACK_LO set: the bf16 lo part of it; REPACK_NONE: zero padding).
+// bf16 = 1: the image is bf16 (hi = rn(x), lo = rn(x - hi)); 0: fp32.  alias: no image, *dst = the stored tensor itself.
+constexpr uint32_t REPACK_LO = 0x80000000u, REPACK_NONE = 0xffffffffu;
+struct RepackJob {
+    std::string key;
+    std::vector<uint32_t> map;
+    int bf16;
+    bool alias;
+    void** dst;
+};
+int  launch_repack(const float* src, const uint32_t* map, size_t n, int bf16, void* dst, cudaStream_t st);
 
 // ---- transition net ------------------------------------------------------------------
 struct PsArgs {

@@ -1348,4 +1348,26 @@ int launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st) {
     return 1;
 }
 
+// ---- weight repacking: gather from the stored fp32 tensor through a destination-indexed map ----
+__global__ void __launch_bounds__(256) k_repack(const float* __restrict__ src, const uint32_t* __restrict__ map, size_t n, int bf16,
+                                                void* __restrict__ dst) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = __ldg(map + i);
+        const float v = m == REPACK_NONE ? 0.0f : __ldg(src + (m & ~REPACK_LO));
+        if (!bf16) {
+            static_cast<float*>(dst)[i] = v;
+        } else {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            static_cast<__nv_bfloat16*>(dst)[i] = (m & REPACK_LO) && m != REPACK_NONE ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+        }
+    }
+}
+
+int launch_repack(const float* src, const uint32_t* map, size_t n, int bf16, void* dst, cudaStream_t st) {
+    if (n == 0) return 0;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_repack<<<blocks, 256, 0, st>>>(src, map, n, bf16, dst);
+    return 1;
+}
+
 }  // namespace dai

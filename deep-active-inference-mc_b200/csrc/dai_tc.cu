@@ -858,45 +858,29 @@ struct TcImpl {
     bool attrs_set = false;
 };
 
-inline uint16_t f2bf(float v) {
-    uint32_t u;
-    memcpy(&u, &v, 4);
-    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
-    u += 0x7fffu + ((u >> 16) & 1u);          // round to nearest even
-    return (uint16_t)(u >> 16);
-}
-inline float bf2f(uint16_t b) {
-    uint32_t u = (uint32_t)b << 16;
-    float v;
-    memcpy(&v, &u, 4);
-    return v;
-}
-
 struct Sub { int kh, kw; };
 
-// One weight block = [plane hi|lo][kc 8][n][8] bf16 with n = sub * Cout + co, K = Cin = 64:
-// the UMMA no-swizzle K-major layout of a (n x 64) operand.  ConvTranspose2d weight is (Cin,Cout,3,3).
 // One weight block = [plane hi|lo][kc Cin/8][n][8] bf16 with n = sub * Cout + co: the UMMA no-swizzle K-major layout
 // of an (n x Cin) operand (concat: [kc][2n rows: hi rows then lo rows][8]).  ConvTranspose2d weights are
 // (Cin,Cout,3,3), Conv2d weights (Cout,Cin,3,3).
-void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs, int nsub, uint16_t* dst, bool concat,
-                bool conv_layout) {
+// Packing is described, not performed, on the host: dst[i] holds the index of the fp32 source element that bf16
+// element i of the packed image is made from (REPACK_LO set: its lo part), and a gather kernel (k_repack, dai_simt.cu)
+// builds the image on the device whenever that weight tensor changes.
+void map_block(int Cin, int Cout, const Sub* subs, int nsub, uint32_t* dst, bool concat, bool conv_layout) {
     const int n = nsub * Cout, KC = Cin / 8;
     for (int s = 0; s < nsub; ++s)
         for (int co = 0; co < Cout; ++co)
             for (int ci = 0; ci < Cin; ++ci) {
-                const size_t wi = conv_layout ? (((size_t)co * Cin + ci) * 3 + subs[s].kh) * 3 + subs[s].kw
-                                              : (((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw;
-                const float v = W[wi];
-                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                const uint32_t wi = (uint32_t)(conv_layout ? (((size_t)co * Cin + ci) * 3 + subs[s].kh) * 3 + subs[s].kw
+                                                           : (((size_t)ci * Cout + co) * 3 + subs[s].kh) * 3 + subs[s].kw);
                 const int nn = s * Cout + co, kc = ci >> 3, e = ci & 7;
                 if (concat) {
-                    dst[((size_t)kc * 2 * n + nn) * 8 + e] = hi;
-                    dst[((size_t)kc * 2 * n + n + nn) * 8 + e] = lo;
+                    dst[((size_t)kc * 2 * n + nn) * 8 + e] = wi;
+                    dst[((size_t)kc * 2 * n + n + nn) * 8 + e] = wi | REPACK_LO;
                 } else {
                     const size_t o = ((size_t)kc * n + nn) * 8 + e;
-                    dst[o] = hi;
-                    dst[(size_t)KC * n * 8 + o] = lo;
+                    dst[o] = wi;
+                    dst[(size_t)KC * n * 8 + o] = wi | REPACK_LO;
                 }
             }
 }
@@ -905,9 +889,9 @@ void pack_block(const std::vector<float>& W, int Cin, int Cout, const Sub* subs,
 // (y+dy, x+dx) with kh = 1 (py = 0); kh = 0 for dy = 1 and kh = 2 for dy = 0 (py = 1); same in x.
 inline int k_of(int parity, int d) { return parity == 0 ? 1 : (d == 1 ? 0 : 2); }
 
-int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool grouped, bool concat, LayerPack* lp,
-                std::vector<void*>* allocs, std::string* err) {
-    std::vector<uint16_t> host((size_t)9 * Cout * Cin * 2);   // 9 taps * Cout * Cin * 2 planes
+int build_layer(const char* key, int mode, int Cin, int Cout, bool grouped, bool concat, LayerPack* lp,
+                std::vector<RepackJob>* jobs) {
+    std::vector<uint32_t> host((size_t)9 * Cout * Cin * 2, REPACK_NONE);   // 9 taps * Cout * Cin * 2 planes
     const int KC = Cin / 8;
     int nu = 0;
     size_t off = 0;                                            // in uint16 elements
@@ -916,7 +900,7 @@ int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool g
         u.oy = (int16_t)oy; u.ox = (int16_t)ox; u.col = (int16_t)col; u.n = (int16_t)(nsub * Cout); u.init = (int16_t)init;
         u.kc0 = (int16_t)kc0;
         u.woff = (int32_t)(off * 2);
-        pack_block(W, Cin, Cout, subs, nsub, host.data() + off, concat, mode == 2);
+        map_block(Cin, Cout, subs, nsub, host.data() + off, concat, mode == 2);
         off += (size_t)nsub * Cout * Cin * 2;
     };
     if (mode == 0) {
@@ -956,11 +940,7 @@ int build_layer(const std::vector<float>& W, int mode, int Cin, int Cout, bool g
         add(1, 1, 2 * Cout, g11, 1, 0, 0);
     }
     lp->nunits = nu;
-    void* d = nullptr;
-    if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(tc weights)"; return -1; }
-    allocs->push_back(d);
-    if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(tc weights)"; return -1; }
-    lp->wpack = static_cast<uint8_t*>(d);
+    jobs->push_back(RepackJob{key, std::move(host), 1, false, reinterpret_cast<void**>(&lp->wpack)});
     return 0;
 }
 
@@ -1075,37 +1055,26 @@ int tc_from_blocked(const void* blocked, int rows, int hw, int C, float* nhwc, c
 
 namespace {
 // torch Linear weight (N,K) -> [n_tile = N/NT][k_chunk = K/64] blocks of [plane hi|lo][kc 8][NT][8] bf16.
-// kperm (optional) maps the GEMM's k index to the reference's input index.
-int pack_dense(TcImpl* im, int which, const std::vector<float>& W, const std::vector<float>& bias, int N, int K, const int* kperm,
-               std::vector<void*>* allocs, std::string* err, int NT = 128) {
+// src(n, k) = index of the source element for GEMM column n, contraction index k.
+template <class F>
+void plan_dense(TcImpl* im, int which, const char* wkey, const char* bkey, int N, int K, F src, std::vector<RepackJob>* jobs, int NT = 128) {
     const int ntn = N / NT, kch = K / 64;
     const size_t blk = (size_t)2 * 8 * NT * 8;               // elements per block
-    std::vector<uint16_t> host((size_t)ntn * kch * blk);
+    std::vector<uint32_t> host((size_t)ntn * kch * blk, REPACK_NONE);
     for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) {
-            const float v = W[(size_t)n * K + (kperm ? kperm[k] : k)];
-            const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+            const uint32_t wi = (uint32_t)src(n, k);
             const size_t o = ((size_t)(n / NT) * kch + k / 64) * blk + ((size_t)((k >> 3) & 7) * NT + (n % NT)) * 8 + (k & 7);
-            host[o] = hi;
-            host[o + (size_t)8 * NT * 8] = lo;
+            host[o] = wi;
+            host[o + (size_t)8 * NT * 8] = wi | REPACK_LO;
         }
-    void* d = nullptr;
-    if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(dense weights)"; return -1; }
-    allocs->push_back(d);
-    if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(dense weights)"; return -1; }
-    void* db = nullptr;
-    if (cudaMalloc(&db, (size_t)N * 4) != cudaSuccess) { *err = "cudaMalloc(dense bias)"; return -1; }
-    allocs->push_back(db);
-    if (cudaMemcpy(db, bias.data(), (size_t)N * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(dense bias)"; return -1; }
-    im->dense_w[which] = static_cast<uint8_t*>(d);
-    im->dense_b[which] = static_cast<float*>(db);
+    jobs->push_back(RepackJob{wkey, std::move(host), 1, false, reinterpret_cast<void**>(&im->dense_w[which])});
+    jobs->push_back(RepackJob{bkey, {}, 0, true, reinterpret_cast<void**>(&im->dense_b[which])});     // the bias is used as stored
     im->dense_k[which] = K; im->dense_n[which] = N;
-    return 0;
 }
 }  // namespace
 
-int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
-                    std::string* err) {
+int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* err) {
     TcImpl* im = static_cast<TcImpl*>(out->impl);
     if (!im) { im = new TcImpl(); out->impl = im; }
     if (!im->encode) {
@@ -1131,67 +1100,55 @@ int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeig
         }
         im->attrs_set = true;
     }
-    if (build_layer(raw.at("po_net.13.weight"), 0, 64, 64, false, CfgCt1::CONCAT, &im->ct1, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("po_net.15.weight"), 1, 64, 64, true, CfgCt2::CONCAT, &im->ct2, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("po_net.17.weight"), 1, 64, 32, true, CfgCt3::CONCAT, &im->ct3, allocs, err) != 0) return -1;
+    build_layer("po_net.13.weight", 0, 64, 64, false, CfgCt1::CONCAT, &im->ct1, jobs);
+    build_layer("po_net.15.weight", 1, 64, 64, true, CfgCt2::CONCAT, &im->ct2, jobs);
+    build_layer("po_net.17.weight", 1, 64, 32, true, CfgCt3::CONCAT, &im->ct3, jobs);
     {
-        const char* keys[7] = {"ps_net.3", "ps_net.6", "po_net.3", "po_net.6", "qs_net.9", "qs_net.12", "qs_net.15"};
+        static const std::string wk[7] = {"ps_net.3.weight", "ps_net.6.weight", "po_net.3.weight", "po_net.6.weight", "qs_net.9.weight",
+                                          "qs_net.12.weight", "qs_net.15.weight"};
+        static const std::string bk[7] = {"ps_net.3.bias", "ps_net.6.bias", "po_net.3.bias", "po_net.6.bias", "qs_net.9.bias",
+                                          "qs_net.12.bias", "qs_net.15.bias"};
         const int N[7] = {512, 512, 256, 256, 256, 256, 256}, K[7] = {512, 512, 256, 256, 576, 256, 256};
-        std::vector<int> perm(576);          // encoder FC1: GEMM k = pixel*64 + c (NHWC flatten) <- reference c*9 + pixel
-        for (int px = 0; px < 9; ++px)
-            for (int c = 0; c < 64; ++c) perm[px * 64 + c] = c * 9 + px;
-        for (int i = 0; i < 7; ++i)
-            if (pack_dense(im, i, raw.at(std::string(keys[i]) + ".weight"), raw.at(std::string(keys[i]) + ".bias"), N[i], K[i],
-                           i == TC_QS0 ? perm.data() : nullptr, allocs, err) != 0)
-                return -1;
+        for (int i = 0; i < 7; ++i) {
+            const int Ki = K[i];
+            if (i == TC_QS0)      // encoder FC1: GEMM k = pixel*64 + c (NHWC flatten) <- reference c*9 + pixel
+                plan_dense(im, i, wk[i].c_str(), bk[i].c_str(), N[i], Ki, [Ki](int n, int k) { return (size_t)n * Ki + (size_t)(k & 63) * 9 + (k >> 6); }, jobs);
+            else
+                plan_dense(im, i, wk[i].c_str(), bk[i].c_str(), N[i], Ki, [Ki](int n, int k) { return (size_t)n * Ki + k; }, jobs);
+        }
     }
-    {   // encoder conv4 (Conv2d 64->64, k3 s2, 7x7 -> 3x3) as a GEMM over im2col rows: B[n = co][k = (kh*3+kw)*64 + ci]
-        const std::vector<float>& W = raw.at("qs_net.6.weight");          // (Cout, Cin, 3, 3)
-        std::vector<float> B((size_t)64 * 576);
-        for (int co = 0; co < 64; ++co)
-            for (int ci = 0; ci < 64; ++ci)
-                for (int t = 0; t < 9; ++t) B[(size_t)co * 576 + t * 64 + ci] = W[((size_t)co * 64 + ci) * 9 + t];
-        if (pack_dense(im, TC_QC4, B, raw.at("qs_net.6.bias"), 64, 576, nullptr, allocs, err, 64) != 0) return -1;
-    }
-    if (build_layer(raw.at("qs_net.2.weight"), 2, 32, 32, false, false, &im->qc2, allocs, err) != 0) return -1;
-    if (build_layer(raw.at("qs_net.4.weight"), 2, 32, 64, false, false, &im->qc3, allocs, err) != 0) return -1;
-    {   // FC4 (16384, 256): reference row e = c*256 + p -> NHWC column n' = p*64 + c; blocks [n_tile][k_chunk]
-        // of [plane][kc 8][256 n][8]
-        const std::vector<float>& W = raw.at("po_net.9.weight");
-        std::vector<uint16_t> host((size_t)16384 * 256 * 2);
-        std::vector<float> bias_tc(16384);
-        const std::vector<float>& braw = raw.at("po_net.9.bias");
+    // encoder conv4 (Conv2d 64->64, k3 s2, 7x7 -> 3x3) as a GEMM over im2col rows: B[n = co][k = (kh*3+kw)*64 + ci] = W[co][ci][tap]
+    plan_dense(im, TC_QC4, "qs_net.6.weight", "qs_net.6.bias", 64, 576,
+               [](int co, int k) { return ((size_t)co * 64 + (k & 63)) * 9 + (k >> 6); }, jobs, 64);
+    build_layer("qs_net.2.weight", 2, 32, 32, false, false, &im->qc2, jobs);
+    build_layer("qs_net.4.weight", 2, 32, 64, false, false, &im->qc3, jobs);
+    {   // FC4 (16384, 256): reference row e = c*256 + p -> column n = ((pg*8 + kc)*4 + pl)*8 + ce for pixel 4*pg + pl,
+        // channel 8*kc + ce; blocks [n_tile][k_chunk] of [plane][kc 8][256 n][8]
+        std::vector<uint32_t> host((size_t)16384 * 256 * 2, REPACK_NONE), bias((size_t)16384);
         for (int n = 0; n < 16384; ++n) {
-            // column n = ((pg*8 + kc)*4 + pl)*8 + ce  <->  pixel px = 4*pg + pl, channel c = 8*kc + ce
             const int ce = n & 7, pl = (n >> 3) & 3, kc8 = (n >> 5) & 7, pg = n >> 8;
             const int px = pg * 4 + pl, c = kc8 * 8 + ce, e = c * 256 + px;
-            bias_tc[n] = braw[e];
+            bias[n] = (uint32_t)e;
             const int nt = n >> 8, nl = n & 255;
             for (int k = 0; k < 256; ++k) {
-                const float v = W[(size_t)e * 256 + k];
-                const uint16_t hi = f2bf(v), lo = f2bf(v - bf2f(hi));
+                const uint32_t wi = (uint32_t)((size_t)e * 256 + k);
                 const int kch = k >> 6, kc = (k >> 3) & 7, ke = k & 7;
                 const size_t blk = ((size_t)nt * 4 + kch) * ((DenseCfg<256, EPI_FC4>::B_BYTES / 2));
                 const size_t o = blk + ((size_t)kc * 256 + nl) * 8 + ke;
-                host[o] = hi;
-                host[o + (size_t)8 * 256 * 8] = lo;
+                host[o] = wi;
+                host[o + (size_t)8 * 256 * 8] = wi | REPACK_LO;
             }
         }
-        void* d = nullptr;
-        if (cudaMalloc(&d, host.size() * 2) != cudaSuccess) { *err = "cudaMalloc(fc4 weights)"; return -1; }
-        allocs->push_back(d);
-        if (cudaMemcpy(d, host.data(), host.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(fc4 weights)"; return -1; }
-        im->fc4_wpack = static_cast<uint8_t*>(d);
-        void* db = nullptr;
-        if (cudaMalloc(&db, 16384 * 4) != cudaSuccess) { *err = "cudaMalloc(fc4 bias)"; return -1; }
-        allocs->push_back(db);
-        if (cudaMemcpy(db, bias_tc.data(), 16384 * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *err = "cudaMemcpy(fc4 bias)"; return -1; }
-        im->fc4_bias = static_cast<float*>(db);
+        jobs->push_back(RepackJob{"po_net.9.weight", std::move(host), 1, false, reinterpret_cast<void**>(&im->fc4_wpack)});
+        jobs->push_back(RepackJob{"po_net.9.bias", std::move(bias), 0, false, reinterpret_cast<void**>(&im->fc4_bias)});
     }
-    const std::vector<float>& w19 = raw.at("po_net.19.weight");     // (Cin 32, Cout 1, 3, 3)
-    for (int c = 0; c < 32; ++c)
-        for (int t = 0; t < 9; ++t) im->w4[c * 9 + t] = w19[(size_t)c * 9 + t];
     return 0;
+}
+
+// po_net.19.weight (Cin 32, Cout 1, 3, 3) = [c][tap]: travels as a kernel parameter of ct3 (constant bank)
+void tc_set_w4(TcWeights* w, const float* w19) {
+    TcImpl* im = static_cast<TcImpl*>(w->impl);
+    if (im) memcpy(im->w4, w19, sizeof(im->w4));
 }
 
 void tc_release(TcWeights* w) {

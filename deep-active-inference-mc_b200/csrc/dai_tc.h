@@ -14,10 +14,11 @@ struct TcWeights {
     void* impl = nullptr;   // opaque (dai_tc.cu)
 };
 
-// Builds the bf16 hi/lo K-major operand planes + TMA descriptors from the raw state_dict.
-// Device allocations are appended to *allocs (owned by the handle).  Returns 0 or -1 (+ *err).
-int tc_pack_weights(const std::map<std::string, std::vector<float>>& raw, TcWeights* out, std::vector<void*>* allocs,
-                    std::string* err);
+// Plans the bf16 hi/lo K-major operand images of the contraction layers: appends one RepackJob per packed image
+// (dai_kernels.h) whose `dst` is the pointer inside the opaque TcImpl that the image's device address must be stored in.
+// Nothing is packed on the host; the handle runs the jobs on the device whenever their source tensor changes.
+int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* err);
+void tc_set_w4(TcWeights* w, const float* w19_host);     // po_net.19.weight, 288 floats
 void tc_release(TcWeights* w);
 
 // FC4 -> ct1 -> ct2 -> ct3 -> pixel terms for one chunk of decoder rows on the tensor cores.

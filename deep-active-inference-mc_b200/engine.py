@@ -40,7 +40,8 @@ class DaiMctsResult(ctypes.Structure):
 
 
 class DaiStats(ctypes.Structure):
-    _fields_ = [("kernel_launches", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64)]
+    _fields_ = [("kernel_launches", ctypes.c_uint64), ("calls", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64),
+                ("repack_launches", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/dai_b200.h declares
@@ -50,6 +51,7 @@ SIGNATURES = {
     "dai_last_error": (ctypes.c_char_p, [_vp]),
     "dai_version": (ctypes.c_char_p, []),
     "dai_set_weight": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "dai_set_weight_async": (ctypes.c_int, [_vp, ctypes.c_char_p, _vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, _vp]),
     "dai_commit_weights": (ctypes.c_int, [_vp, _vp]),
     "dai_set_rng": (ctypes.c_int, [_vp, ctypes.c_uint64, ctypes.c_uint64]),
     "dai_get_rng": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
@@ -174,15 +176,21 @@ class Engine:
 
     # ------------------------------------------------------------------ state
     def set_weights(self, state):
-        """state: {key: tensor / ndarray} with the 46 state_dict keys."""
-        for key, val in state.items():
-            t = torch.as_tensor(val).detach().to(torch.float32).contiguous()
-            shape = (ctypes.c_int64 * t.dim())(*t.shape)
-            with torch.cuda.device(self.device):
+        """state: {key: tensor / ndarray} — all 46 state_dict keys the first time, afterwards any subset (the tensors
+        that changed).  Device tensors are copied device-to-device on the current stream, host tensors through the
+        blocking entry point; the commit re-packs only the images of the tensors given (on the device, same stream)."""
+        st = self._stream()
+        with torch.cuda.device(self.device):
+            for key, val in state.items():
+                t = torch.as_tensor(val).detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.to(torch.float32).contiguous()
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
                 if t.is_cuda:
-                    torch.cuda.current_stream(self.device).synchronize()
-                self._ck(self.lib.dai_set_weight(self.h, key.encode(), _p(t), shape, t.dim()))
-        self._ck(self.lib.dai_commit_weights(self.h, self._stream()))
+                    self._ck(self.lib.dai_set_weight_async(self.h, key.encode(), _p(t), shape, t.dim(), st))
+                else:
+                    self._ck(self.lib.dai_set_weight(self.h, key.encode(), _p(t), shape, t.dim()))
+            self._ck(self.lib.dai_commit_weights(self.h, st))
 
     def set_rng(self, seed, call=0):
         self._ck(self.lib.dai_set_rng(self.h, int(seed), int(call)))
@@ -201,7 +209,8 @@ class Engine:
     def stats(self, reset=False):
         s = DaiStats()
         self._ck(self.lib.dai_get_stats(self.h, ctypes.byref(s), 1 if reset else 0))
-        return {"kernel_launches": s.kernel_launches, "calls": s.calls, "workspace_bytes": s.workspace_bytes}
+        return {"kernel_launches": s.kernel_launches, "calls": s.calls, "workspace_bytes": s.workspace_bytes,
+                "repack_launches": s.repack_launches}
 
     # ------------------------------------------------------------------ nets
     def encode(self, o, sample=False):

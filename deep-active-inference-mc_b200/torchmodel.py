@@ -140,6 +140,7 @@ class ActiveInferenceModel:
         self.host_results = True
         self._versions = None
         self._plist = None
+        self._train_flag = None
         self._group = None          # torch.distributed group for MC-sample sharding
         self._native_comm = False   # True: the C ABI owns the all-reduce (dai_comm_init)
         self._engine.set_rng(seed, 0)
@@ -152,21 +153,44 @@ class ActiveInferenceModel:
                 raise DaiError("the model lives on %s (one engine handle per device); construct it with device=%s" % (self.device, d))
         return self
 
-    def _params(self):
+    def _entries(self):
+        """[(state_dict key, owning module, parameter name)] — resolved once; the Parameter itself is looked up at
+        every sync, so a parameter that is REPLACED (module.weight = nn.Parameter(...)) is seen like one that is
+        updated in place."""
         if self._plist is None:
-            self._plist = [(name, p) for m in (self.model_top, self.model_mid, self.model_down)
-                           for name, p in m.state_dict(keep_vars=True).items()]
+            self._plist = []
+            for m in (self.model_top, self.model_mid, self.model_down):
+                for name, _ in m.named_parameters():
+                    mod_path, _, pname = name.rpartition(".")
+                    self._plist.append((name, m.get_submodule(mod_path), pname))
         return self._plist
 
     def _sync(self):
-        """Re-pack the engine's weights when any parameter changed (optimizer step, load_state_dict)."""
-        v = tuple((p.data_ptr(), p._version) for _, p in self._params())
-        train = (self.model_mid.training, self.model_down.training)
-        if v != self._versions:
-            self._engine.set_weights({name: p.detach() for name, p in self._params()})
-            self._versions = v
-        # nn.Dropout follows module.training: the reference never leaves train mode (SURVEY.md §0 fact 4)
-        self._engine.set_training(all(train))
+        """Bring the engine's packed weights up to date: 46 (identity, version) reads when nothing changed (a few
+        microseconds, no tensor work); otherwise ONLY the changed tensors are handed over (device-to-device) and only
+        their packed images are rebuilt, on the device (dai_set_weight_async + dai_commit_weights)."""
+        sig = self._versions
+        dirty = None
+        for i, (key, mod, pname) in enumerate(self._entries()):
+            p = mod._parameters[pname]
+            cur = (id(p), p._version, p.data_ptr())
+            if sig is None or sig[i] != cur:
+                if dirty is None:
+                    dirty = {}
+                    sig = list(sig) if sig is not None else [None] * len(self._plist)
+                dirty[key] = p.detach()
+                sig[i] = cur
+        if dirty is not None:
+            self._engine.set_weights(dirty)
+            self._versions = sig
+        # nn.Dropout follows module.training; the reference never leaves train mode (SURVEY.md §0 fact 4).  One flag
+        # serves the whole handle, so a call with the nets in different modes is refused instead of silently wrong.
+        train = self.model_down.training
+        if self.model_mid.training != train:
+            raise DaiError("model_mid and model_down are in different train/eval modes; the engine applies one mode to all dropout sites")
+        if train != self._train_flag:
+            self._engine.set_training(train)
+            self._train_flag = train
 
     def load_numpy_weights(self, weights):
         """Load {state_dict key: ndarray} (synthetic.make_weights) into the three modules."""

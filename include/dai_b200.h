@@ -65,6 +65,7 @@ typedef struct dai_stats {
     uint64_t kernel_launches; /* kernels of this library launched since the last reset */
     uint64_t calls;           /* compute entry points served                           */
     uint64_t workspace_bytes; /* device bytes currently held by the handle             */
+    uint64_t repack_launches; /* gather kernels of the last dai_commit_weights         */
 } dai_stats;
 
 DAI_API int  dai_create(const dai_config* cfg, int device, dai_handle** out);
@@ -75,9 +76,18 @@ DAI_API const char* dai_version(void);
 /* ---- weights: the 46 state_dict tensors of model_top / model_mid / model_down
  *      (src/torchmodel.py:167-177 checkpoint keys, e.g. "po_net.9.weight"); torch layouts
  *      (Linear (out,in); Conv2d (Cout,Cin,3,3); ConvTranspose2d (Cin,Cout,3,3)).
- *      `data` may be a host or a device pointer.  dai_commit_weights repacks (transposes,
- *      NHWC permutations, bf16 hi/lo split) and must be called before any compute call. */
+ *      `data` may be a host or a device pointer; the tensor is copied into the handle's own device
+ *      copy (a device source never leaves the device) and marked dirty.  dai_set_weight waits for
+ *      the copy; dai_set_weight_async enqueues it on `stream` (the source must stay valid until
+ *      the stream reaches it; pass the stream that produced it, e.g. the optimizer's).
+ *      dai_commit_weights re-packs — on the device, on `stream`, one gather kernel per packed
+ *      image (transposes, NHWC permutations, tensor-core K-major bf16 hi/lo images) — ONLY the
+ *      images of tensors set since the last commit, and must be called before the next compute
+ *      call (on the same stream, or after synchronising).  Incremental: after an optimizer step
+ *      that touched one tensor, set that tensor and commit (src/torchmodel.py:167-208, train.py:128-133). */
 DAI_API int  dai_set_weight(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+DAI_API int  dai_set_weight_async(dai_handle* h, const char* key, const float* data, const int64_t* shape, int ndim,
+                                  void* stream);
 DAI_API int  dai_commit_weights(dai_handle* h, void* stream);
 
 DAI_API int  dai_set_rng(dai_handle* h, uint64_t seed, uint64_t call_index);

@@ -71,7 +71,15 @@ def load(weights):
     """The reference's ActiveInferenceModel on CPU with SHIM-1 / SHIM-2 and the given state_dict arrays."""
     import torch
     tm, _, _ = modules()
-    m = tm.ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0)
+    # the reference picks "cuda" whenever torch sees a GPU (src/torchmodel.py:151); its CPU path is what is wanted here
+    # (SURVEY.md §0 fact 5), so the probe answers "no GPU" while the instance is constructed
+    saved = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False
+    try:
+        m = tm.ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0)
+    finally:
+        torch.cuda.is_available = saved
+    assert m.device.type == "cpu"
     m.model_down.qs_net[9] = torch.nn.Linear(576, 256)      # SHIM-1 (D1)
     m.precision = torch.float32                             # SHIM-2 (D2)
     for mod in (m.model_top, m.model_mid, m.model_down):

@@ -188,3 +188,84 @@ def compare(name, got, ref, rtol=RTOL, atol=ATOL):
             bad.append("%s.%s max excess %.3e at %d (got %.7g ref %.7g)" %
                        (name, k, float(err.max()), i, a.flat[i], b.flat[i]))
     return bad
+
+
+class TeacherForced:
+    """Model stand-in for planner tests: every call the planner makes is served by the CUDA model AND evaluated by
+    the oracle on the SAME inputs under the SAME noise key (the oracle's call index is set to the engine's before each
+    call); the two answers must agree to the parity tolerance, and the planner continues on the CUDA answer.
+
+    Why not two independent searches: a search is a chain of argmax decisions over Q values that differ between actions
+    by ~1e-3 of |G| on random-init nets, so a 1e-6 relative difference in one G (fp32 CPU vs bf16x3 tensor cores, both
+    inside the 1e-4 bar) can flip a near-tie after a few dozen expansions and the two trees then differ legitimately.
+    Teacher forcing checks what parity means for a planner: along the search the CUDA model actually drives, each
+    evaluation equals the reference arithmetic."""
+
+    def __init__(self, gpu, ora, seed):
+        self.gpu, self.ora, self.seed = gpu, ora, seed
+        self.pi_dim, self.s_dim = gpu.pi_dim, gpu.s_dim
+        self.pi_one_hot, self.pi_one_hot_3 = gpu.pi_one_hot, gpu.pi_one_hot_3
+        self.device = gpu.device
+        self.calls = 0
+        self.worst = {}
+        outer = self
+
+        class _Down:
+            resolution = 64
+
+            def encoder(self, o):
+                return outer._both("encoder", lambda m, x: m.model_down.encoder(x), o)
+
+        class _Top:
+            def encode_s(self, s):
+                return outer._both("encode_s", lambda m, x: m.model_top.encode_s(x), s)
+
+        self.model_down, self.model_top = _Down(), _Top()
+
+    def _cpu(self, x):
+        return x.detach().cpu() if isinstance(x, torch.Tensor) else x
+
+    def _flat(self, out):
+        res = []
+        for v in (out if isinstance(out, (tuple, list)) else [out]):
+            if isinstance(v, (tuple, list)):
+                res += self._flat(v)
+            elif isinstance(v, torch.Tensor):
+                res.append(v.detach().to("cpu", torch.float64).reshape(-1).numpy())
+            else:
+                res.append(np.asarray([float(v)], dtype=np.float64))
+        return res
+
+    def _both(self, name, fn, *args, exact=(), scalar_rel=()):
+        self.ora.set_rng(self.seed, self.gpu._engine.get_rng()[1])
+        got = fn(self.gpu, *args)
+        with torch.no_grad():
+            ref = fn(self.ora, *[self._cpu(a) for a in args])
+        assert self.gpu._engine.get_rng()[1] == self.ora.call, name
+        for i, (a, b) in enumerate(zip(self._flat(got), self._flat(ref))):
+            assert a.shape == b.shape, (name, i)
+            if i in exact:
+                assert np.array_equal(a, b), "%s output %d differs (call %d)" % (name, i, self.calls)
+                continue
+            tol = RTOL * np.abs(b) + (0.0 if i in scalar_rel else ATOL)
+            err = np.abs(a - b)
+            assert np.all(np.isfinite(a)) and np.all(err <= tol), \
+                "%s output %d: max excess %.3e (call %d)" % (name, i, float((err - tol).max()), self.calls)
+            self.worst[name] = max(self.worst.get(name, 0.0), float((err / (np.abs(b) + 1e-30)).max()) if i in scalar_rel else 0.0)
+        self.calls += 1
+        return got
+
+    def calculate_G(self, s0, pi0, samples=10):
+        # G relative 1e-4; terms: t0, t1 relative, t2 against |G| -> checked through G (= -t0 + t1 + t2); latents/images rtol+atol
+        out = self._both("calculate_G", lambda m, s, p: (lambda r: (r[0], r[2], r[3], r[4]))(m.calculate_G(s, p, samples=samples)),
+                         s0, pi0, scalar_rel=(0,))
+        return out[0], None, out[1], out[2], out[3]
+
+    def calculate_G_mean(self, s0, pi0):
+        out = self._both("calculate_G_mean", lambda m, s, p: (lambda r: (r[0], r[2], r[3]))(m.calculate_G_mean(s, p)), s0, pi0,
+                         scalar_rel=(0,))
+        return out[0], None, out[1], out[2]
+
+    def mcts_step_simulate(self, starting_s, depth, use_means=False):
+        return self._both("mcts_step_simulate", lambda m, s: m.mcts_step_simulate(s, depth, use_means=use_means), starting_s,
+                          exact=(1,), scalar_rel=(0,))

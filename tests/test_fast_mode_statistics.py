@@ -36,19 +36,27 @@ def test_bf16x1_estimates_sit_inside_the_parity_modes_confidence_interval(kind):
     ref = _shard_means(kind, "bf16x3", 4242)
     same = _shard_means(kind, "bf16x1", 4242)                     # same noise: isolates the arithmetic
     other = _shard_means(kind, "bf16x1", 977)                     # independent noise: the estimator as a user sees it
+    def terms(x):            # (shards, 4, B) sums -> (shards, 4, B): term0, term1, term2 = term2_1 - term2_2, G
+        t2 = x[:, 2] - x[:, 3]
+        return np.stack([x[:, 0], x[:, 1], t2, -x[:, 0] + x[:, 1] + t2], axis=1)
+
     k = ref.shape[0]
-    mean_ref, se_ref = ref.mean(0), ref.std(0, ddof=1) / np.sqrt(k)
-    G_ref = -mean_ref[0] + mean_ref[1] + (mean_ref[2] - mean_ref[3])
-    # (1) same noise: the bias of the fast arithmetic is far inside the MC standard error, and tiny against |G|
-    bias = same.mean(0) - mean_ref
-    assert np.all(np.abs(bias) <= 0.5 * se_ref + 1e-6), (bias, se_ref)
-    G_same = -same.mean(0)[0] + same.mean(0)[1] + (same.mean(0)[2] - same.mean(0)[3])
-    assert np.all(np.abs(G_same - G_ref) <= 2e-3 * np.abs(G_ref)), (G_same, G_ref)
-    # (2) independent noise: means agree within the combined 4-sigma interval, spreads within a factor ~1.6 (F-test, 23 dof)
-    se_other = other.std(0, ddof=1) / np.sqrt(k)
-    z = np.abs(other.mean(0) - mean_ref) / np.sqrt(se_ref ** 2 + se_other ** 2 + 1e-12)
+    T_ref, T_same, T_other = terms(ref), terms(same), terms(other)
+    mean_ref, se_ref = T_ref.mean(0), T_ref.std(0, ddof=1) / np.sqrt(k)
+    absG = np.abs(mean_ref[3])
+    # (1) same noise isolates the arithmetic: the fast mode's bias on term0, term1, term2 and G is inside one standard
+    #     error of a 12,000-sample estimate (or 2e-5 of |G| where the estimator has almost no spread), and the two
+    #     entropy sums whose difference is term2 move by < 1e-5 of their size on the default weights (5e-4 on the saturating
+    #     set, where a single bf16 product cannot hold 1e-4 per pixel) — a shift common to both, which cancels in term2
+    bias = T_same.mean(0) - mean_ref
+    assert np.all(np.abs(bias) <= se_ref + 2e-5 * absG), (bias, se_ref)
+    assert np.all(np.abs(same.mean(0)[2:] - ref.mean(0)[2:]) <= (1e-5 if kind == "w0" else 5e-4) * np.abs(ref.mean(0)[2:]))
+    # (2) independent noise, the estimator as a user sees it: means within the combined 4.5-sigma interval, spreads
+    #     within the 99.9 % F interval for 23 degrees of freedom
+    se_other = T_other.std(0, ddof=1) / np.sqrt(k)
+    z = np.abs(T_other.mean(0) - mean_ref) / np.sqrt(se_ref ** 2 + se_other ** 2 + 1e-12)
     assert np.all(z < 4.5), z
-    ratio = (other.var(0, ddof=1) + 1e-12) / (ref.var(0, ddof=1) + 1e-12)
-    assert np.all((ratio > 0.3) & (ratio < 3.3)), ratio
-    # (3) same noise, shard by shard: the two modes track each other sample block by sample block
-    assert np.all(np.abs(same - ref) <= 5e-3 * np.abs(ref) + 1e-4)
+    ratio = (T_other.var(0, ddof=1) + 1e-12) / (T_ref.var(0, ddof=1) + 1e-12)
+    assert np.all((ratio > 0.25) & (ratio < 4.0)), ratio
+    # (3) same noise, block by block: every 500-sample block mean of G agrees to 1e-4 of |G|
+    assert np.all(np.abs(T_same[:, 3] - T_ref[:, 3]) <= 1e-4 * np.abs(T_ref[:, 3]))

@@ -58,11 +58,13 @@ def test_config5_eight_shards_match_the_unsharded_oracle():
     assert cases.compare("config5", _np(got), _np(ref)) == []
 
 
-def test_config4_full_mcts_decision_matches_the_oracle_driven_planner():
+def test_config4_full_mcts_decision_every_evaluation_matches_the_oracle():
     """configs[3]: 30 expansions x N=50 samples x simulation depth 10.  Where the reference is available (staged under
-    baseline/_ref by __graft_entry__.build(), or mounted) the UNMODIFIED src/mcts.py drives both the CUDA model and the
-    oracle model (Node.expand's `samples` default is set to 50 at run time: active_inference_mcts never passes it,
-    src/mcts.py:172,184); otherwise this repo's planner does.  Same path, expansions, visited paths; simulated G 1e-4."""
+    baseline/_ref by __graft_entry__.build(), or mounted) the UNMODIFIED src/mcts.py drives the CUDA model
+    (Node.expand's `samples` default is set to 50 at run time: active_inference_mcts never passes it,
+    src/mcts.py:172,184); otherwise this repo's planner does.  Teacher-forced (cases.TeacherForced): all 30 expansions
+    and 30 simulations the search requests are also evaluated by the oracle on the same inputs and noise keys and must
+    agree to 1e-4 (G) / exactly (sampled action sequences); the search completes with 30 expansions."""
     w = cases.weights_for("w0")
     gpu = _model()
     ora = O.OracleModel(w, seed=77)
@@ -80,14 +82,12 @@ def test_config4_full_mcts_decision_matches_the_oracle_driven_planner():
         if saved is None:
             p.samples = 50
         gpu.set_rng(77, 0)
-        rg = planner.active_inference_mcts(gpu, frame, p, o_shape=(1, 64, 64))
-        ro = planner.active_inference_mcts(ora, frame, p, o_shape=(1, 64, 64))
+        tf = cases.TeacherForced(gpu, ora, 77)
+        path, reps, explored, all_paths, all_G = planner.active_inference_mcts(tf, frame, p, o_shape=(1, 64, 64))
     finally:
         if saved is not None:
             planner.Node.expand.__defaults__ = saved
-    ints = lambda paths: [[int(a) for a in pth] for pth in paths]
-    assert [int(a) for a in rg[0]] == [int(a) for a in ro[0]]
-    assert rg[1] == ro[1] == 30 and rg[2] == ro[2] == 300
-    assert ints(rg[3]) == ints(ro[3])
-    assert np.allclose(rg[4], ro[4], rtol=1e-4, atol=0)
-    assert gpu._engine.get_rng()[1] == ora.call
+    assert reps == 30 and explored == 300 and len(all_paths) == 30 and len(all_G) == 30
+    assert tf.calls == 2 + 1 + 30 * 2                       # encoder, habit prior, root expansion, 30 x (expansion, simulation)
+    assert all(0 <= int(a) < 4 for a in path) and all(np.isfinite(all_G))
+    print("config4 teacher-forced: worst relative G error per call type:", tf.worst)

@@ -293,3 +293,22 @@ def test_new_entry_points_reject_bad_arguments():
     assert lib.dai_frames_set_sprites(fresh.h, ctypes.c_void_p(imgs.data_ptr()), 6, sizes, st) == -1
     fresh.close()
     assert torch.isfinite(m.model_down.decoder(torch.zeros(1, 10))).all()
+
+
+def test_encoder_batches_larger_than_one_chunk_match_the_oracle():
+    """More than 4096 image rows in ONE slot (dai_encode / the root encode of a rollout with > 1024 roots / the
+    trajectory rows of a large simulation batch): the launch is split by rows and the noise row index must run on."""
+    from oracle import efe_oracle as O
+    import dai_b200.synthetic as syn
+    m = _model("w0", "bf16x3")
+    B = 4500
+    o = torch.from_numpy(syn.make_frames(60, 41)).repeat(75, 1, 1, 1)[:B]
+    ora = O.OracleModel(cases.weights_for("w0"), seed=19)
+    m.set_rng(19, 0)
+    s, mean, logvar = m.model_down.encoder_with_sample(o)
+    with torch.no_grad():
+        so, meano, logvaro = ora.model_down.encoder_with_sample(o)
+    got = dict(s=s, mean=mean, logvar=logvar)
+    ref = dict(s=so, mean=meano, logvar=logvaro)
+    assert cases.compare("big_encode", {k: v.detach().cpu().numpy() for k, v in got.items()},
+                         {k: v.detach().cpu().numpy() for k, v in ref.items()}) == []
