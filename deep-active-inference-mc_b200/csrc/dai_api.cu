@@ -98,6 +98,19 @@ struct dai_handle {
     int32_t* plan_stop_host = nullptr;   // mapped pinned flag: the search's threshold test fired
     int32_t* plan_stop_dev = nullptr;
     cudaEvent_t plan_sel_ev = nullptr;   // recorded after every selection kernel: bounds the host's run-ahead to one batch
+    // one EFE step as a replayed CUDA graph: cache of instantiated step graphs keyed by everything a
+    // step's launches depend on except the noise key, which the kernels then read from `keybuf`
+    struct StepGraph { uint64_t sig = 0; uint64_t gen = 0; cudaGraphExec_t exec = nullptr; uint64_t nlaunch = 0; int seen = 0; uint64_t stamp = 0; };
+    std::vector<StepGraph> graphs;
+    uint64_t alloc_gen = 0;            // bumped whenever a workspace is (re)allocated: invalidates every cached graph
+    bool capturing = false, capture_failed = false;
+    int graphs_enabled = 1;            // env DAI_GRAPHS=0 disables (A/B)
+    uint32_t* keybuf = nullptr;        // device {k0, k1, step}
+    // the legacy default stream cannot be captured: work a caller enqueues on it runs on this stream instead, fenced
+    // with events on both sides (StreamSwap)
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    uint64_t graph_stamp = 0, graph_replays = 0;
     // sample-shard communicator (NCCL, resolved at run time; SURVEY.md §8 e)
     void* comm = nullptr;      // ncclComm_t
     int comm_rank = 0, comm_world = 1;
@@ -130,8 +143,37 @@ int fail(dai_handle* h, int code, const char* fmt, ...) {
         if (rc__ != DAI_OK) return rc__; \
     } while (0)
 
+// Graph capture needs a capturable stream.  If the caller hands in the legacy default stream (what torch's current stream is
+// unless the user switched), the call's work is enqueued on the handle's own non-blocking stream, ordered after everything
+// already on the caller's stream and followed by a wait on the caller's stream, so the caller-visible ordering is unchanged.
+struct StreamSwap {
+    dai_handle* h;
+    cudaStream_t user, use;
+    StreamSwap(dai_handle* h_, cudaStream_t st) : h(h_), user(st), use(st) {
+        const bool legacy = st == nullptr || st == cudaStreamLegacy;
+        if (!legacy || !h->graphs_enabled || !h->own_stream) return;
+        if (cudaEventRecord(h->ev_in, user) != cudaSuccess || cudaStreamWaitEvent(h->own_stream, h->ev_in, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        use = h->own_stream;
+    }
+    ~StreamSwap() {
+        if (use == user) return;
+        if (cudaEventRecord(h->ev_out, use) == cudaSuccess) cudaStreamWaitEvent(user, h->ev_out, 0);
+        cudaGetLastError();
+    }
+    StreamSwap(const StreamSwap&) = delete;
+    StreamSwap& operator=(const StreamSwap&) = delete;
+};
+
 int reserve(dai_handle* h, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return DAI_OK;
+    if (h->capturing) {                 // a stream capture cannot allocate or synchronise: give up on this capture
+        h->capture_failed = true;
+        return fail(h, DAI_E_CUDA, "workspace growth during graph capture");
+    }
+    ++h->alloc_gen;
     if (b.p) {
         CK(cudaDeviceSynchronize());
         CK(cudaFree(b.p));
@@ -152,7 +194,7 @@ T* ptr(DevBuf& b) { return static_cast<T*>(b.p); }
 
 NoiseKey make_key(const dai_handle* h, uint64_t call, uint32_t step) {
     const uint64_t k = h->seed + call;
-    NoiseKey nk;
+    NoiseKey nk{};
     nk.k0 = (uint32_t)(k & 0xffffffffu);
     nk.k1 = (uint32_t)(k >> 32);
     nk.step = step;
@@ -356,7 +398,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     RET(reserve(h, h->mask, (size_t)ch * 512 * sizeof(uint32_t)));
     RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act1, (size_t)ch * 16384 * esz));
-    RET(reserve(h, h->act2, (size_t)ch * 65536 * esz));
+    RET(reserve(h, h->act2, std::max((size_t)ch * 65536 * esz, tc ? tc_ct23_scratch_bytes(ch) : (size_t)0)));
     RET(reserve(h, h->act3, tc ? (size_t)ch * PROJ_ROW_FLOATS * sizeof(float) : (size_t)ch * 131072 * esz));
     fc.h3 = tc ? nullptr : ptr<float>(h->h3);
     fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
@@ -557,6 +599,104 @@ int run_step(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
     return post_launch(h, "step finalize");
 }
 
+__global__ void k_set_key(uint32_t* keybuf, uint32_t k0, uint32_t k1, uint32_t step) {
+    keybuf[0] = k0; keybuf[1] = k1; keybuf[2] = step;
+}
+
+uint64_t mix64(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+// run_step through a cached CUDA graph: the first evaluation with a given signature runs eagerly (it sizes the
+// workspaces), the second is captured (stream capture of the very same launch code) and instantiated, later ones are
+// ONE cudaGraphLaunch — ~30 kernels without per-launch host work or launch gaps.  The noise key of the call and the
+// step index are the only things that change between replays; the kernels read them from h->keybuf (NoiseKey::dyn),
+// which a one-thread kernel writes ahead of every launch.
+int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
+    if (!h->graphs_enabled || h->timer.on) return run_step(h, st, sp);
+    uint64_t sig = 1469598103934665603ull;
+    const uint64_t fields[] = {(uint64_t)(uintptr_t)sp.s0, (uint64_t)(uintptr_t)sp.pi, (uint64_t)sp.B, (uint64_t)sp.samples, (uint64_t)sp.j0,
+                               (uint64_t)sp.j1, (uint64_t)sp.mean_variant, (uint64_t)(uintptr_t)sp.acc, (uint64_t)(uintptr_t)sp.carry_dst,
+                               (uint64_t)sp.carry_mean, (uint64_t)(uintptr_t)sp.out_ps1, (uint64_t)(uintptr_t)sp.out_mean,
+                               (uint64_t)(uintptr_t)sp.out_logvar, (uint64_t)(uintptr_t)sp.out_po1, (uint64_t)h->cfg.precision,
+                               (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk, (uint64_t)(uintptr_t)st};
+    for (uint64_t f : fields) sig = mix64(sig, f);
+    dai_handle::StepGraph* g = nullptr;
+    for (auto& e : h->graphs)
+        if (e.sig == sig) { g = &e; break; }
+    if (g && g->gen != h->alloc_gen) {          // a workspace moved since: the captured pointers are stale
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        g->exec = nullptr; g->seen = 0; g->gen = h->alloc_gen;
+    }
+    if (!g) {
+        if (h->graphs.size() >= 24) {           // drop the least recently used entry
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].stamp < h->graphs[lru].stamp) lru = i;
+            if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs.erase(h->graphs.begin() + (long)lru);
+        }
+        h->graphs.push_back(dai_handle::StepGraph{});
+        g = &h->graphs.back();
+        g->sig = sig; g->gen = h->alloc_gen;
+    }
+    g->stamp = ++h->graph_stamp;
+    if (!h->keybuf) CK(cudaMalloc(&h->keybuf, 16));
+    if (g->exec) {
+        k_set_key<<<1, 1, 0, st>>>(h->keybuf, sp.nk.k0, sp.nk.k1, sp.nk.step);
+        CK(cudaGraphLaunch(g->exec, st));
+        h->launches += g->nlaunch + 1;
+        ++h->graph_replays;
+        return post_launch(h, "step graph");
+    }
+    if (g->seen++ == 0) {                        // first time: eager (grows the workspaces), and see whether anything moved
+        const uint64_t gen0 = h->alloc_gen;
+        RET(run_step(h, st, sp));
+        g->gen = h->alloc_gen;
+        if (h->alloc_gen != gen0) g->seen = 1;
+        return DAI_OK;
+    }
+    // capture
+    StepSpec cs = sp;
+    cs.nk.dyn = h->keybuf;
+    k_set_key<<<1, 1, 0, st>>>(h->keybuf, sp.nk.k0, sp.nk.k1, sp.nk.step);
+    const uint64_t l0 = h->launches;
+    h->capturing = true; h->capture_failed = false;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        h->capturing = false;
+        h->graphs_enabled = 0;                   // this stream cannot be captured (e.g. the legacy default stream): stay eager
+        return run_step(h, st, sp);
+    }
+    const int rc = run_step(h, st, cs);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    h->capturing = false;
+    if (rc != DAI_OK || ce != cudaSuccess || !graph || h->capture_failed) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        h->launches = l0;
+        g->seen = 1;                             // try again on a later call
+        if (h->capture_failed) { h->capture_failed = false; return run_step(h, st, sp); }
+        if (rc != DAI_OK) return rc;
+        return run_step(h, st, sp);
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphDestroy(graph);
+        h->launches = l0;
+        h->graphs_enabled = 0;
+        return run_step(h, st, sp);
+    }
+    cudaGraphDestroy(graph);
+    g->exec = exec; g->nlaunch = h->launches - l0; g->gen = h->alloc_gen;
+    CK(cudaGraphLaunch(g->exec, st));
+    h->launches += 1;
+    ++h->graph_replays;
+    return post_launch(h, "step graph (first launch)");
+}
+
 __global__ void k_fill_eye(float* pi, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * 4) pi[i] = ((i >> 2) & 3) == (i & 3) ? 1.0f : 0.0f;
@@ -604,7 +744,7 @@ int rollout_impl(dai_handle* h, cudaStream_t st, const float* o, const float* pi
         sp.acc = ptr<double>(h->acc);
         sp.carry_dst = ptr<float>(h->carry); sp.carry_mean = calc_mean;
         sp.out_po1 = (t == steps - 1) ? po1 : nullptr;
-        RET(run_step(h, st, sp));
+        RET(run_step_cached(h, st, sp));
     }
     return finish_outputs(h, st, B, mean_variant ? 1 : samples, sums, G, t0, t1, t2);
 }
@@ -639,9 +779,19 @@ int dai_create(const dai_config* cfg, int device, dai_handle** out) {
         const int v = atoi(e);
         if (v >= 32 && v <= 8192) h->dec_chunk = v;
     }
+    if (const char* e = getenv("DAI_GRAPHS")) h->graphs_enabled = atoi(e) != 0;
+    if (getenv("DAI_TC_COUNTERS") || getenv("DAI_TC_DBG")) h->graphs_enabled = 0;      // the experiment hooks synchronise
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DAI_E_CUDA; }
     if (cudaMallocHost(&h->pinned, 4096) != cudaSuccess) { delete h; return DAI_E_NOMEM; }
     h->pinned_cap = 4096;
+    if (h->graphs_enabled) {
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            h->graphs_enabled = 0;
+        }
+    }
     *out = h;
     return DAI_OK;
 }
@@ -656,6 +806,11 @@ int dai_destroy(dai_handle* h) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (void* p : h->wallocs) cudaFree(p);
     for (float* p : h->raw_dev) if (p) cudaFree(p);
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->keybuf) cudaFree(h->keybuf);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     tc_release(&h->tcw);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->plan_stop_host) cudaFreeHost(h->plan_stop_host);
@@ -803,7 +958,8 @@ int dai_calculate_G(dai_handle* h, const float* s0, const float* pi0, int B, int
     RET(check_ready(h));
     if (!s0 || !pi0 || B <= 0 || samples <= 0 || sample_begin < 0 || sample_end > samples || sample_begin > sample_end)
         return fail(h, DAI_E_INVALID, "calculate_G: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
     CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
     StepSpec sp;
@@ -812,7 +968,7 @@ int dai_calculate_G(dai_handle* h, const float* s0, const float* pi0, int B, int
     ++h->calls;
     sp.acc = ptr<double>(h->acc);
     sp.out_ps1 = ps1; sp.out_mean = ps1_mean; sp.out_logvar = ps1_logvar; sp.out_po1 = po1;
-    RET(run_step(h, st, sp));
+    RET(run_step_cached(h, st, sp));
     return finish_outputs(h, st, B, samples, sums, G, t0, t1, t2);
 }
 
@@ -820,7 +976,8 @@ int dai_calculate_G_mean(dai_handle* h, const float* s0, const float* pi0, int B
                          float* t2, float* ps1_mean, float* po1, void* stream) {
     RET(check_ready(h));
     if (!s0 || !pi0 || B <= 0) return fail(h, DAI_E_INVALID, "calculate_G_mean: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));
     CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
     StepSpec sp;
@@ -829,7 +986,7 @@ int dai_calculate_G_mean(dai_handle* h, const float* s0, const float* pi0, int B
     ++h->calls;
     sp.acc = ptr<double>(h->acc);
     sp.out_mean = ps1_mean; sp.out_po1 = po1;
-    RET(run_step(h, st, sp));
+    RET(run_step_cached(h, st, sp));
     return finish_outputs(h, st, B, 1, nullptr, G, t0, t1, t2);
 }
 
@@ -876,7 +1033,8 @@ int dai_rollout(dai_handle* h, const float* o, const float* pi, int B, int steps
                 void* stream) {
     RET(check_ready(h));
     if (!o) return fail(h, DAI_E_INVALID, "rollout: o is NULL");
-    return rollout_impl(h, (cudaStream_t)stream, o, pi, B, steps, samples, calc_mean, four, sample_begin, sample_end,
+    StreamSwap sw(h, (cudaStream_t)stream);
+    return rollout_impl(h, sw.use, o, pi, B, steps, samples, calc_mean, four, sample_begin, sample_end,
                         sums, G, t0, t1, t2, po1);
 }
 
@@ -893,7 +1051,8 @@ int dai_rollout_host(dai_handle* h, const float* o_host, const float* pi_host, i
                      float* po1_host, void* stream) {
     RET(check_ready(h));
     if (!o_host || B <= 0) return fail(h, DAI_E_INVALID, "rollout_host: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     const size_t in_bytes = (size_t)B * IMG * sizeof(float) + (size_t)B * 4 * sizeof(float);
     const size_t out_f = (size_t)4 * B + (po1_host ? (size_t)B * IMG : 0);
     RET(reserve(h, h->stage_in, in_bytes));
@@ -967,7 +1126,8 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
     if (K < 1 || K > PLAN_MAX_K || R < 0 || R > 100000 || depth < 1 || depth > 256 || nrep < 1 || prm->samples < 1)
         return fail(h, DAI_E_INVALID, "mcts_plan: 1 <= leaves <= %d, repeats >= 0, 1 <= simulation_depth <= 256, "
                     "simulation_repeats >= 1, samples >= 1", PLAN_MAX_K);
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     if (!h->plan_stop_host) {
         CK(cudaHostAlloc(&h->plan_stop_host, 64, cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer(&h->plan_stop_dev, h->plan_stop_host, 0));
@@ -1015,18 +1175,18 @@ int dai_mcts_plan(dai_handle* h, const float* frame, const float* qs0_mean_in, c
     // ---- root: qs0 = encoder mean (src/mcts.py:158), habit prior (:164), first expansion (:172)
     const float* root_mean = qs0_mean_in;
     if (!root_mean) {
-        RET(dai_encode(h, frame, 1, m0, lv0, nullptr, stream));
+        RET(dai_encode(h, frame, 1, m0, lv0, nullptr, (void*)st));
         root_mean = m0;
     }
-    RET(dai_habit(h, root_mean, 1, nullptr, rootq, nullptr, stream));
+    RET(dai_habit(h, root_mean, 1, nullptr, rootq, nullptr, (void*)st));
     h->launches += launch_plan_init(t, root_mean, rootq, st);
     auto expand = [&](int kv) -> int {          // kv <= 0: the root itself
         const int rows = PI_DIM * std::max(kv, 1);
         h->launches += launch_plan_select(t, kv, prm->threshold, pk, s_rows, starts, st);
         CK(cudaEventRecord(h->plan_sel_ev, st));
-        if (prm->use_means) RET(dai_calculate_G_mean(h, s_rows, pi_eye, rows, Gd, nullptr, nullptr, nullptr, nxt, nullptr, stream));
+        if (prm->use_means) RET(dai_calculate_G_mean(h, s_rows, pi_eye, rows, Gd, nullptr, nullptr, nullptr, nxt, nullptr, (void*)st));
         else RET(dai_calculate_G(h, s_rows, pi_eye, rows, prm->samples, 0, prm->samples, nullptr, Gd, nullptr, nullptr, nullptr,
-                                 nxt, nullptr, nullptr, nullptr, stream));
+                                 nxt, nullptr, nullptr, nullptr, (void*)st));
         h->launches += launch_plan_expand(t, pk, Gd, nxt, st);
         return post_launch(h, "planner expansion");
     };
@@ -1169,8 +1329,23 @@ int dai_profile_end(dai_handle* h, float ms[5], int64_t launches[5], int64_t row
 
 int dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, int nrows, float* out, void* stream) {
     RET(check_ready(h));
-    if (!in || !out || nrows <= 0 || layer < 1 || layer > 3) return fail(h, DAI_E_INVALID, "debug_layer: bad arguments");
+    if (!in || !out || nrows <= 0 || ((layer < 1 || layer > 3) && layer != 23)) return fail(h, DAI_E_INVALID, "debug_layer: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (layer == 23) {
+        // ct2 -> ct3 fused pair kernel: (nrows,256,64) fp32 NHWC in, the last deconv's row planes (nrows,3,4096) out
+        if (precision == DAI_PREC_FP32_SIMT) return fail(h, DAI_E_INVALID, "debug_layer 23 is the tensor-core pair kernel");
+        RET(reserve(h, h->act0, (size_t)nrows * 256 * 64 * 4));
+        RET(reserve(h, h->act2, tc_ct23_scratch_bytes(nrows)));
+        RET(reserve(h, h->act3, (size_t)nrows * PROJ_ROW_FLOATS * sizeof(float)));
+        h->launches += tc_to_blocked(in, nrows, 256, 64, h->act0.p, st);
+        std::string terr;
+        h->timer.begin(2, nrows, st);
+        const int nl = tc_ct23(h->tcw, h->w, precision, h->act0.p, h->act2.p, h->act3.p, nrows, st, &terr);
+        if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core pair kernel: %s", terr.c_str());
+        h->timer.end(st);
+        h->launches += nl + launch_proj_rows(ptr<float>(h->act3), nrows, out, st);
+        return post_launch(h, "debug layer (ct2+ct3 pair)");
+    }
     if (precision == DAI_PREC_FP32_SIMT) {
         if (layer == 1) h->launches += launch_ct1_simt(h->w, in, nrows, out, st);
         if (layer == 2) h->launches += launch_ct2_simt(h->w, in, nrows, out, st);
@@ -1293,7 +1468,8 @@ int dai_rollout_sharded(dai_handle* h, const float* o, const float* pi, int B, i
                         float* G, float* t0, float* t1, float* t2, float* po1, void* stream) {
     RET(check_ready(h));
     if (!o) return fail(h, DAI_E_INVALID, "rollout_sharded: o is NULL");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     int j0 = 0, j1 = samples;
     const bool sharded = h->comm_world > 1 && !(four && calc_mean);    // calculate_G_mean steps have one sample: nothing to shard
     if (sharded) shard_of(samples, h->comm_rank, h->comm_world, &j0, &j1);
@@ -1307,7 +1483,8 @@ int dai_calculate_G_sharded(dai_handle* h, const float* s0, const float* pi0, in
                             float* t2, float* ps1, float* ps1_mean, float* ps1_logvar, float* po1, void* stream) {
     RET(check_ready(h));
     if (!s0 || !pi0 || B <= 0 || samples <= 0) return fail(h, DAI_E_INVALID, "calculate_G_sharded: bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
+    StreamSwap sw(h, (cudaStream_t)stream);
+    cudaStream_t st = sw.use;
     int j0 = 0, j1 = samples;
     if (h->comm_world > 1) shard_of(samples, h->comm_rank, h->comm_world, &j0, &j1);
     RET(reserve(h, h->acc, (size_t)4 * B * sizeof(double)));

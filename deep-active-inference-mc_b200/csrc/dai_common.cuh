@@ -18,6 +18,8 @@ struct NoiseKey {
     uint32_t k0, k1;     // seed + call_index
     uint32_t step;
     int32_t training;    // 0: dropout is identity
+    const uint32_t* dyn; // non-null: {k0, k1, step} are read from device memory instead (replayed CUDA graphs: the
+                         // captured kernels keep their parameters, the key of the call / step is written before each launch)
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -35,7 +37,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
 // 128 random bits for (site, block) of (row, sample) at this key/step
 __device__ __forceinline__ uint4 noise_block(const NoiseKey& nk, uint32_t site, uint32_t blk,
                                              uint32_t row, uint32_t sample) {
-    return philox4x32_10(make_uint4(blk | (site << 16), row, sample, nk.step), nk.k0, nk.k1);
+    uint32_t k0 = nk.k0, k1 = nk.k1, step = nk.step;
+    if (nk.dyn) { k0 = __ldg(nk.dyn); k1 = __ldg(nk.dyn + 1); step = __ldg(nk.dyn + 2); }
+    return philox4x32_10(make_uint4(blk | (site << 16), row, sample, step), k0, k1);
 }
 
 // standard normal for element e: Box-Muller in fp64 on words 0,1 of block e, rounded once

@@ -61,6 +61,12 @@ size_t tc_qs_conv4_scratch_bytes(int rows);
 int tc_qs_conv4(const TcWeights& tw, int precision, const float* c3, int rows, void* scratch, size_t rows_pad, void* out,
                 cudaStream_t st, std::string* err);
 
+// ct2 -> ct3 fused on CTA pairs (k_tc_ct23): act1 blocked planes in, the last deconv's row planes out; `scratch` =
+// tc_ct23_scratch_bytes(nrows) bytes that stay L2-resident (2 images per CTA).
+size_t tc_ct23_scratch_bytes(int nrows);
+int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void* act1, void* scratch, void* act3, int nrows,
+            cudaStream_t st, std::string* err);
+
 // One tensor-core layer (1: ct1, 2: ct2, 3: ct3) on channel-blocked bf16 hi/lo input planes.
 int tc_layer(const TcWeights& tw, const DevWeights& w, int precision, int layer, const void* in, void* out, int nrows,
              cudaStream_t st, std::string* err);

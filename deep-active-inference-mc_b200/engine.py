@@ -371,9 +371,10 @@ class Engine:
         x = self.dev(x)
         n = x.shape[0]
         prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
-        hw_out, c_out = {1: (256, 64), 2: (1024, 64), 3: (4096, 32)}[layer]
-        # layer 3 on tensor cores returns the last deconv's row planes [n][3][4096] (see dai_tc.cu), not the 32 channels
-        out = self.new(n, 3, 4096) if (layer == 3 and prec != PREC_FP32_SIMT) else self.new(n, hw_out, c_out)
+        hw_out, c_out = {1: (256, 64), 2: (1024, 64), 3: (4096, 32), 23: (4096, 32)}[layer]
+        # layer 3 on tensor cores (and 23, the fused ct2 -> ct3 pair kernel) returns the last deconv's row planes
+        # [n][3][4096] (see dai_tc.cu), not the 32 channels
+        out = self.new(n, 3, 4096) if (layer in (3, 23) and prec != PREC_FP32_SIMT) else self.new(n, hw_out, c_out)
         self._ck(self.lib.dai_debug_layer(self.h, layer, prec, _p(x), n, _p(out), self._stream()))
         return out
 

@@ -265,7 +265,9 @@ DAI_API int  dai_profile_end(dai_handle* h, float ms[5], int64_t launches[5], in
  * fp32 NHWC in and out, in the given DAI_PREC_* arithmetic.  Used by tests to compare the tcgen05
  * kernels with the fp32 CUDA-core kernels layer by layer.  Exception: layer 3 in a tensor-core precision returns what
  * that kernel hands to the pixel kernel — the last deconv's channel and kw sums, out (nrows,3,4096):
- * e[kh][oy][ox] = sum_kw sum_c relu(ct3)[oy][ox+1-kw][c] * w4[c][kh][kw]. */
+ * e[kh][oy][ox] = sum_kw sum_c relu(ct3)[oy][ox+1-kw][c] * w4[c][kh][kw].
+ * layer 23 (tensor-core precisions only) is the production pair kernel that runs layers 2 and 3 fused (the
+ * 32x32x64 activation between them stays in an L2-resident scratch): in (nrows,256,64), out (nrows,3,4096) as for 3. */
 DAI_API int  dai_debug_layer(dai_handle* h, int layer, int precision, const float* in, int nrows, float* out, void* stream);
 
 #ifdef __cplusplus

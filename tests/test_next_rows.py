@@ -113,7 +113,7 @@ def test_incremental_device_side_repack(capsys):
         torch.cuda.synchronize()
         timings[key] = (time.perf_counter() - t) * 1e3
         n = m._engine.stats()["repack_launches"]
-        assert 1 <= n <= 3, (key, n)                            # the tensor's own images only (fp32 + tensor-core form)
+        assert n <= 3 and (n >= 1 or key.endswith("bias")), (key, n)   # its own images only (fp32, tensor-core, pair form); a bias is used as stored
     # a REPLACED parameter object is picked up too
     with torch.no_grad():
         newb = torch.nn.Parameter(m.model_down.po_net[13].bias.detach() + 0.25)
