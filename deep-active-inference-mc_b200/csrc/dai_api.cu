@@ -389,7 +389,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     const int rows = fc.map.rows();
     if (rows <= 0) return DAI_OK;
     const bool tc = h->cfg.precision != DAI_PREC_FP32_SIMT;
-    const size_t rows_pad = ((size_t)rows + 127) / 128 * 128 + 128;      // the tensor-core FC4 reads whole 128-row tiles
+    const size_t rows_pad = ((size_t)rows + 127) / 128 * 128 + 256;      // the tensor-core FC4 reads whole 256-row blocks (CTA pairs) from any chunk start
     RET(reserve(h, h->h3, tc ? rows_pad * 256 * 2 * sizeof(unsigned short) : (size_t)rows * 256 * sizeof(float)));
     // equal chunks (a short last chunk leaves most SMs idle for a whole pass): ceil(rows / nchunks), 32-row granular
     const int nchunks = (rows + h->dec_chunk - 1) / h->dec_chunk;

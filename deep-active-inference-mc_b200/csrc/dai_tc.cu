@@ -40,6 +40,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without memory-ordering semantics: used where the barrier hands over a TMEM accumulator that has already been
+// read into registers (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order the tensor-memory side).  The default
+// .release arrive makes the warp wait for all of its outstanding global stores first (MEMBAR + ERRBAR in SASS; 11 % of
+// the pair kernel's samples before this change).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -478,7 +485,15 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
             if constexpr (DBG) e_wait += clock64() - ew0;
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * C::ACC_COLS);
+            // the accumulator buffer goes back to the MMA issuer as soon as this warp's part of it sits in registers — before
+            // the arithmetic and the stores, and without waiting for them (relaxed arrive)
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(&acc_empty[buf]);
+            };
             if (DBG && (p.dbg & 1)) {
+                release_acc();
             } else if (C::MODE != 1) {
                 // 32 of the NPH output channels of this pixel (half = which 32, when NPH = 64)
                 const int c0 = (C::NPH == 64) ? half * 32 : 0;
@@ -491,6 +506,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                 }
+                release_acc();
                 if (active && C::OUT == OUT_NHWC_F32) {
                     float* out = reinterpret_cast<float*>(p.out) + (((size_t)row * C::VH + y) * C::VW + x) * C::NPH + c0;
 #pragma unroll
@@ -548,6 +564,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     uint32_t rl[32], rr[32];
                     tmem_ld32(tbase + slot_l * 32, rl);
                     tmem_ld32(tbase + slot_r * 32, rr);
+                    release_acc();
                     if (DBG && (p.dbg & 8)) {       // experiment: TMEM loads only
                         if (rl[0] == 0x12345678u && rr[5] == 0x9abcdef0u) out[o] = 1.0f;
                     } else
@@ -593,6 +610,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                         uint32_t rl[32], rr[32];
                         tmem_ld32(tbase + slot_l * C::NPH + c0, rl);
                         tmem_ld32(tbase + slot_r * C::NPH + c0, rr);
+                        if (c0 + 32 >= C::NPH) release_acc();
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint32_t hl[4], ll[4], hr[4], lr[4];
@@ -610,9 +628,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
         if constexpr (DBG) {
             if (p.counters && warp == 0 && lane == 0) {
@@ -796,6 +811,11 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
             for (int c0 = 0; c0 < NT / 2; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tbase + c0, r);
+                if (c0 + 32 >= NT / 2) {          // last columns of this warp's share are in registers: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&acc_empty[buf]);
+                }
                 if (row >= p.nrows) continue;
                 const int n0 = nt * NT + half * (NT / 2) + c0;
                 if (EPI == EPI_FC4) {
@@ -822,9 +842,6 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
@@ -875,6 +892,11 @@ struct F23 {
     static constexpr int SMEM_A = NA * PLANE;
     static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + 1024;
     static constexpr int THREADS = 512;
+    // scratch image = ct2's output as blocked bf16 planes [kc 8][32][32][8], hi and lo: what ct3's tensor-map boxes read.
+    // (Storing it as ct3's eight halo tiles instead — one contiguous 19.6 KB block per (tile, plane), loaded with a single bulk
+    // copy — was measured: the scattered 16-byte stores with their duplicates for the halo rows/columns made the ct2 epilogue
+    // 66 % slower, and the issuer's waits for halos did not shrink: those were the relay's fences, not the TMA boxes.)
+    static constexpr int SCR_IMAGE = 2 * 64 * 32 * 32 * 2;         // 262,144 B
     static_assert(C2::PLANE_A == C3::PLANE_A, "the two layers share the halo ring");
     static_assert(PLANE % 128 == 0 && W_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -901,11 +923,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+// Arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster, without memory-ordering semantics.
+// Everything handed over this way was written by the async proxy (TMA / bulk copies, whose completion the sender observed on
+// its own mbarrier) or sits in tensor memory and is read by the tensor core; a .release.cluster arrive instead costs a
+// MEMBAR.ALL.GPU + ERRBAR per arrival — in the relay thread that was most of the MMA issuer's wait for halos.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // the barrier at this offset in BOTH CTAs gets one arrival once every MMA issued so far has completed
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
@@ -931,6 +956,34 @@ __host__ __device__ constexpr uint32_t umma2_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// L2 eviction priorities: the pair kernel's scratch images should stay in L2 between the ct2 epilogue's stores, ct3's loads
+// and the next overwrite two stages later (evict_last); its streaming traffic (act1 in, projection rows out) should not
+// push them out (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_5d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4,
+                                                 uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void st_global_256_hint(void* p, const uint32_t (&a)[4], const uint32_t (&b)[4], uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]),
+                 "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_f2_hint(float* p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 
 // ---- unit tables of the pair kernel ---------------------------------------------------------------------------
 // Every item of the pair kernel accumulates into ONE 128-column TMEM buffer, so all items share a 4-buffer ring:
@@ -974,10 +1027,15 @@ __host__ __device__ constexpr int pu_woff(int u) {
 template <int L>
 __host__ __device__ constexpr int pu_bytes() { return pu_woff<L>(pu_count<L>()); }
 
-// All pair MMAs of one item of layer L.  a_hi16 / a_lo16 / w16: shared-memory addresses >> 4 of the two halo planes and
-// of this CTA's weight image of layer L; d0: TMEM address of the item's buffer.
-template <int L>
-__device__ __forceinline__ void issue_item_pair(uint32_t a_hi16, uint32_t a_lo16, uint32_t w16, uint32_t d0, bool x3) {
+// The pair MMAs of one item of layer L that read ONE halo plane.  a16 / w16: shared-memory addresses >> 4 of that plane
+// and of this CTA's weight image of layer L; d0: TMEM address of the item's buffer.
+//   PASS 0: the products on the hi plane (A_hi*B_hi, which initialises the accumulator, and — bf16x3 — A_hi*B_lo)
+//   PASS 1: the product on the lo plane (A_lo*B_hi)
+// Plane-major order lets the hi plane's ring slot go back to the producer after two thirds of a tile's MMAs and gives the
+// lo plane's load that much more time: the ring holds only three tiles and the issuer runs about one tile ahead of the
+// tensor pipe, so with both planes waited for together the issuer spent 18 % of its time waiting for halos.
+template <int L, int PASS>
+__device__ __forceinline__ void issue_item_pair(uint32_t a16, uint32_t w16, uint32_t d0, bool x3) {
     constexpr int HX = 9, KC_STRIDE = 17 * 9 * 16, KCIN = 8, KSTEPS = 4;
     constexpr uint32_t A_TOP = (uint32_t)((HX * 16) >> 4) | (1u << 14);
     constexpr uint32_t B_TOP = (uint32_t)(128 >> 4) | (1u << 14);
@@ -994,28 +1052,31 @@ __device__ __forceinline__ void issue_item_pair(uint32_t a_hi16, uint32_t a_lo16
         const uint32_t d = d0 + (uint32_t)un.col;
 #pragma unroll
         for (int k = 0; k < KSTEPS; ++k) {
-            const uint32_t acc0 = (un.init && k == 0) ? 0u : 1u;
             const uint32_t a_imm = ((a_off + (uint32_t)(2 * k) * KC_STRIDE) >> 4) + A_LBO;
             const uint32_t b_imm = ((woff + (uint32_t)(2 * k) * bk) >> 4) + ((bk >> 4) << 16);
-            const uint32_t a_hi = a_hi16 + a_imm, a_lo = a_lo16 + a_imm;
+            const uint32_t a = a16 + a_imm;
             const uint32_t b_hi = w16 + b_imm, b_lo = w16 + b_imm + (b_plane >> 4);
-            umma2_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_hi, umma2_idesc(un.n), acc0);
-            if (x3) {
-                umma2_bf16_split<A_TOP, B_TOP>(lead, d, a_lo, b_hi, umma2_idesc(un.n), 1u);
-                umma2_bf16_split<A_TOP, B_TOP>(lead, d, a_hi, b_lo, umma2_idesc(un.n), 1u);
+            if (PASS == 0) {
+                umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_hi, umma2_idesc(un.n), (un.init && k == 0) ? 0u : 1u);
+                if (x3) umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_lo, umma2_idesc(un.n), 1u);
+            } else {
+                umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_hi, umma2_idesc(un.n), 1u);
             }
         }
     }
 }
 
 // Item k of a stage (12 items, all roles walk the same list):
-//   0: ct2 tile 0 parity 0   1: ct2 tile 0 parity 1   2,3,4: ct3 tiles 0,1,2
-//   5: ct2 tile 1 parity 0   6: ct2 tile 1 parity 1   7..11: ct3 tiles 3..7
-// The two parities of a ct2 tile are adjacent (they share the tile's halo planes); the ct2 tiles are spread out so the
-// four ct2-epilogue warps (store-bound, ~4.5k cycles per item) are never two tiles behind.
+//   0: ct2 tile 0 parity 0   1: ct2 tile 0 parity 1   2: ct3 tile 0
+//   3: ct2 tile 1 parity 0   4: ct2 tile 1 parity 1   5..11: ct3 tiles 1..7
+// The two parities of a ct2 tile are adjacent (they share the tile's halo planes).  The ct2 items come EARLY in the stage:
+// the four ct2-epilogue warps work through them back to back (store-bound, ~4.5k cycles each) and the scratch image must
+// be complete well before the producer wants to prefetch the next stage's first ct3 halo (measured: with the ct2 tiles
+// spread over the stage the MMA issuer waited 23 % of its time for halos).
 constexpr int F23_ITEMS = 12;
-__device__ __forceinline__ int item_layer(int k) { return (k == 0 || k == 5) ? 0 : ((k == 1 || k == 6) ? 1 : 2); }
-__device__ __forceinline__ int item_tile(int k) { return k < 2 ? 0 : (k < 5 ? k - 2 : (k < 7 ? 1 : k - 4)); }
+constexpr int F23_LAST_CT2 = 4;
+__device__ __forceinline__ int item_layer(int k) { return (k == 0 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2); }
+__device__ __forceinline__ int item_tile(int k) { return k < 3 ? 0 : (k < 5 ? 1 : k - 4); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F23::THREADS, 1)
 k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CUtensorMap tmapScr, const FusedParams p) {
@@ -1085,6 +1146,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
         // ===== halo producer: one TMA box per plane per TILE (the two parities of a ct2 tile share it) =====
         if (lane == 0) {
             int cnt = 0;
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
             for (int j = 0; j <= J; ++j) {
                 const int row = min(2 * (pair + j * npairs) + (int)rank, p.nrows - 1);
                 const int par = (j - 1) & 1;
@@ -1101,8 +1163,8 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                         const int s = cnt % F23::NA;
                         mbar_wait(&a_empty[s], ((uint32_t)(cnt / F23::NA) & 1u) ^ 1u);
                         mbar_expect_tx(&a_full[s], F23::PLANE);
-                        if (L == 2) tma_load_5d(smA + (size_t)s * F23::PLANE, &tmapScr, &a_full[s], x0 * 8, y0, 0, srow0 + par, pl);
-                        else tma_load_5d(smA + (size_t)s * F23::PLANE, &tmapIn, &a_full[s], x0 * 8, y0, 0, row, pl);
+                        if (L == 2) tma_load_5d_hint(smA + (size_t)s * F23::PLANE, &tmapScr, &a_full[s], x0 * 8, y0, 0, srow0 + par, pl, pol_keep);
+                        else tma_load_5d_hint(smA + (size_t)s * F23::PLANE, &tmapIn, &a_full[s], x0 * 8, y0, 0, row, pl, pol_stream);
                     }
                 }
             }
@@ -1117,7 +1179,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
             for (int off = 0; off < F23::W3_HALF; off += 4096) bulk_load(smW + F23::W2_HALF + off, s3 + off, 4096, w_full);
             if (rank == 1) {
                 mbar_wait(w_full, 0);
-                mbar_arrive_remote(peer_w, 0);
+                mbar_arrive_remote_relaxed(peer_w, 0);
             }
         }
     } else if (warp == W_MMA && rank == 1) {
@@ -1127,7 +1189,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
             for (int cnt = 0; cnt < planes_total; ++cnt) {
                 const int s = cnt % F23::NA;
                 mbar_wait(&a_full[s], (uint32_t)(cnt / F23::NA) & 1u);
-                mbar_arrive_remote(&peer_full[s], 0);
+                mbar_arrive_remote_relaxed(&peer_full[s], 0);
             }
         }
     } else if (warp == W_MMA) {
@@ -1140,7 +1202,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
         int cnt = 0, seq = 0;
         int s0 = 0, s1 = -1;
         uint32_t ah = 0, al = 0;
-        long long t_begin = 0, w_acc = 0, w_a = 0, tw = 0;
+        long long t_begin = 0, w_acc = 0, w_a = 0, w_a2 = 0, tw = 0;
         if (timing) t_begin = clock64();
         for (int j = 0; j <= J; ++j) {
             F23_FOR_ITEMS(j, k, L, t) {
@@ -1150,15 +1212,26 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                 mbar_wait_cluster(&acc_empty[buf], ((uint32_t)(seq >> 2) & 1u) ^ 1u);
                 ++seq;
                 if (timing) { w_acc += clock64() - tw; tw = clock64(); }
-                if (L != 1) {                                          // a new tile: its halo planes
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * 128);
+                // pass 0 on the hi plane
+                if (L != 1) {                                          // a new tile: wait for its hi plane
                     s0 = cnt % F23::NA;
                     const uint32_t ph0 = (uint32_t)(cnt / F23::NA) & 1u;
                     mbar_wait(&a_full[s0], ph0);
                     mbar_wait_cluster(&peer_full[s0], ph0);
                     ++cnt;
                     ah = a16 + (uint32_t)s0 * (F23::PLANE >> 4);
-                    s1 = -1; al = 0;
-                    if (nplanes == 2) {
+                }
+                if (timing) { const long long dt = clock64() - tw; w_a += dt; if (L != 2) w_a2 += dt; }
+                tc_fence_after();
+                if (L == 0) issue_item_pair<0, 0>(ah, w2a_16, d0, nplanes == 2);
+                else if (L == 1) issue_item_pair<1, 0>(ah, w2b_16, d0, nplanes == 2);
+                else issue_item_pair<2, 0>(ah, w3_16, d0, nplanes == 2);
+                if (L != 0) umma2_commit(&a_empty[s0]);                // the hi plane is done with (after parity 1 for ct2)
+                if (nplanes == 2) {
+                    // pass 1 on the lo plane
+                    if (timing) tw = clock64();
+                    if (L != 1) {
                         s1 = cnt % F23::NA;
                         const uint32_t ph1 = (uint32_t)(cnt / F23::NA) & 1u;
                         mbar_wait(&a_full[s1], ph1);
@@ -1166,23 +1239,19 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                         ++cnt;
                         al = a16 + (uint32_t)s1 * (F23::PLANE >> 4);
                     }
-                }
-                if (timing) w_a += clock64() - tw;
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + (uint32_t)(buf * 128);
-                if (L == 0) issue_item_pair<0>(ah, al, w2a_16, d0, nplanes == 2);
-                else if (L == 1) issue_item_pair<1>(ah, al, w2b_16, d0, nplanes == 2);
-                else issue_item_pair<2>(ah, al, w3_16, d0, nplanes == 2);
-                if (L != 0) {                                          // the tile's halo is done with (after parity 1 for ct2)
-                    umma2_commit(&a_empty[s0]);
-                    if (s1 >= 0) umma2_commit(&a_empty[s1]);
+                    if (timing) { const long long dt = clock64() - tw; w_a += dt; if (L != 2) w_a2 += dt; }
+                    tc_fence_after();
+                    if (L == 0) issue_item_pair<0, 1>(al, w2a_16, d0, true);
+                    else if (L == 1) issue_item_pair<1, 1>(al, w2b_16, d0, true);
+                    else issue_item_pair<2, 1>(al, w3_16, d0, true);
+                    if (L != 0) umma2_commit(&a_empty[s1]);
                 }
                 umma2_commit(&acc_full[(L == 2 ? 4 : 0) + buf]);
             }
         }
         if (timing && lane == 0) {
             long long* c = p.counters + (size_t)blockIdx.x * 8;
-            c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = J;
+            c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = J; c[7] = w_a2;
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== ct2 epilogue (both CTAs, 4 warps): lane = pixel of the tile, one output-row parity per item =====
@@ -1193,6 +1262,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
         __nv_bfloat16* scr = reinterpret_cast<__nv_bfloat16*>(p.scratch);
         const size_t scr_plane = (size_t)p.srows * 64 * 32 * 32;
         int seq = 0;
+        const uint64_t pol_keep = l2_policy_evict_last();
         uint32_t own[4] = {0, 0, 0, 0};            // this group's uses of each TMEM buffer so far (phase of its barrier)
         long long e_begin = 0, e_wait = 0, e_fence = 0, tw = 0;
         if (timing) e_begin = clock64();
@@ -1223,8 +1293,8 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                         tc_fence_before();
                         __syncwarp();
                         if (lane < 2) {
-                            if (rank == 0) mbar_arrive(&acc_empty[buf]);
-                            else mbar_arrive_remote(&acc_empty[buf], 0);
+                            if (rank == 0) mbar_arrive_relaxed(&acc_empty[buf]);
+                            else mbar_arrive_remote_relaxed(&acc_empty[buf], 0);
                         }
                     }
 #pragma unroll
@@ -1238,11 +1308,11 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                         }
                         const int kc = (c0 >> 3) + qq;
                         const size_t o = ((((size_t)srow * 8 + kc) * 32 + oy) * 32 + ox) * 8;
-                        st_global_256(scr + o, hl, hr);               // pixels (oy, 2x) and (oy, 2x+1): 32 B
-                        st_global_256(scr + scr_plane + o, ll, lr);
+                        st_global_256_hint(scr + o, hl, hr, pol_keep);               // pixels (oy, 2x) and (oy, 2x+1): 32 B
+                        st_global_256_hint(scr + scr_plane + o, ll, lr, pol_keep);
                     }
                 }
-                if (k == 6) {
+                if (k == F23_LAST_CT2) {
                     // last ct2 item of the image: the scratch image is ready once this warp's stores (of all four items)
                     // are visible to the async proxy — TMA reads them back
                     if (timing) tw = clock64();
@@ -1255,7 +1325,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
         }
         if (timing && warp == 8 && lane == 0) {
             long long* c = p.counters + (size_t)blockIdx.x * 8;
-            c[6] = clock64() - e_begin - e_wait; c[7] = e_fence;
+            c[6] = clock64() - e_begin - e_wait; (void)e_fence;
         }
     } else if (warp < 8) {
         // ===== ct3 epilogue (both CTAs, 8 warps): lane = pixel; warps 0-3 output-row parity 0, warps 4-7 parity 1 =====
@@ -1265,6 +1335,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
         const int ty = m >> 3, tx = m & 7;
         const int slot_l = py == 0 ? 0 : 3, slot_r = py == 0 ? 1 : 2;      // TMEM column slots [00, 01, 11, 10]
         int seq = 0;
+        const uint64_t pol_stream = l2_policy_evict_first();
         uint32_t own[4] = {0, 0, 0, 0};
         long long e_begin = 0, e_wait = 0, tw = 0;
         if (timing) e_begin = clock64();
@@ -1293,8 +1364,8 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (rank == 0) mbar_arrive(&acc_empty[buf]);
-                    else mbar_arrive_remote(&acc_empty[buf], 0);
+                    if (rank == 0) mbar_arrive_relaxed(&acc_empty[buf]);
+                    else mbar_arrive_remote_relaxed(&acc_empty[buf], 0);
                 }
                 unsigned long long acc[9];
 #pragma unroll
@@ -1321,7 +1392,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                     e.x = (dr0 + dl1) + (txl > 0 ? from_left : 0.0f);
                     e.y = (dr1 + dl2) + (txl < 7 ? from_right : 0.0f);
                     if (live) {
-                        *reinterpret_cast<float2*>(out + (size_t)kh * HO * WO + o) = e;
+                        st_global_f2_hint(out + (size_t)kh * HO * WO + o, e, pol_stream);
                         if (txl == 0) edge[(size_t)kh * HO * C3::TILES_X * 2] = dl0;
                         if (txl == 7) edge[(size_t)kh * HO * C3::TILES_X * 2 + 1] = dr2;
                     }
@@ -1338,6 +1409,201 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
     __syncthreads();
     cluster_sync_all();
     if (warp == W_ALLOC) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// =======================================================================================
+// FC4 (256 -> 16384) on CTA pairs with the A operand RESIDENT: k_tc_fc4_pair.
+//
+// The generic kernel (k_tc_dense<256, FC4>) moves 384 KB of operands per 128 x 256 tile through L2 for 6.1k cycles of MMA
+// work — 63 B/clk per SM where the L2 path delivers ~32 — and ran at 44 % tensor-pipe activity.  Here a pair of CTAs computes
+// 256 rows x 256 columns per tile with ONE cta_group::2 MMA stream: each CTA keeps ITS 128 rows of A (all of K = 256, hi and
+// lo planes: 128 KB) resident in shared memory for as long as the pair stays on the same row block, and streams only its HALF
+// of the tile's B columns (32 KB per K = 64 stage, 3 stages): 128 KB per tile per CTA, 21 B/clk.  Tiles are dealt out as one
+// contiguous run per pair in (row-block, column-tile) order, so A is reloaded about once per 16 tiles.
+//   barriers per CTA: full[s] (own B stage landed), empty[s] / acc_full[b] / a_free (multicast commits of the leader),
+//   a_full (own A landed); in the leader also peer_full[s], peer_a (relay from rank 1) and acc_empty[b] (8 epilogue warps of
+//   each CTA).
+// =======================================================================================
+struct Fc4Pair {
+    static constexpr int NT = 256, NS = 3;
+    static constexpr int A_CHUNK = 2 * 8 * 128 * 16;        // 32 KB: one K = 64 chunk of this CTA's 128 rows, [hi|lo][kc 8][128][8]
+    static constexpr int A_BYTES = 4 * A_CHUNK;             // 128 KB
+    static constexpr int B_STAGE = 2 * 8 * 128 * 16;        // 32 KB: [hi|lo][kc 8][this CTA's 128 of the 256 columns][8]
+    static constexpr int SMEM = A_BYTES + NS * B_STAGE + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one())
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pair(const DenseParams p) {
+    using P = Fc4Pair;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smAres = smem;
+    uint8_t* smB = smem + P::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P::A_BYTES + P::NS * P::B_STAGE);
+    uint64_t* full = bars;                    // [NS]
+    uint64_t* peer_full = full + P::NS;       // [NS]  (leader)
+    uint64_t* empty = peer_full + P::NS;      // [NS]
+    uint64_t* acc_full = empty + P::NS;       // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]   (leader)
+    uint64_t* a_full = acc_empty + 2;         // [1]
+    uint64_t* peer_a = a_full + 1;            // [1]   (leader)
+    uint64_t* a_free = peer_a + 1;            // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P::NS; ++i) { mbar_init(&full[i], 1); mbar_init(&peer_full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+        mbar_init(a_full, 1); mbar_init(peer_a, 1); mbar_init(a_free, 1);
+        fence_barrier_init();
+    }
+    if (warp == 10) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * P::NT) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // tiles in (row block of 256, column tile) order; this pair's contiguous run [t0, t1)
+    const int mtiles = (p.nrows + 127) / 128, mpairs = (mtiles + 1) / 2;
+    const long long total = (long long)mpairs * p.ntn;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int t0 = (int)(total * pair / npairs), t1 = (int)(total * (pair + 1) / npairs);
+    const int nplanes = p.nprod == 3 ? 2 : 1;
+
+    if (warp == 8) {          // producer (both CTAs): own A rows when the row block changes, own half of the B columns per stage
+        if (lane == 0) {
+            int cnt = 0, loads = 0, cur_mp = -1;
+            for (int tile = t0; tile < t1; ++tile) {
+                const int mp = tile / p.ntn, nt = tile % p.ntn;
+                if (mp != cur_mp) {
+                    cur_mp = mp;
+                    if (loads > 0) mbar_wait(a_free, (uint32_t)(loads - 1) & 1u);      // every MMA on the previous rows has completed
+                    ++loads;
+                    const int mt = 2 * mp + (int)rank;
+                    mbar_expect_tx(a_full, nplanes == 2 ? P::A_BYTES : P::A_BYTES / 2);
+                    for (int kch = 0; kch < 4; ++kch)
+                        for (int pl = 0; pl < nplanes; ++pl)
+                            for (int kc = 0; kc < 8; ++kc)
+                                bulk_load(smAres + kch * P::A_CHUNK + (pl * 8 + kc) * 2048,
+                                          p.a + pl * p.a_plane + (size_t)(kch * 8 + kc) * p.a_kc_stride + (size_t)mt * 128 * 8, 2048, a_full);
+                }
+                for (int kch = 0; kch < 4; ++kch, ++cnt) {
+                    const int s = cnt % P::NS;
+                    mbar_wait(&empty[s], (((uint32_t)(cnt / P::NS)) & 1u) ^ 1u);
+                    uint8_t* sb = smB + (size_t)s * P::B_STAGE;
+                    mbar_expect_tx(&full[s], nplanes == 2 ? P::B_STAGE : P::B_STAGE / 2);
+                    const uint8_t* blk = p.wpack + ((size_t)nt * 4 + kch) * 65536;      // [hi 32 KB | lo 32 KB], each [kc 8][256][8]
+                    for (int pl = 0; pl < nplanes; ++pl)
+                        for (int kc = 0; kc < 8; ++kc)
+                            bulk_load(sb + (pl * 8 + kc) * 2048, blk + (size_t)pl * 32768 + ((size_t)kc * 256 + 128 * rank) * 16, 2048, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 9 && rank == 1) {   // relay (peer): tell the leader what has landed here
+        if (lane == 0) {
+            int cnt = 0, loads = 0, cur_mp = -1;
+            for (int tile = t0; tile < t1; ++tile) {
+                const int mp = tile / p.ntn;
+                if (mp != cur_mp) {
+                    cur_mp = mp;
+                    mbar_wait(a_full, (uint32_t)loads & 1u);
+                    ++loads;
+                    mbar_arrive_remote_relaxed(peer_a, 0);
+                }
+                for (int kch = 0; kch < 4; ++kch, ++cnt) {
+                    const int s = cnt % P::NS;
+                    mbar_wait(&full[s], ((uint32_t)(cnt / P::NS)) & 1u);
+                    mbar_arrive_remote_relaxed(&peer_full[s], 0);
+                }
+            }
+        }
+    } else if (warp == 9) {   // MMA issuer (leader): converged warp, one elected lane issues
+        const uint32_t idesc = umma2_idesc(P::NT);
+        const uint32_t a_res = smem_u32(smAres);
+        int it = 0, cnt = 0, loads = 0, cur_mp = -1;
+        for (int tile = t0; tile < t1; ++tile, ++it) {
+            const int mp = tile / p.ntn;
+            const int buf = it & 1;
+            mbar_wait_cluster(&acc_empty[buf], (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            if (mp != cur_mp) {
+                cur_mp = mp;
+                mbar_wait(a_full, (uint32_t)loads & 1u);
+                mbar_wait_cluster(peer_a, (uint32_t)loads & 1u);
+                ++loads;
+            }
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)(buf * P::NT);
+            for (int kch = 0; kch < 4; ++kch, ++cnt) {
+                const int s = cnt % P::NS;
+                const uint32_t ph = ((uint32_t)(cnt / P::NS)) & 1u;
+                mbar_wait(&full[s], ph);
+                mbar_wait_cluster(&peer_full[s], ph);
+                tc_fence_after();
+                const uint32_t a_base = a_res + (uint32_t)(kch * P::A_CHUNK);
+                const uint32_t b_base = smem_u32(smB + (size_t)s * P::B_STAGE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t a_hi = umma_desc(a_base + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                    const uint64_t b_hi = umma_desc(b_base + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                    umma2_bf16(d, a_hi, b_hi, idesc, (kch == 0 && k == 0) ? 0u : 1u);
+                    if (nplanes == 2) {
+                        const uint64_t a_lo = umma_desc(a_base + 16384u + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                        const uint64_t b_lo = umma_desc(b_base + 16384u + (uint32_t)(2 * k) * 2048u, 2048, 128);
+                        umma2_bf16(d, a_lo, b_hi, idesc, 1u);
+                        umma2_bf16(d, a_hi, b_lo, idesc, 1u);
+                    }
+                }
+                umma2_commit(&empty[s]);
+            }
+            umma2_commit(&acc_full[buf]);
+            // last tile on these rows: once its MMAs are through, the resident A may be replaced
+            if (tile + 1 < t1 && (tile + 1) / p.ntn != mp) umma2_commit(a_free);
+        }
+    } else if (warp < 8) {    // epilogue (both CTAs): this CTA's 128 rows x 256 columns
+        const int ew = warp & 3, half = warp >> 2;
+        const int m = ew * 32 + lane;
+        int it = 0;
+        for (int tile = t0; tile < t1; ++tile, ++it) {
+            const int buf = it & 1;
+            const int mp = tile / p.ntn, nt = tile % p.ntn;
+            const int row = (2 * mp + (int)rank) * 128 + m;
+            mbar_wait(&acc_full[buf], ((uint32_t)(it >> 1)) & 1u);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * P::NT + half * (P::NT / 2));
+#pragma unroll 1
+            for (int c0 = 0; c0 < P::NT / 2; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tbase + c0, r);
+                if (c0 + 32 >= P::NT / 2) {       // this warp's share of the accumulator sits in registers: hand the buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rank == 0) mbar_arrive_relaxed(&acc_empty[buf]);
+                        else mbar_arrive_remote_relaxed(&acc_empty[buf], 0);
+                    }
+                }
+                if (row >= p.nrows) continue;
+                fc4_store32(p, r, row, nt, nt * P::NT + half * (P::NT / 2) + c0);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 10) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * P::NT) : "memory");
 }
 
 using CfgCt1 = Cfg<TrCt1>;   // 144 KB of weights + 3 x 22.5 KB halo planes
@@ -1627,6 +1893,7 @@ int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* e
             cudaFuncSetAttribute(k_tc_conv<CfgQc2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_ct23, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_fc4_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Fc4Pair::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<256, EPI_FC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, EPI_FC4>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<128, EPI_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, EPI_HIDDEN>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<64, EPI_CONV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<64, EPI_CONV4>::SMEM) != cudaSuccess) {
@@ -1818,6 +2085,15 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
     // (an A-resident variant — m-tile's A kept in shared memory, B streamed in K = 32 stages through a 3-slot ring — was
     // measured 11 % SLOWER, 3.46 vs 3.11 ms per rollout: with 96 KB instead of 192 KB of loads in flight the kernel is
     // bound by load latency x bytes in flight, not by the L2 traffic that variant saves)
+    static const bool pairs = !(getenv("DAI_TC_FC4_PAIR") && atoi(getenv("DAI_TC_FC4_PAIR")) == 0);     // A/B switch (experiments)
+    if (pairs) {
+        // CTA pairs with A resident (k_tc_fc4_pair): needs rows_pad to cover whole 256-row blocks (run_decoder pads by 256)
+        const int mpairs = ((nrows + 127) / 128 + 1) / 2;
+        const long long total = (long long)mpairs * 64;
+        const int npairs = (int)std::max<long long>(1, std::min<long long>(total, sms / 2));
+        k_tc_fc4_pair<<<2 * npairs, 384, Fc4Pair::SMEM, st>>>(p);
+        return 1;
+    }
     k_tc_dense<256, EPI_FC4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, EPI_FC4>::SMEM, st>>>(p);
     return 1;
 }
@@ -1828,7 +2104,7 @@ size_t tc_ct23_scratch_bytes(int nrows) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int npairs = std::max(1, std::min((nrows + 1) / 2, sms / 2));
-    return (size_t)(4 * npairs) * 65536 * 4;          // 2 CTAs x 2 images x (32*32*64 elements x hi/lo bf16)
+    return (size_t)(4 * npairs) * F23::SCR_IMAGE;     // 2 CTAs x 2 images x (32*32*64 elements x hi/lo bf16)
 }
 
 int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void* act1, void* scratch, void* act3, int nrows,
@@ -1877,7 +2153,7 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F23::THREADS); cfg.dynamicSmemBytes = F23::SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     if (l2_state == 1) {
-        const size_t bytes = (size_t)srows * 65536 * 4;
+        const size_t bytes = (size_t)srows * F23::SCR_IMAGE;
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = scratch;
         attr[0].val.accessPolicyWindow.num_bytes = std::min(bytes, l2_win_max);
@@ -1902,7 +2178,7 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
         }
         if (printed++ % 23 == 3)
             fprintf(stderr, "[tc counters] ct2+ct3 pair kernel rows %d: per leader cycles: mma loop %.0f (wait acc_empty %.0f, wait a_full %.0f) | "
-                    "ct3 epilogue: loop %.0f (wait acc_full %.0f) | ct2 epilogue busy %.0f (proxy fence %.0f) | images %.1f => %.0f cycles per image\n",
+                    "ct3 epilogue: loop %.0f (wait acc_full %.0f) | ct2 epilogue busy %.0f | a_full wait on ct2 tiles %.0f | images %.1f => %.0f cycles per image\n",
                     nrows, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[3], a[3] > 0 ? a[0] / a[3] : 0.0);
     }
     return 1;
@@ -1918,10 +2194,10 @@ int tc_decoder_chunk(const TcWeights& tw, const DevWeights& w, int precision, co
     if ((rc = tc_fc4(tw, w, precision, h3b, rows_pad, row0, mask, nrows, act0, st, err)) < 0) return -1;
     T.end(st);
     n += rc;
-    // ct2 -> ct3 as ONE kernel (k_tc_ct23) is opt-in (env DAI_TC_FUSE23=1): it is parity-green and keeps the 256 KB/row
-    // activation out of HBM reads, but measured 2.4 % SLOWER end to end than the two kernels (profiles/README.md, round 2),
-    // so the two-kernel path stays the default.
-    static const bool fuse23 = getenv("DAI_TC_FUSE23") && atoi(getenv("DAI_TC_FUSE23")) != 0;
+    // ct2 -> ct3 run as ONE kernel (k_tc_ct23): the 256 KB/row activation between them stays in an L2-resident scratch (DRAM
+    // traffic of the two layers 3.02 -> 1.37 GB per 4800 rows) and the pair is ~1 % faster end to end than the two kernels.
+    // env DAI_TC_FUSE23=0 selects the two separate kernels (A/B, and the reference for tests/test_gpu_layers.py).
+    static const bool fuse23 = !(getenv("DAI_TC_FUSE23") && atoi(getenv("DAI_TC_FUSE23")) == 0);
     const void* in[3] = {act0, act1, act2};
     void* out[3] = {act1, act2, act3};
     for (int layer = 1; layer <= 3; ++layer) {

@@ -69,9 +69,9 @@ def test_fused_ct2_ct3_pair_kernel_matches_fp32(eng, rows):
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
     assert err <= 4e-5 * max(scale, 1.0), "rows %d: max err %.3e (scale %.3e)" % (rows, err, scale)
-    # and the same numbers as the two separate tensor-core kernels (same products, same accumulation order; the test
-    # hook re-splits ct2's output into hi/lo, which can move a rounding tie)
+    # and the same numbers as the two separate tensor-core kernels up to fp32 accumulation order (same products; the pair
+    # kernel issues them plane-major)
     sep = eng.debug_layer(3, "bf16x3", eng.debug_layer(2, "bf16x3", x))
-    assert (got - sep).abs().max().item() <= 2e-6 * max(scale, 1.0), "rows %d: fused differs from ct2 then ct3 by %.3e" % (rows, (got - sep).abs().max().item())
+    assert (got - sep).abs().max().item() <= 1e-5 * max(scale, 1.0), "rows %d: fused differs from ct2 then ct3 by %.3e" % (rows, (got - sep).abs().max().item())
     fast = eng.debug_layer(23, "bf16x1", x)
     assert (fast - ref).abs().max().item() <= 3e-2 * max(scale, 1.0)
