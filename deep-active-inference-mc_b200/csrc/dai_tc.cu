@@ -666,15 +666,33 @@ struct DenseParams {
     NoiseKey nk;
     NoiseRows nr;
     int32_t layer;               // dropout site = nr.site[set] + layer
+    long long* counters;         // experiments only (DAI_TC_COUNTERS, pair FC4): per CTA {mma loop, wait acc_empty, wait own B, wait peer B, wait A, tiles}
 };
 
 // FC4 epilogue for 32 accumulator columns of one row: bias + ReLU + MC-dropout bit + hi/lo split + stores.
 // FC4 column order (chosen on the host): n = ((pg*8 + kc)*4 + pl)*8 + e for pixel 4*pg + pl, channel 8*kc + e.  A
 // 256-column tile is one group of 4 pixels x 64 channels and 32 consecutive columns are 4 pixels x 8 channels of one
 // kc: 64 contiguous bytes of the blocked plane -> two 256-bit stores per plane.
-__device__ __forceinline__ void fc4_store32(const DenseParams& p, const uint32_t (&r)[32], int row, int nt, int n0) {
+// The inputs of that epilogue which do not depend on the accumulator, requested BEFORE the warp waits for the tile's MMAs:
+// the row's dropout words of the warp's 128 columns (one 16-byte load) and, per 32-column chunk, this lane's one bias value
+// (lane j holds bias[n + j]; the chunk code broadcasts it with shuffles).  Loading them inside the chunk loop left their
+// global-memory latency — a scattered 2 KB-stride mask word and 32 broadcast bias loads per chunk — exposed four times per tile,
+// and with two accumulator buffers that epilogue, not the operand stream, paced the kernel (measured: a version with A resident
+// and half the B traffic ran no faster).
+struct Fc4Pre {
+    uint4 mw;
+    float b[4];
+};
+__device__ __forceinline__ Fc4Pre fc4_prefetch(const DenseParams& p, int row, int n_base, int lane) {
+    Fc4Pre f;
+    f.mw = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (p.mask && row < p.nrows) f.mw = __ldg(reinterpret_cast<const uint4*>(p.mask + (size_t)row * 512 + (n_base >> 5)));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f.b[c] = __ldg(p.bias + n_base + c * 32 + lane);
+    return f;
+}
+__device__ __forceinline__ void fc4_store32(const DenseParams& p, const uint32_t (&r)[32], int row, int nt, int n0, uint32_t mw, float bias_lane) {
     const size_t plane = (size_t)p.nrows * 16384;
-    const uint32_t mw = p.mask ? p.mask[(size_t)row * 512 + (n0 >> 5)] : 0xffffffffu;
     const float s2 = p.mask ? 2.0f : 1.0f;
     const int kc = (n0 >> 5) & 7;
     uint32_t hi[4][4], lo[4][4];
@@ -683,9 +701,10 @@ __device__ __forceinline__ void fc4_store32(const DenseParams& p, const uint32_t
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j0 = pl * 8 + 2 * e, j1 = j0 + 1;
-            split2(r[j0], r[j1], __ldg(p.bias + n0 + j0), __ldg(p.bias + n0 + j1),
+            split2(r[j0], r[j1], __shfl_sync(0xffffffffu, bias_lane, j0), __shfl_sync(0xffffffffu, bias_lane, j1),
                    ((mw >> j0) & 1u) ? s2 : 0.0f, ((mw >> j1) & 1u) ? s2 : 0.0f, hi[pl][e], lo[pl][e]);
         }
+    if (row >= p.nrows) return;
     const size_t o = (((size_t)row * 8 + kc) * 256 + nt * 4) * 8;
     st_global_256(p.out + o, hi[0], hi[1]);
     st_global_256(p.out + o + 16, hi[2], hi[3]);
@@ -794,6 +813,8 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
             const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             const int nt = tile / mtiles, mt = tile % mtiles;
             const int row = mt * 128 + m;
+            Fc4Pre pre{};
+            if (EPI == EPI_FC4) pre = fc4_prefetch(p, row, nt * NT + half * (NT / 2), lane);
             mbar_wait(&acc_full[buf], aph);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * NT + half * (NT / 2));
@@ -816,11 +837,15 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive_relaxed(&acc_empty[buf]);
                 }
-                if (row >= p.nrows) continue;
                 const int n0 = nt * NT + half * (NT / 2) + c0;
                 if (EPI == EPI_FC4) {
-                    fc4_store32(p, r, row, nt, n0);
-                } else {
+                    const int c = c0 >> 5;
+                    fc4_store32(p, r, row, nt, n0, c == 0 ? pre.mw.x : c == 1 ? pre.mw.y : c == 2 ? pre.mw.z : pre.mw.w,
+                                c == 0 ? pre.b[0] : c == 1 ? pre.b[1] : c == 2 ? pre.b[2] : pre.b[3]);
+                    continue;
+                }
+                if (row >= p.nrows) continue;
+                {
                     const int wsel = (half * (NT / 2) + c0) >> 5;       // which 32-bit word of the Philox block
                     const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
 #pragma unroll
@@ -1534,23 +1559,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
         const uint32_t idesc = umma2_idesc(P::NT);
         const uint32_t a_res = smem_u32(smAres);
         int it = 0, cnt = 0, loads = 0, cur_mp = -1;
+        const bool timing = p.counters != nullptr;
+        long long t_begin = 0, w_acc = 0, w_b = 0, w_pb = 0, w_a = 0, tw = 0;
+        if (timing) t_begin = clock64();
         for (int tile = t0; tile < t1; ++tile, ++it) {
             const int mp = tile / p.ntn;
             const int buf = it & 1;
+            if (timing) tw = clock64();
             mbar_wait_cluster(&acc_empty[buf], (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            if (timing) { w_acc += clock64() - tw; tw = clock64(); }
             if (mp != cur_mp) {
                 cur_mp = mp;
                 mbar_wait(a_full, (uint32_t)loads & 1u);
                 mbar_wait_cluster(peer_a, (uint32_t)loads & 1u);
                 ++loads;
             }
+            if (timing) w_a += clock64() - tw;
             tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)(buf * P::NT);
             for (int kch = 0; kch < 4; ++kch, ++cnt) {
                 const int s = cnt % P::NS;
                 const uint32_t ph = ((uint32_t)(cnt / P::NS)) & 1u;
+                if (timing) tw = clock64();
                 mbar_wait(&full[s], ph);
+                if (timing) { w_b += clock64() - tw; tw = clock64(); }
                 mbar_wait_cluster(&peer_full[s], ph);
+                if (timing) w_pb += clock64() - tw;
                 tc_fence_after();
                 const uint32_t a_base = a_res + (uint32_t)(kch * P::A_CHUNK);
                 const uint32_t b_base = smem_u32(smB + (size_t)s * P::B_STAGE);
@@ -1572,6 +1606,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
             // last tile on these rows: once its MMAs are through, the resident A may be replaced
             if (tile + 1 < t1 && (tile + 1) / p.ntn != mp) umma2_commit(a_free);
         }
+        if (timing && lane == 0) {
+            long long* c = p.counters + (size_t)blockIdx.x * 8;
+            c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_b; c[3] = w_pb; c[4] = w_a; c[5] = t1 - t0;
+        }
     } else if (warp < 8) {    // epilogue (both CTAs): this CTA's 128 rows x 256 columns
         const int ew = warp & 3, half = warp >> 2;
         const int m = ew * 32 + lane;
@@ -1580,6 +1618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
             const int buf = it & 1;
             const int mp = tile / p.ntn, nt = tile % p.ntn;
             const int row = (2 * mp + (int)rank) * 128 + m;
+            const Fc4Pre pre = fc4_prefetch(p, row, nt * P::NT + half * (P::NT / 2), lane);
             mbar_wait(&acc_full[buf], ((uint32_t)(it >> 1)) & 1u);
             tc_fence_after();
             const uint32_t tbase = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * P::NT + half * (P::NT / 2));
@@ -1595,8 +1634,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
                         else mbar_arrive_remote_relaxed(&acc_empty[buf], 0);
                     }
                 }
-                if (row >= p.nrows) continue;
-                fc4_store32(p, r, row, nt, nt * P::NT + half * (P::NT / 2) + c0);
+                const int c = c0 >> 5;
+                fc4_store32(p, r, row, nt, nt * P::NT + half * (P::NT / 2) + c0,
+                            c == 0 ? pre.mw.x : c == 1 ? pre.mw.y : c == 2 ? pre.mw.z : pre.mw.w,
+                            c == 0 ? pre.b[0] : c == 1 ? pre.b[1] : c == 2 ? pre.b[2] : pre.b[3]);
             }
         }
     }
@@ -2091,7 +2132,25 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
         const int mpairs = ((nrows + 127) / 128 + 1) / 2;
         const long long total = (long long)mpairs * 64;
         const int npairs = (int)std::max<long long>(1, std::min<long long>(total, sms / 2));
+        static long long* dbg_counters = nullptr;
+        static const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;                // experiments only
+        if (want_counters) {
+            if (!dbg_counters) cudaMalloc(&dbg_counters, 8 * 8 * 512);
+            cudaMemsetAsync(dbg_counters, 0, 8 * 8 * 512, st);
+            p.counters = dbg_counters;
+        }
         k_tc_fc4_pair<<<2 * npairs, 384, Fc4Pair::SMEM, st>>>(p);
+        if (want_counters) {
+            static int printed = 0;
+            cudaStreamSynchronize(st);
+            long long hc[8 * 512];
+            cudaMemcpy(hc, dbg_counters, sizeof(long long) * 8 * 2 * npairs, cudaMemcpyDeviceToHost);
+            double a[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 2 * npairs; i += 2) for (int j = 0; j < 6; ++j) a[j] += (double)hc[i * 8 + j] / npairs;
+            if (printed++ % 23 == 3)
+                fprintf(stderr, "[tc counters] fc4 pair kernel rows %d: per leader cycles: mma loop %.0f (wait acc_empty %.0f, own B %.0f, peer B %.0f, A %.0f) | "
+                        "tiles %.1f => %.0f cycles per tile\n", nrows, a[0], a[1], a[2], a[3], a[4], a[5], a[5] > 0 ? a[0] / a[5] : 0.0);
+        }
         return 1;
     }
     k_tc_dense<256, EPI_FC4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<256, EPI_FC4>::SMEM, st>>>(p);

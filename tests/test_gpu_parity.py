@@ -129,11 +129,21 @@ def test_abi_rejects_bad_arguments_without_crashing():
 
 
 def test_large_batch_and_many_samples_chunking():
-    """More decoder rows than one activation chunk (1024) and more encoder rows than one chunk (2048): chunk
-    boundaries must not change the result — compare a big batched call with the same rows evaluated separately."""
+    """More decoder rows than one activation chunk and more encoder rows than one chunk: chunk boundaries must not
+    change the result — a big batched call against the same rows evaluated separately, and a handle with small
+    decoder chunks (env DAI_DEC_CHUNK, read at dai_create: 7 chunks of 1056 rows, odd row counts for the CTA-pair
+    kernels) against the default one-chunk handle, bit for bit."""
+    import os
+    from dai_b200.torchmodel import ActiveInferenceModel
     m = _model("w0", "bf16x3")
     eng = m._engine
     m._sync()
+    os.environ["DAI_DEC_CHUNK"] = "1031"
+    try:
+        small = ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, precision="bf16x3", device="cuda:0").load_numpy_weights(cases.weights_for("w0"))
+    finally:
+        del os.environ["DAI_DEC_CHUNK"]
+    small._sync()
     s0 = torch.from_numpy(np.random.default_rng(11).standard_normal((8, 10)).astype(np.float32)).cuda()
     pi = torch.eye(4, device="cuda").repeat(2, 1)
     eng.set_rng(5, 0)
@@ -144,6 +154,9 @@ def test_large_batch_and_many_samples_chunking():
     b = eng.calculate_G(s0, pi, 300, shard=(100, 300))
     assert torch.allclose(a["sums"] + b["sums"], big["sums"], rtol=1e-9, atol=1e-6)
     assert torch.equal(a["ps1"], big["ps1"]) and torch.equal(b["po1"], big["po1"])
+    small._engine.set_rng(5, 0)
+    chunked = small._engine.calculate_G(s0, pi, 300)
+    assert torch.equal(chunked["sums"], big["sums"]) and torch.equal(chunked["po1"], big["po1"]) and torch.equal(chunked["G"], big["G"])
 
 
 # ---- BASELINE.json configs at full size ----------------------------------------------------------------------
