@@ -357,6 +357,13 @@ def main():
         d5, e5, _, _ = make_steps(1, 800, 15, sh5, None, 3, native=world > 1)
         ms5 = timed(d5, ks, 2)
         ms5e = timed(e5, ks, 1)
+        # the same partition with 16 roots per step (rows per rank as in the main line): how the 8-rank all-reduce partition
+        # scales when every rank has a full batch
+        d5b, _, _, _ = make_steps(16, 800, 15, sh5, None, 4, native=world > 1)
+        ms5b = timed(d5b, 2, 1)
+        extra["c5_sample_sharded_R16"] = {"value": 16.0 / (ms5b * 1e-3), "unit": "rollouts/s", "ms_per_step": ms5b, "n_gpus": world,
+                                          "scaling": "strong", "config": "configs[4] with 16 roots per step: N=800 samples over all ranks, T=15",
+                                          "algorithmic_tflops": 16 * rollout_flops(800, 15) / (ms5b * 1e-3) / 1e12}
         extra["c5_sample_sharded"] = {"value": 1.0 / (ms5 * 1e-3), "e2e": 1.0 / (ms5e * 1e-3), "unit": "rollouts/s", "ms_per_step": ms5,
                                       "n_gpus": world, "scaling": "strong", "samples_per_rank": (sh5[1] - sh5[0]) if sh5 else 800,
                                       "collective": ("one ncclAllReduce(sum) of (4,4) float64 over %d ranks per rollout, issued inside "

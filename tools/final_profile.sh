@@ -1,12 +1,12 @@
 #!/bin/bash
-# Round-1 closing measurements: roots sweep, launch list, ncu full of the conv kernels.
+# Round-2 closing profiles on one B200 (the numbers under profiles/r02_*): bench line, launch list, ncu --set full captures.
+# Never a bench value: ncu serialises and replays kernels (compare SHARES, not absolutes).
+set -x
 mkdir -p gpurun_out
-for r in 8 32 64; do
-  python bench.py --steps 4 --no-cpu-baseline --roots $r 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('roots $r: %.1f rollouts/s, e2e %.1f' % (d['value'], d['e2e']['value']), d['clocks']['sm_mhz'], {k: round(v,2) for k,v in d['roofline']['step_share_ms'].items()})"
-done
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-cat gpurun_out/bench_default.json | cut -c1-400
-ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 700 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --quick --roots 16 > gpurun_out/ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_tc_conv -s 20 -c 8 -o gpurun_out/prof_conv python bench.py --steps 1 --quick --roots 16 > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log | cut -c1-200
-ls -la gpurun_out/prof_conv.ncu-rep
+python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
+cut -c1-200 gpurun_out/r02_bench.json
+DAI_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 700 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --quick --no-extras --no-cpu-baseline > gpurun_out/r02_ncu_list.log 2>&1
+DAI_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_tc_ct23|k_tc_fc4_pair|k_tc_conv|k_ct4_gather|k_qs_conv1|k_fc4_mask" -s 30 -c 9 -o gpurun_out/r02_decoder -f python bench.py --no-extras --no-cpu-baseline --steps 1 --quick > gpurun_out/r02_ncu_full.log 2>&1
+tail -2 gpurun_out/r02_ncu_full.log | cut -c1-200
+DAI_GRAPHS=0 DAI_TC_FUSE23=0 DAI_TC_FC4_PAIR=0 timeout 900 ncu --set full --clock-control none -k "regex:k_tc_conv<.*TrCt[23]|k_tc_dense<256" -s 30 -c 3 -o gpurun_out/r02_separate -f python bench.py --no-extras --no-cpu-baseline --steps 1 --quick > gpurun_out/r02_ncu_sep.log 2>&1
+ls -la gpurun_out/r02_*.ncu-rep
