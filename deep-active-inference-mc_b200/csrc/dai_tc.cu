@@ -891,9 +891,11 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
 // so ct3's inputs were written one stage earlier and no role ever waits for the ct2 epilogue -> store -> TMA round trip.
 // TMEM: four 128-column slots used round-robin; a ct2 tile (256 columns) takes an aligned slot pair, a ct3 tile one
 // slot; one stage is exactly 3 turns of the ring.
-// Barriers per CTA: a_full[s] (own halo plane landed), a_empty[s] / acc_full[q] (multicast commits from the leader),
-// act2_ready[parity] (the ct2-epilogue warps: this CTA's scratch image is complete and visible to TMA);
-// in the leader also peer_full[s] (relay from rank 1) and acc_empty[q] (8 epilogue warps of each CTA).
+// Barriers: in the leader a_full[s] (BOTH CTAs' halo planes of slot s landed: the peer's TMA loads complete on the leader's
+// barrier, cp.async.bulk.tensor .cta_group::2) and acc_empty[q] (8 epilogue warps of each CTA); per CTA a_empty[s] /
+// acc_full[group][q] (multicast commits from the leader) and act2_ready[parity] (the ct2-epilogue warps: this CTA's scratch
+// image is complete and visible to TMA).  (The first version announced the peer's planes through a relay thread in
+// rank 1 and a second barrier per slot: 527 against 532 rollouts/s.)
 // =======================================================================================
 struct FusedParams {
     const uint8_t* wpack2;   // ct2 weights, [rank][half image]: per unit the rank's half of the B rows
@@ -932,21 +934,57 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// wait on a local mbarrier whose arrivals come from the peer CTA (acquire at cluster scope); bounded like mbar_wait
+// Wait on a local mbarrier whose arrivals come from the peer CTA, WITHOUT acquire semantics.  Everything the MMA issuer
+// waits for this way is either in tensor memory (ordered by tcgen05.fence::after_thread_sync) or was written by the async
+// proxy and is read by it; an .acquire.cluster wait instead compiles to a CCTL.IVALL (invalidate all of L1) on every
+// success — three per tile in the issuer's loop, ~150 cycles each.  Bounded like mbar_wait.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    const long long t0 = clock64();
+    long long t0 = 0;
     while (true) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (t0 == 0) t0 = clock64();                       // the clock is read only once the first probe has failed
+        else if (clock64() - t0 > 4000000000ll) __trap();
     }
+}
+// The same wait for a CONVERGED warp (the MMA issuer), leaving the loop on a warp-uniform vote: with a per-thread exit
+// condition the compiler treats everything the issuer's loop carries (slot and buffer counters, operand addresses) as
+// thread-varying and pays a VIADD + R2UR.BROADCAST for each descriptor of each MMA — 12 instructions per MMA on a warp that
+// shares its scheduler with three epilogue warps; with uniform control flow they stay in uniform registers.
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t parity) {
+    long long t0 = 0;
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (__all_sync(0xffffffffu, ok != 0)) return;
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+// one non-blocking probe of the same kind, by a converged warp
+__device__ __forceinline__ bool mbar_test_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return __all_sync(0xffffffffu, ok != 0) != 0;          // whole warp, uniform result (see mbar_wait_cluster_warp)
 }
 // Arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster, without memory-ordering semantics.
 // Everything handed over this way was written by the async proxy (TMA / bulk copies, whose completion the sender observed on
@@ -994,11 +1032,15 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ void tma_load_5d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4,
-                                                 uint64_t pol) {
+// A 5-D box load with an L2 eviction hint, issued by either CTA of a pair, its completion signalled on the LEADER's barrier (cta_group::2 lets the
+// mbarrier live in the peer CTA): the leader's a_full[s] then counts both CTAs' planes and no relay thread is needed.
+__device__ __forceinline__ void tma_load_5d_hint_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                      int c4, uint64_t pol) {
+    uint32_t lead_bar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(lead_bar) : "r"(smem_u32(bar)), "r"(0u));
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(lead_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
         : "memory");
 }
 __device__ __forceinline__ void st_global_256_hint(void* p, const uint32_t (&a)[4], const uint32_t (&b)[4], uint64_t pol) {
@@ -1059,8 +1101,8 @@ __host__ __device__ constexpr int pu_bytes() { return pu_woff<L>(pu_count<L>());
 // Plane-major order lets the hi plane's ring slot go back to the producer after two thirds of a tile's MMAs and gives the
 // lo plane's load that much more time: the ring holds only three tiles and the issuer runs about one tile ahead of the
 // tensor pipe, so with both planes waited for together the issuer spent 18 % of its time waiting for halos.
-template <int L, int PASS>
-__device__ __forceinline__ void issue_item_pair(uint32_t a16, uint32_t w16, uint32_t d0, bool x3) {
+template <int L, int PASS, bool X3>
+__device__ __forceinline__ void issue_item_pair(uint32_t a16, uint32_t w16, uint32_t d0) {
     constexpr int HX = 9, KC_STRIDE = 17 * 9 * 16, KCIN = 8, KSTEPS = 4;
     constexpr uint32_t A_TOP = (uint32_t)((HX * 16) >> 4) | (1u << 14);
     constexpr uint32_t B_TOP = (uint32_t)(128 >> 4) | (1u << 14);
@@ -1083,7 +1125,7 @@ __device__ __forceinline__ void issue_item_pair(uint32_t a16, uint32_t w16, uint
             const uint32_t b_hi = w16 + b_imm, b_lo = w16 + b_imm + (b_plane >> 4);
             if (PASS == 0) {
                 umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_hi, umma2_idesc(un.n), (un.init && k == 0) ? 0u : 1u);
-                if (x3) umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_lo, umma2_idesc(un.n), 1u);
+                if (X3) umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_lo, umma2_idesc(un.n), 1u);
             } else {
                 umma2_bf16_split<A_TOP, B_TOP>(lead, d, a, b_hi, umma2_idesc(un.n), 1u);
             }
@@ -1103,6 +1145,10 @@ constexpr int F23_LAST_CT2 = 4;
 __device__ __forceinline__ int item_layer(int k) { return (k == 0 || k == 3) ? 0 : ((k == 1 || k == 4) ? 1 : 2); }
 __device__ __forceinline__ int item_tile(int k) { return k < 3 ? 0 : (k < 5 ? 1 : k - 4); }
 
+// DBG = true is the experiments build (DAI_TC_COUNTERS): in the production instantiation no role carries a counter — a
+// single `if (timing && lane == 0)` inside the MMA issuer's loop makes the compiler give up on the warp being converged and
+// turns every descriptor of every MMA into VIADD + predicated R2UR.BROADCAST (10.8 instead of 5.3 instructions per MMA).
+template <bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F23::THREADS, 1)
 k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CUtensorMap tmapScr, const FusedParams p) {
     using C2 = F23::C2;
@@ -1113,8 +1159,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F23::W_BYTES + F23::SMEM_A);
     uint64_t* a_full = bars;                      // [NA]
     uint64_t* a_empty = a_full + F23::NA;         // [NA]
-    uint64_t* peer_full = a_empty + F23::NA;      // [NA]   (leader)
-    uint64_t* acc_full = peer_full + F23::NA;     // [2][4]: per epilogue group (0: ct2 items, 1: ct3 items) and TMEM buffer.  Each
+    uint64_t* acc_full = a_empty + F23::NA;       // [2][4]: per epilogue group (0: ct2 items, 1: ct3 items) and TMEM buffer.  Each
                                                   // group waits only for its own items, and a parity wait must never skip a
                                                   // phase — so the two groups cannot share a barrier.
     uint64_t* acc_empty = acc_full + 8;           // [4]    (leader; only the MMA issuer waits, item by item)
@@ -1124,16 +1169,17 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_w + 1);
     float* sbias2 = reinterpret_cast<float*>(tmem_slot + 2);   // [64]
     float* sbias3 = sbias2 + 64;                                // [32]
+    long long* whist = reinterpret_cast<long long*>(sbias3 + 32);   // [36] experiments only: the issuer's waits per item of the stage
 
-    // warps 0-7: ct3 epilogue; 8-11: ct2 epilogue; 12: halo producer; 13: MMA issuer (leader) / relay (peer);
+    // warps 0-7: ct3 epilogue; 8-11: ct2 epilogue; 12: halo producer; 13: MMA issuer (leader);
     // 14: TMEM allocator; 15: weight loader.  (TMEM lane quarter of an epilogue warp = warp % 4; the single-thread roles
     // sit in the highest warp ids, which the scheduler favours.)
     constexpr int W_PROD = 12, W_MMA = 13, W_ALLOC = 14, W_WGT = 15;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
     const uint32_t rank = cluster_ctarank();
     const int nplanes = p.nprod == 3 ? 2 : 1;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < F23::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&peer_full[i], 1); }
+        for (int i = 0; i < F23::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 8; ++i) mbar_init(&acc_full[i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&acc_empty[i], 16);     // 8 arrivals per CTA, whichever group owns the item
         for (int i = 0; i < 2; ++i) mbar_init(&act2_ready[i], 4);     // the 4 ct2-epilogue warps, once per image
@@ -1159,7 +1205,7 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
     const int pairs_total = (p.nrows + 1) / 2;
     const int J = pair < pairs_total ? (pairs_total - pair + npairs - 1) / npairs : 0;
     const int srow0 = (int)blockIdx.x * 2;           // this CTA's two scratch images
-    const bool timing = p.counters != nullptr;
+    const bool timing = DBG && p.counters != nullptr;
     // Every role numbers the items it walks with `seq` (items that exist in this stage, in list order): item seq uses
     // TMEM buffer seq & 3, in its (seq >> 2)-th use.
 #define F23_FOR_ITEMS(j, k, L, t)                                                   \
@@ -1187,9 +1233,12 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                     for (int pl = 0; pl < nplanes; ++pl, ++cnt) {
                         const int s = cnt % F23::NA;
                         mbar_wait(&a_empty[s], ((uint32_t)(cnt / F23::NA) & 1u) ^ 1u);
-                        mbar_expect_tx(&a_full[s], F23::PLANE);
-                        if (L == 2) tma_load_5d_hint(smA + (size_t)s * F23::PLANE, &tmapScr, &a_full[s], x0 * 8, y0, 0, srow0 + par, pl, pol_keep);
-                        else tma_load_5d_hint(smA + (size_t)s * F23::PLANE, &tmapIn, &a_full[s], x0 * 8, y0, 0, row, pl, pol_stream);
+                        uint8_t* dst = smA + (size_t)s * F23::PLANE;
+                        // both CTAs' planes complete on the leader's a_full[s] (the peer's bytes may land before the leader
+                        // has posted the expectation of this phase: the transaction count is signed)
+                        if (rank == 0) mbar_expect_tx(&a_full[s], 2 * F23::PLANE);
+                        if (L == 2) tma_load_5d_hint_pair(dst, &tmapScr, &a_full[s], x0 * 8, y0, 0, srow0 + par, pl, pol_keep);
+                        else tma_load_5d_hint_pair(dst, &tmapIn, &a_full[s], x0 * 8, y0, 0, row, pl, pol_stream);
                     }
                 }
             }
@@ -1207,76 +1256,125 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
                 mbar_arrive_remote_relaxed(peer_w, 0);
             }
         }
-    } else if (warp == W_MMA && rank == 1) {
-        // ===== relay (peer): tell the leader that this CTA's halo plane has landed =====
-        if (lane == 0) {
-            const int planes_total = J * (C2::TILES + C3::TILES) * nplanes;
-            for (int cnt = 0; cnt < planes_total; ++cnt) {
-                const int s = cnt % F23::NA;
-                mbar_wait(&a_full[s], (uint32_t)(cnt / F23::NA) & 1u);
-                mbar_arrive_remote_relaxed(&peer_full[s], 0);
-            }
-        }
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA && rank == 0) {
         // ===== MMA issuer (leader): the whole warp runs the loop converged, one elected lane issues =====
-        mbar_wait(w_full, 0);
-        mbar_wait_cluster(peer_w, 0);
+        mbar_wait_cluster_warp(w_full, 0);
+        mbar_wait_cluster_warp(peer_w, 0);
         tc_fence_after();
         const uint32_t w2a_16 = smem_u32(smW) >> 4, w2b_16 = smem_u32(smW + pu_bytes<0>()) >> 4,
                        w3_16 = smem_u32(smW + F23::W2_HALF) >> 4, a16 = smem_u32(smA) >> 4;
+        // The loop is software-pipelined over the passes.  Before a pass is issued the barriers of the NEXT pass are probed
+        // (item i's lo plane before its pass 0; item i+1's accumulator and hi plane before item i's pass 1) with a
+        // non-blocking test: the ring runs two tiles ahead, so the probe normally succeeds, and the next pass then follows the
+        // commits directly — the ~200 cycles of wait + commit + loop code per pass (measured: uniform over all items, i.e.
+        // latency of the code path, not starvation) overlap the tail of the queued MMAs instead of draining the tensor pipe.
+        // A probe that fails is waited for only AFTER everything already possible has been issued and committed: blocking
+        // earlier would delay this item's commits (and, on a one-image schedule, deadlock: the first ct3 halo needs the
+        // ct2 epilogue of the item being issued).
         int cnt = 0, seq = 0;
-        int s0 = 0, s1 = -1;
-        uint32_t ah = 0, al = 0;
         long long t_begin = 0, w_acc = 0, w_a = 0, w_a2 = 0, tw = 0;
-        if (timing) t_begin = clock64();
-        for (int j = 0; j <= J; ++j) {
-            F23_FOR_ITEMS(j, k, L, t) {
-                (void)t;
-                const int buf = seq & 3;
-                if (timing) tw = clock64();
-                mbar_wait_cluster(&acc_empty[buf], ((uint32_t)(seq >> 2) & 1u) ^ 1u);
-                ++seq;
-                if (timing) { w_acc += clock64() - tw; tw = clock64(); }
-                const uint32_t d0 = tmem_base + (uint32_t)(buf * 128);
-                // pass 0 on the hi plane
-                if (L != 1) {                                          // a new tile: wait for its hi plane
-                    s0 = cnt % F23::NA;
-                    const uint32_t ph0 = (uint32_t)(cnt / F23::NA) & 1u;
-                    mbar_wait(&a_full[s0], ph0);
-                    mbar_wait_cluster(&peer_full[s0], ph0);
-                    ++cnt;
-                    ah = a16 + (uint32_t)s0 * (F23::PLANE >> 4);
-                }
-                if (timing) { const long long dt = clock64() - tw; w_a += dt; if (L != 2) w_a2 += dt; }
-                tc_fence_after();
-                if (L == 0) issue_item_pair<0, 0>(ah, w2a_16, d0, nplanes == 2);
-                else if (L == 1) issue_item_pair<1, 0>(ah, w2b_16, d0, nplanes == 2);
-                else issue_item_pair<2, 0>(ah, w3_16, d0, nplanes == 2);
-                if (L != 0) umma2_commit(&a_empty[s0]);                // the hi plane is done with (after parity 1 for ct2)
-                if (nplanes == 2) {
-                    // pass 1 on the lo plane
-                    if (timing) tw = clock64();
-                    if (L != 1) {
-                        s1 = cnt % F23::NA;
-                        const uint32_t ph1 = (uint32_t)(cnt / F23::NA) & 1u;
-                        mbar_wait(&a_full[s1], ph1);
-                        mbar_wait_cluster(&peer_full[s1], ph1);
-                        ++cnt;
-                        al = a16 + (uint32_t)s1 * (F23::PLANE >> 4);
-                    }
-                    if (timing) { const long long dt = clock64() - tw; w_a += dt; if (L != 2) w_a2 += dt; }
-                    tc_fence_after();
-                    if (L == 0) issue_item_pair<0, 1>(al, w2a_16, d0, true);
-                    else if (L == 1) issue_item_pair<1, 1>(al, w2b_16, d0, true);
-                    else issue_item_pair<2, 1>(al, w3_16, d0, true);
-                    if (L != 0) umma2_commit(&a_empty[s1]);
-                }
-                umma2_commit(&acc_full[(L == 2 ? 4 : 0) + buf]);
+        if (timing) {
+            if (lane == 0) for (int i = 0; i < 36; ++i) whist[i] = 0;
+            __syncwarp();
+            t_begin = clock64();
+        }
+        auto exists = [&](int j, int k) { return item_layer(k) == 2 ? j >= 1 : j < J; };
+        auto advance = [&](int& j, int& k) {               // next item of the schedule; j > J when there is none
+            do {
+                if (++k == F23_ITEMS) { k = 0; ++j; }
+            } while (j <= J && !exists(j, k));
+        };
+        struct Prep { int buf, s_hi, k; uint32_t d0, ah, ph_acc, ph_hi; bool acc_ok, hi_ok; };
+        Prep cur{}, nxt{};
+        // accumulator buffer and hi-plane slot of the next item in the schedule (no waiting); an item of ct2's parity 1 reads
+        // the planes of the item before it
+        auto begin = [&](int k, const Prep& prev, Prep& out) {
+            out.k = k;
+            out.buf = seq & 3;
+            out.ph_acc = ((uint32_t)(seq >> 2) & 1u) ^ 1u;
+            ++seq;
+            out.d0 = tmem_base + (uint32_t)(out.buf * 128);
+            out.acc_ok = false;
+            if (item_layer(k) != 1) {
+                out.s_hi = cnt % F23::NA;
+                out.ph_hi = (uint32_t)(cnt / F23::NA) & 1u;
+                ++cnt;
+                out.ah = a16 + (uint32_t)out.s_hi * (F23::PLANE >> 4);
+                out.hi_ok = false;
+            } else {
+                out.s_hi = prev.s_hi; out.ah = prev.ah; out.ph_hi = prev.ph_hi;
+                out.hi_ok = true;
             }
+        };
+        auto probe = [&](Prep& q) {
+            if (!q.acc_ok) q.acc_ok = mbar_test_cluster(&acc_empty[q.buf], q.ph_acc);
+            if (!q.hi_ok) q.hi_ok = mbar_test_cluster(&a_full[q.s_hi], q.ph_hi);
+        };
+        auto finish = [&](Prep& q) {
+            if (!q.acc_ok) {
+                if (timing) tw = clock64();
+                mbar_wait_cluster_warp(&acc_empty[q.buf], q.ph_acc);
+                if (timing) { const long long dt = clock64() - tw; w_acc += dt; if (lane == 0) whist[24 + q.k] += dt; }
+            }
+            if (!q.hi_ok) {
+                if (timing) tw = clock64();
+                mbar_wait_cluster_warp(&a_full[q.s_hi], q.ph_hi);
+                if (timing) { const long long dt = clock64() - tw; w_a += dt; if (item_layer(q.k) != 2) w_a2 += dt; if (lane == 0) whist[q.k] += dt; }
+            }
+            q.acc_ok = q.hi_ok = true;
+        };
+        int j = 0, k = -1;
+        advance(j, k);
+        if (j <= J) { begin(k, cur, cur); finish(cur); }
+        int s_lo = 0;
+        uint32_t al = 0;
+        while (j <= J) {
+            const int L = item_layer(k);
+            bool lo_ok = true;
+            uint32_t ph_lo = 0;
+            if (nplanes == 2 && L != 1) {                              // this item's lo plane: probed before pass 0 goes out
+                s_lo = cnt % F23::NA;
+                ph_lo = (uint32_t)(cnt / F23::NA) & 1u;
+                ++cnt;
+                al = a16 + (uint32_t)s_lo * (F23::PLANE >> 4);
+                lo_ok = mbar_test_cluster(&a_full[s_lo], ph_lo);
+            }
+            tc_fence_after();
+            if (nplanes == 2) {
+                if (L == 0) issue_item_pair<0, 0, true>(cur.ah, w2a_16, cur.d0);
+                else if (L == 1) issue_item_pair<1, 0, true>(cur.ah, w2b_16, cur.d0);
+                else issue_item_pair<2, 0, true>(cur.ah, w3_16, cur.d0);
+            } else {
+                if (L == 0) issue_item_pair<0, 0, false>(cur.ah, w2a_16, cur.d0);
+                else if (L == 1) issue_item_pair<1, 0, false>(cur.ah, w2b_16, cur.d0);
+                else issue_item_pair<2, 0, false>(cur.ah, w3_16, cur.d0);
+            }
+            if (L != 0) umma2_commit(&a_empty[cur.s_hi]);              // the hi plane is done with (after parity 1 for ct2)
+            int jn = j, kn = k;
+            advance(jn, kn);
+            if (jn <= J) begin(kn, cur, nxt);
+            if (nplanes == 2) {
+                if (!lo_ok) {
+                    if (timing) tw = clock64();
+                    mbar_wait_cluster_warp(&a_full[s_lo], ph_lo);
+                    if (timing) { const long long dt = clock64() - tw; w_a += dt; if (L != 2) w_a2 += dt; if (lane == 0) whist[12 + k] += dt; }
+                }
+                if (jn <= J) probe(nxt);
+                tc_fence_after();
+                if (L == 0) issue_item_pair<0, 1, true>(al, w2a_16, cur.d0);
+                else if (L == 1) issue_item_pair<1, 1, true>(al, w2b_16, cur.d0);
+                else issue_item_pair<2, 1, true>(al, w3_16, cur.d0);
+                if (L != 0) umma2_commit(&a_empty[s_lo]);
+            }
+            umma2_commit(&acc_full[(L == 2 ? 4 : 0) + cur.buf]);
+            if (jn <= J) finish(nxt);
+            j = jn; k = kn; cur = nxt;
         }
         if (timing && lane == 0) {
             long long* c = p.counters + (size_t)blockIdx.x * 8;
             c[0] = clock64() - t_begin; c[1] = w_acc; c[2] = w_a; c[5] = J; c[7] = w_a2;
+            long long* hst = p.counters + 8 * 512 + (size_t)(blockIdx.x >> 1) * 36;
+            for (int i = 0; i < 36; ++i) hst[i] = whist[i];
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== ct2 epilogue (both CTAs, 4 warps): lane = pixel of the tile, one output-row parity per item =====
@@ -1468,6 +1566,7 @@ __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uin
         : "memory");
 }
 
+template <bool DBG>      // true: experiments build with the issuer's cycle counters (see k_tc_ct23)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pair(const DenseParams p) {
     using P = Fc4Pair;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1559,7 +1658,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
         const uint32_t idesc = umma2_idesc(P::NT);
         const uint32_t a_res = smem_u32(smAres);
         int it = 0, cnt = 0, loads = 0, cur_mp = -1;
-        const bool timing = p.counters != nullptr;
+        const bool timing = DBG && p.counters != nullptr;
         long long t_begin = 0, w_acc = 0, w_b = 0, w_pb = 0, w_a = 0, tw = 0;
         if (timing) t_begin = clock64();
         for (int tile = t0; tile < t1; ++tile, ++it) {
@@ -1933,8 +2032,10 @@ int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* e
             cudaFuncSetAttribute(k_tc_conv<CfgCt3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_ct23, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(k_tc_fc4_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, Fc4Pair::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_ct23<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_ct23<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_fc4_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fc4Pair::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_fc4_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fc4Pair::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<256, EPI_FC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<256, EPI_FC4>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<128, EPI_HIDDEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<128, EPI_HIDDEN>::SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_dense<64, EPI_CONV4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseCfg<64, EPI_CONV4>::SMEM) != cudaSuccess) {
@@ -2139,7 +2240,8 @@ int tc_fc4(const TcWeights& tw, const DevWeights& w, int precision, const void* 
             cudaMemsetAsync(dbg_counters, 0, 8 * 8 * 512, st);
             p.counters = dbg_counters;
         }
-        k_tc_fc4_pair<<<2 * npairs, 384, Fc4Pair::SMEM, st>>>(p);
+        if (want_counters) k_tc_fc4_pair<true><<<2 * npairs, 384, Fc4Pair::SMEM, st>>>(p);
+        else k_tc_fc4_pair<false><<<2 * npairs, 384, Fc4Pair::SMEM, st>>>(p);
         if (want_counters) {
             static int printed = 0;
             cudaStreamSynchronize(st);
@@ -2186,8 +2288,8 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
     static long long* dbg_counters = nullptr;
     static const bool want_counters = getenv("DAI_TC_COUNTERS") != nullptr;                // experiments only
     if (want_counters) {
-        if (!dbg_counters) cudaMalloc(&dbg_counters, 8 * 8 * 512);
-        cudaMemsetAsync(dbg_counters, 0, 8 * 8 * 512, st);
+        if (!dbg_counters) cudaMalloc(&dbg_counters, 16 * 8 * 512);
+        cudaMemsetAsync(dbg_counters, 0, 16 * 8 * 512, st);
         p.counters = dbg_counters;
     }
     // Optional (env DAI_TC_L2PERSIST=1, experiments): mark the scratch as an L2-persisting access window for this launch, so
@@ -2221,7 +2323,8 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-    if (cudaLaunchKernelEx(&cfg, k_tc_ct23, mapIn, mapScr, p) != cudaSuccess) {
+    if ((want_counters ? cudaLaunchKernelEx(&cfg, k_tc_ct23<true>, mapIn, mapScr, p)
+                       : cudaLaunchKernelEx(&cfg, k_tc_ct23<false>, mapIn, mapScr, p)) != cudaSuccess) {
         *err = std::string("launch of the ct2->ct3 pair kernel failed: ") + cudaGetErrorString(cudaGetLastError());
         return -1;
     }
@@ -2239,6 +2342,15 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
             fprintf(stderr, "[tc counters] ct2+ct3 pair kernel rows %d: per leader cycles: mma loop %.0f (wait acc_empty %.0f, wait a_full %.0f) | "
                     "ct3 epilogue: loop %.0f (wait acc_full %.0f) | ct2 epilogue busy %.0f | a_full wait on ct2 tiles %.0f | images %.1f => %.0f cycles per image\n",
                     nrows, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[3], a[3] > 0 ? a[0] / a[3] : 0.0);
+        if (printed % 23 == 4) {
+            static long long hh[512 * 36 / 2];
+            cudaMemcpy(hh, dbg_counters + 8 * 512, sizeof(long long) * 36 * npairs, cudaMemcpyDeviceToHost);
+            double w[36];
+            for (int i = 0; i < 36; ++i) { w[i] = 0; for (int q = 0; q < npairs; ++q) w[i] += (double)hh[q * 36 + i] / npairs; }
+            fprintf(stderr, "[tc counters] ct2+ct3 issuer waits per stage item (cycles per image; hi plane | lo plane | accumulator):");
+            for (int k = 0; k < 12; ++k) fprintf(stderr, " k%d %.0f|%.0f|%.0f", k, w[k] / a[3], w[12 + k] / a[3], w[24 + k] / a[3]);
+            fprintf(stderr, "\n");
+        }
     }
     return 1;
 }
