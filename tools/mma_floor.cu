@@ -25,34 +25,26 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
-struct Unit { uint32_t n, col; };
-struct Case {
-    int pair;            // 1: cta_group::2 (M = 256), 0: cta_group::1 (M = 128)
-    int nunits;
-    Unit u[4];
-    uint32_t a_sbo, a_lbo;   // bytes
-    int reps;
-    int distinct;        // 1: A/B addresses advance per instruction as in the kernels, 0: the same operands every time
-};
-
+// One case = up to four "units" (N, TMEM column) issued round-robin, four K = 16 steps each, all compile-time constants so
+// that the issue loop is a handful of uniform-datapath instructions per MMA and the tensor pipe, not the issuer, is timed.
 template <int PAIR>
-__device__ __forceinline__ void mma(uint32_t lead, uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma(uint32_t lead, uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
     if (PAIR)
-        asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
-                     "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
-                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(a_hi), "r"(b_hi), "r"(lead) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n\t}"
+                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(a_hi), "r"(b_hi), "r"(lead) : "memory");
     else
-        asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %6};\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
-                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(a_hi), "r"(b_hi), "r"(lead) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %4};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 q, %6, 0;\n\t"
+                     "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n\t}"
+                     ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(a_hi), "r"(b_hi), "r"(lead) : "memory");
 }
 
-template <int PAIR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_floor(Case c, long long* out) {
+template <int PAIR, int N0, int N1, int N2, int N3, int SBO, int LBO>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_floor(int reps, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t slot;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const uint32_t rank = cluster_ctarank();
     for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + (uint32_t)i % 7u;
     if (threadIdx.x == 0) {
@@ -77,24 +69,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_floor(Case
     if (warp == 0 && (!PAIR || rank == 0)) {
         const uint32_t lead = elect_one() ? 1u : 0u;
         const uint32_t a16 = smem_u32(smem) >> 4, b16 = smem_u32(smem + 96 * 1024) >> 4;
-        const uint32_t a_hi = (c.a_sbo >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
-        const uint32_t mbits = PAIR ? (256u >> 4) : (128u >> 4);
+        constexpr uint32_t a_hi = ((uint32_t)SBO >> 4) | (1u << 14), b_hi = (128u >> 4) | (1u << 14);
+        constexpr uint32_t mbits = PAIR ? (256u >> 4) : (128u >> 4);
+        constexpr int NS[4] = {N0, N1, N2, N3};
+        constexpr int COL[4] = {0, N0 >= 256 ? 0 : 128, 256, 384};
         const long long t0 = clock64();
-        int count = 0;
-        for (int r = 0; r < c.reps; ++r) {
-#pragma unroll 1
-            for (int u = 0; u < c.nunits; ++u) {
-                const uint32_t n = c.u[u].n;
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (NS[u] == 0) continue;
+                constexpr uint32_t dummy = 0; (void)dummy;
+                const uint32_t n = (uint32_t)NS[u];
                 const uint32_t nh = PAIR ? n / 2 : n;
                 const uint32_t bk = nh * 16u;
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | (mbits << 24);
-                const uint32_t d = tmem + c.u[u].col;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t ka = c.distinct ? (uint32_t)(2 * k) * c.a_lbo + (uint32_t)u * 16u : 0u;
-                    const uint32_t kb = c.distinct ? (uint32_t)(2 * k) * bk + (uint32_t)u * 4096u : 0u;
-                    mma<PAIR>(lead, d, a16 + (ka >> 4) + ((c.a_lbo >> 4) << 16), a_hi, b16 + (kb >> 4) + ((bk >> 4) << 16), b_hi, idesc, 1u);
-                    ++count;
+                    const uint32_t ka = (uint32_t)(2 * k) * (uint32_t)LBO + (uint32_t)u * 16u;
+                    const uint32_t kb = (uint32_t)(2 * k) * bk + (uint32_t)u * 4096u;
+                    mma<PAIR>(lead, tmem + (uint32_t)COL[u], a16 + (ka >> 4) + (((uint32_t)LBO >> 4) << 16), a_hi,
+                              b16 + (kb >> 4) + ((bk >> 4) << 16), b_hi, idesc);
                 }
             }
         }
@@ -108,7 +102,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_floor(Case
         }
         while (!mbar_try(&bar, 0)) {}
         const long long t2 = clock64();
-        if (threadIdx.x == 0) { out[blockIdx.x * 4] = t2 - t0; out[blockIdx.x * 4 + 1] = t1 - t0; out[blockIdx.x * 4 + 2] = count; }
+        constexpr int per_rep = 4 * ((N0 > 0) + (N1 > 0) + (N2 > 0) + (N3 > 0));
+        if (threadIdx.x == 0) { out[blockIdx.x * 4] = t2 - t0; out[blockIdx.x * 4 + 1] = t1 - t0; out[blockIdx.x * 4 + 2] = (long long)reps * per_rep; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -119,49 +114,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_floor(Case
     }
 }
 
-static void run(const char* name, Case c, int grid) {
+template <int PAIR, int N0, int N1, int N2, int N3, int SBO, int LBO>
+static void run(const char* name, int grid) {
     static long long* d = nullptr;
     if (!d) cudaMalloc(&d, 4 * 8 * 1024);
     cudaMemset(d, 0, 4 * 8 * 1024);
     const int smem = 160 * 1024;
-    if (c.pair) {
-        cudaFuncSetAttribute(k_floor<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_floor<1><<<grid, 128, smem>>>(c, d);
-    } else {
-        cudaFuncSetAttribute(k_floor<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        k_floor<0><<<grid, 128, smem>>>(c, d);
-    }
+    auto kern = k_floor<PAIR, N0, N1, N2, N3, SBO, LBO>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<grid, 128, smem>>>(64, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
     static long long h[4 * 1024];
     cudaMemcpy(h, d, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost);
     double tot = 0, iss = 0, cnt = 0; int nb = 0;
     for (int b = 0; b < grid; ++b) if (h[b * 4 + 2] > 0) { tot += (double)h[b * 4]; iss += (double)h[b * 4 + 1]; cnt = (double)h[b * 4 + 2]; ++nb; }
-    printf("%-58s grid %3d: %6.1f cycles per MMA (issue loop alone %6.1f), %d instructions\n", name, grid, tot / nb / cnt, iss / nb / cnt, (int)cnt);
+    printf("%s %-44s grid %3d: %6.1f cycles per MMA (issue loop alone %6.1f), %d instructions\n", PAIR ? "pair M=256  " : "single M=128", name, grid,
+           tot / nb / cnt, iss / nb / cnt, (int)cnt);
+}
+
+template <int PAIR>
+static void suite(int grid) {
+    constexpr int SH = 144, LH = 17 * 9 * 16, SA = 128, LA = 128 * 16;
+    run<PAIR, 256, 0, 0, 0, SH, LH>("N=256, halo strides", grid);
+    run<PAIR, 128, 0, 0, 0, SH, LH>("N=128, halo strides", grid);
+    run<PAIR, 64, 0, 0, 0, SH, LH>("N=64, halo strides", grid);
+    run<PAIR, 32, 0, 0, 0, SH, LH>("N=32, halo strides", grid);
+    run<PAIR, 128, 0, 0, 0, SA, LA>("N=128, 128-B aligned row groups", grid);
+    run<PAIR, 64, 0, 0, 0, SA, LA>("N=64, 128-B aligned row groups", grid);
+    run<PAIR, 32, 0, 0, 0, SA, LA>("N=32, 128-B aligned row groups", grid);
+    run<PAIR, 128, 64, 64, 32, SH, LH>("ct3 mix N=128,64,64,32", grid);
+    run<PAIR, 128, 64, 128, 64, SH, LH>("ct2 mix N=128,64,128,64", grid);
+    run<PAIR, 128, 128, 128, 128, SH, LH>("N=128 x 4 accumulators", grid);
+    run<PAIR, 64, 64, 64, 64, SH, LH>("N=64 x 4 accumulators", grid);
 }
 
 int main() {
-    const uint32_t sbo_halo = 144, lbo_halo = 17 * 9 * 16, sbo_al = 128, lbo_al = 128 * 16;
     for (int grid : {2, 148}) {
-        for (int pair : {1, 0}) {
-            for (uint32_t n : {256u, 128u, 64u, 32u, 16u}) {
-                if (pair && n < 32) continue;
-                char nm[128];
-                snprintf(nm, sizeof nm, "%s N=%u, halo strides, distinct operands", pair ? "pair M=256" : "single M=128", n);
-                run(nm, Case{pair, 1, {{n, 0}, {0, 0}, {0, 0}, {0, 0}}, sbo_halo, lbo_halo, 64, 1}, grid);
-            }
-            char nm[128];
-            snprintf(nm, sizeof nm, "%s N=64, halo strides, SAME operands", pair ? "pair M=256" : "single M=128");
-            run(nm, Case{pair, 1, {{64, 0}, {0, 0}, {0, 0}, {0, 0}}, sbo_halo, lbo_halo, 64, 0}, grid);
-            snprintf(nm, sizeof nm, "%s N=64, 128-B aligned row groups", pair ? "pair M=256" : "single M=128");
-            run(nm, Case{pair, 1, {{64, 0}, {0, 0}, {0, 0}, {0, 0}}, sbo_al, lbo_al, 64, 1}, grid);
-            snprintf(nm, sizeof nm, "%s N=128, 128-B aligned row groups", pair ? "pair M=256" : "single M=128");
-            run(nm, Case{pair, 1, {{128, 0}, {0, 0}, {0, 0}, {0, 0}}, sbo_al, lbo_al, 64, 1}, grid);
-            snprintf(nm, sizeof nm, "%s ct3 mix N=128,64,64,32 (model 202 per 4)", pair ? "pair M=256" : "single M=128");
-            run(nm, Case{pair, 4, {{128, 0}, {64, 32}, {64, 64}, {32, 64}}, sbo_halo, lbo_halo, 32, 1}, grid);
-            snprintf(nm, sizeof nm, "%s ct2 mix N=128,64,128,64", pair ? "pair M=256" : "single M=128");
-            run(nm, Case{pair, 4, {{128, 0}, {64, 0}, {128, 0}, {64, 0}}, sbo_halo, lbo_halo, 32, 1}, grid);
-        }
+        suite<1>(grid);
+        suite<0>(grid);
     }
     return 0;
 }
