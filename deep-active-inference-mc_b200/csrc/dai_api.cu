@@ -110,6 +110,10 @@ struct dai_handle {
     // with events on both sides (StreamSwap)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    // side stream of a step: work that depends on nothing but the noise key (FC4's dropout bit planes) is forked onto it and
+    // joined before its consumer — inside a captured step the fork/join become graph edges (env DAI_FORK=0 disables)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t graph_stamp = 0, graph_replays = 0;
     // sample-shard communicator (NCCL, resolved at run time; SURVEY.md §8 e)
     void* comm = nullptr;      // ncclComm_t
@@ -403,6 +407,15 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     fc.h3 = tc ? nullptr : ptr<float>(h->h3);
     fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
     fc.rows_pad = rows_pad;
+    // FC4's dropout bit planes depend on the noise key alone: with one chunk per call they are generated on the side
+    // stream next to the (latency-bound) FC1..3 launches instead of between them and FC4
+    const bool fork_mask = tc && fc.nk.training && nchunks == 1 && h->side != nullptr && !h->timer.on;
+    if (fork_mask) {
+        CK(cudaEventRecord(h->ev_fork, st));
+        CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        h->launches += launch_fc4_mask(fc.map, fc.nk, 0, rows, ptr<uint32_t>(h->mask), 1, h->side);
+        CK(cudaEventRecord(h->ev_join, h->side));
+    }
     if (!tc) {
         h->launches += launch_po_fc123(h->w, fc, st);
     } else {
@@ -421,7 +434,8 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
         const int n = std::min(ch, rows - r0);
         const uint32_t* mask = nullptr;
         if (fc.nk.training) {
-            h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), tc ? 1 : 0, st);
+            if (fork_mask) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+            else h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), tc ? 1 : 0, st);
             mask = ptr<uint32_t>(h->mask);
         }
         const float* h3c = tc ? nullptr : fc.h3 + (size_t)r0 * 256;
@@ -792,6 +806,16 @@ int dai_create(const dai_config* cfg, int device, dai_handle** out) {
             h->graphs_enabled = 0;
         }
     }
+    const char* fk = getenv("DAI_FORK");
+    if (!(fk && atoi(fk) == 0)) {
+        if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            if (h->side) cudaStreamDestroy(h->side);
+            h->side = nullptr;
+        }
+    }
     *out = h;
     return DAI_OK;
 }
@@ -811,6 +835,9 @@ int dai_destroy(dai_handle* h) {
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     tc_release(&h->tcw);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->plan_stop_host) cudaFreeHost(h->plan_stop_host);

@@ -101,6 +101,16 @@ struct NoiseRows {
     }
 };
 
+// Programmatic dependent launch.  A kernel launched with the programmatic-serialization attribute (launch_dep in
+// dai_kernels.h) may start while the kernel before it in the stream is still running: whatever it does before
+// pdl_wait() — barrier and tensor-memory set-up, weight loads — overlaps that kernel's tail; pdl_wait() returns once
+// the preceding grid has completed and its memory is visible.  Every kernel that can be launched that way calls it
+// before its first access to anything another kernel of the step writes or reads (so completion is transitive along
+// the chain); without the attribute both instructions are no-ops.  pdl_trigger(): this CTA no longer minds the
+// next kernel's CTAs being scheduled next to it (they only become resident where resources are free).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,6 +10,22 @@
 
 namespace dai {
 
+// Launch `k` so that it may begin while the previous kernel of `st` drains (programmatic dependent launch, see
+// pdl_wait() in dai_common.cuh); dep = false or env DAI_PDL=0: an ordinary launch.  Inside a stream capture the
+// relaxed dependency becomes a programmatic edge of the step graph.
+bool pdl_enabled();
+template <class... P, class... A>
+inline cudaError_t launch_dep(void (*k)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dep, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (dep && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, static_cast<P>(args)...);
+}
+
 // Repacked fp32 weights (built once in dai_commit_weights).
 //   *_t  : hidden FC layers transposed to [Kpad][N] (coalesced over outputs)
 //   tail FCs keep torch's [N][K] (warp-per-output dot products)

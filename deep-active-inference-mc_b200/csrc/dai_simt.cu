@@ -559,6 +559,7 @@ int launch_ct4_efe(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {
 //   x[oy][ox] = b + sum_t D_t[oy + 1 - kh][ox + 1 - kw]   (every D element is read exactly once).
 __global__ void __launch_bounds__(256) k_ct4_gather(DevWeights w, Ct4Args a) {
     __shared__ float red[2][8];
+    pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rl = blockIdx.x;
     const int r = a.row0 + rl;
@@ -632,7 +633,7 @@ int launch_proj_rows(const float* act3, int nrows, float* out, cudaStream_t st) 
 
 int launch_ct4_gather(const DevWeights& w, const Ct4Args& a, cudaStream_t st) {
     if (a.nrows <= 0) return 0;
-    k_ct4_gather<<<a.nrows, 256, 0, st>>>(w, a);
+    launch_dep(k_ct4_gather, dim3(a.nrows), dim3(256), 0, st, true, w, a);
     return 1;
 }
 
@@ -677,6 +678,7 @@ __global__ void __launch_bounds__(256) k_qs_conv1(const float* __restrict__ img,
     for (int i = threadIdx.x; i < 288; i += 256) ws[i] = wgt[i];
     if (threadIdx.x < 32) bs[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
+    pdl_wait();
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= rows * 961) return;
     const int r = idx / 961, rem = idx - r * 961;
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(QF_NT) k_qs_fc(DevWeights w, QsArgs a) {
 // conv1 -> fp32 NHWC (c1) or parity-split blocked bf16 planes (c1p) for the tensor-core conv2
 int launch_qs_conv1(const DevWeights& w, const float* img, int rows, float* c1, void* c1p, cudaStream_t st) {
     if (rows <= 0) return 0;
-    k_qs_conv1<<<(rows * 961 + 255) / 256, 256, 0, st>>>(img, rows, w.qc1_w, w.qc1_b, c1, static_cast<unsigned short*>(c1p));
+    launch_dep(k_qs_conv1, dim3((rows * 961 + 255) / 256), dim3(256), 0, st, true, img, rows, (const float*)w.qc1_w, (const float*)w.qc1_b, c1, static_cast<unsigned short*>(c1p));
     return 1;
 }
 
@@ -831,8 +833,10 @@ int launch_qs(const DevWeights& w, const QsArgs& a, cudaStream_t st) {
 // ======================================================================================
 // Tensor-core MLP path: CUDA-core first layers and tails around the tcgen05 dense kernel.
 // Activations between layers are K-blocked bf16 hi/lo planes [plane][N/8][rows_pad][8].
-// Thread mapping: lane = row (32 rows per CTA), the 8 warps stride over the 8-column groups,
-// so every store is 32 rows x 16 B = 512 contiguous bytes.
+// First layers: grid (rows / 32, N / 64); a CTA owns 32 rows (lane = row) x 64 columns (warp = one 8-column
+// group), so every store is 32 rows x 16 B = 512 contiguous bytes and no thread loops over column groups: the
+// kernel is two dependent L2 round trips (inputs, then nothing but arithmetic) instead of eight serial ones
+// (measured before: 27 us for 14 -> 512 on 400 rows as on 6,400 — pure latency).
 // ======================================================================================
 __device__ __forceinline__ void store_kblocked8(unsigned short* out, size_t plane, size_t o, const float (&v)[8]) {
     uint32_t hi[4], lo[4];
@@ -848,99 +852,132 @@ __device__ __forceinline__ void store_kblocked8(unsigned short* out, size_t plan
     *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// layer 0 of Ps (14 -> 512) or Po (10 -> 256): x[KIN] per row -> relu + dropout(site + 0) -> K-blocked planes
+constexpr int L0_ROWS = 32, L0_NT = 256;
+
+// layer 0 of Ps (14 -> 512) or Po (10 -> 256) for this thread's row and its warp's column group kc:
+// xs[KIN] (shared memory) -> relu + dropout(site + 0) -> K-blocked planes
 template <int KIN, int N>
-__device__ __forceinline__ void mlp_l0_row(const float (&x)[KIN], const float* __restrict__ Wt /*[KINpad][N]*/,
-                                           const float* __restrict__ bias, const NoiseKey& nk, int site, int b, uint32_t sample,
-                                           bool valid, int row, size_t rows_pad, unsigned short* out) {
-    const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ void mlp_l0_group(const float* xs, int kc, const float* __restrict__ Wt /*[KINpad][N]*/,
+                                             const float* __restrict__ bias, const NoiseKey& nk, int site, int b, uint32_t sample,
+                                             bool valid, int row, size_t rows_pad, unsigned short* out) {
     const size_t plane = (size_t)(N / 8) * rows_pad * 8;
-    uint4 drop = make_uint4(0, 0, 0, 0);
-    int have_blk = -1;
-    for (int kc = warp; kc < N / 8; kc += 8) {
-        float v[8];
+    float4 w0[KIN], w1[KIN];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(bias + kc * 8 + e);
-#pragma unroll
-        for (int k = 0; k < KIN; ++k) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8 + 4));
-            v[0] = fmaf(x[k], w0.x, v[0]); v[1] = fmaf(x[k], w0.y, v[1]); v[2] = fmaf(x[k], w0.z, v[2]); v[3] = fmaf(x[k], w0.w, v[3]);
-            v[4] = fmaf(x[k], w1.x, v[4]); v[5] = fmaf(x[k], w1.y, v[5]); v[6] = fmaf(x[k], w1.z, v[6]); v[7] = fmaf(x[k], w1.w, v[7]);
-        }
-        if (nk.training) {
-            const int blk = kc >> 4;                      // 128 columns per Philox block
-            if (blk != have_blk) { drop = noise_block(nk, (uint32_t)site, (uint32_t)blk, (uint32_t)b, sample); have_blk = blk; }
-            const int wsel = (kc >> 2) & 3;
-            const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
-            const int sh = (kc & 3) * 8;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = ((mw >> (sh + e)) & 1u) ? fmaxf(v[e], 0.0f) * 2.0f : 0.0f;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
-        }
-        if (valid) store_kblocked8(out, plane, ((size_t)kc * rows_pad + row) * 8, v);
+    for (int k = 0; k < KIN; ++k) {
+        w0[k] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8));
+        w1[k] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8 + 4));
     }
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + kc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + kc * 8 + 4));
+    uint4 drop = make_uint4(0, 0, 0, 0);
+    if (nk.training) drop = noise_block(nk, (uint32_t)site, (uint32_t)(kc >> 4), (uint32_t)b, sample);   // 128 columns per Philox block
+    float v[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+        const float x = xs[k];
+        v[0] = fmaf(x, w0[k].x, v[0]); v[1] = fmaf(x, w0[k].y, v[1]); v[2] = fmaf(x, w0[k].z, v[2]); v[3] = fmaf(x, w0[k].w, v[3]);
+        v[4] = fmaf(x, w1[k].x, v[4]); v[5] = fmaf(x, w1[k].y, v[5]); v[6] = fmaf(x, w1[k].z, v[6]); v[7] = fmaf(x, w1[k].w, v[7]);
+    }
+    if (nk.training) {
+        const int wsel = (kc >> 2) & 3;
+        const uint32_t mw = wsel == 0 ? drop.x : wsel == 1 ? drop.y : wsel == 2 ? drop.z : drop.w;
+        const int sh = (kc & 3) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = ((mw >> (sh + e)) & 1u) ? fmaxf(v[e], 0.0f) * 2.0f : 0.0f;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.0f);
+    }
+    if (valid) store_kblocked8(out, plane, ((size_t)kc * rows_pad + row) * 8, v);
 }
 
-__global__ void __launch_bounds__(256) k_ps_l0(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, unsigned short* out) {
+__global__ void __launch_bounds__(L0_NT) k_ps_l0(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, unsigned short* out) {
+    __shared__ float xs[L0_ROWS][15];                 // odd stride: lane = row reads are conflict-free
+    pdl_wait();
     const int rows = (a.nA + a.nB) * a.B;
-    const int row = blockIdx.x * 32 + (threadIdx.x & 31);
+    for (int i = threadIdx.x; i < L0_ROWS * 14; i += L0_NT) {
+        const int r = i / 14, k = i - r * 14;
+        int site, b;
+        uint32_t sample;
+        nr.decode(min((int)blockIdx.x * L0_ROWS + r, rows - 1), site, b, sample);
+        xs[r][k] = k < 4 ? a.pi[b * 4 + k] : a.s0[b * 10 + k - 4];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * L0_ROWS + lane;
     const bool valid = row < rows;
     int site, b;
     uint32_t sample;
     nr.decode(valid ? row : rows - 1, site, b, sample);
-    float x[14];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = a.pi[b * 4 + k];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) x[4 + k] = a.s0[b * 10 + k];
-    mlp_l0_row<14, 512>(x, w.ps_w0t, w.ps_b0, a.nk, site, b, sample, valid, row, rows_pad, out);
+    mlp_l0_group<14, 512>(xs[lane], blockIdx.y * 8 + warp, w.ps_w0t, w.ps_b0, a.nk, site, b, sample, valid, row, rows_pad, out);
 }
 
-__global__ void __launch_bounds__(256) k_po_l0(DevWeights w, PoFcArgs a, size_t rows_pad, unsigned short* out) {
+__global__ void __launch_bounds__(L0_NT) k_po_l0(DevWeights w, PoFcArgs a, size_t rows_pad, unsigned short* out) {
+    __shared__ float xs[L0_ROWS][11];
+    pdl_wait();
     const int rows = a.map.rows();
-    const int row = blockIdx.x * 32 + (threadIdx.x & 31);
+    // one thread per (row, latent): the fp64 Box-Muller of the reparameterised set is computed once per CTA, not per warp
+    for (int i = threadIdx.x; i < L0_ROWS * 10; i += L0_NT) {
+        const int r = i / 10, k = i - r * 10;
+        int set, slot, b;
+        a.map.decode(min((int)blockIdx.x * L0_ROWS + r, rows - 1), set, slot, b);
+        float x;
+        if (a.mode[set] == 0) {
+            const size_t zr = a.zbcast[set] ? (size_t)b : (size_t)slot * a.map.B + b;
+            x = a.z[set][zr * S_DIM + k];
+        } else {
+            const float eps = noise_normal(a.nk, (uint32_t)a.rp_site, (uint32_t)k, (uint32_t)b, a.map.sample_of(slot));
+            x = reparam(eps, a.rp_mean[b * S_DIM + k], a.rp_logvar[b * S_DIM + k]);
+        }
+        xs[r][k] = x;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * L0_ROWS + lane;
     const bool valid = row < rows;
     int set, slot, b;
     a.map.decode(valid ? row : rows - 1, set, slot, b);
-    const uint32_t sample = a.map.sample_of(slot);
-    float x[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        if (a.mode[set] == 0) {
-            const size_t zr = a.zbcast[set] ? (size_t)b : (size_t)slot * a.map.B + b;
-            x[k] = a.z[set][zr * S_DIM + k];
-        } else {
-            const float eps = noise_normal(a.nk, (uint32_t)a.rp_site, (uint32_t)k, (uint32_t)b, sample);
-            x[k] = reparam(eps, a.rp_mean[b * S_DIM + k], a.rp_logvar[b * S_DIM + k]);
-        }
-    }
-    mlp_l0_row<10, 256>(x, w.po_w0t, w.po_b0, a.nk, a.map.site[set], b, sample, valid, row, rows_pad, out);
+    mlp_l0_group<10, 256>(xs[lane], blockIdx.y * 8 + warp, w.po_w0t, w.po_b0, a.nk, a.map.site[set], b, a.map.sample_of(slot), valid, row,
+                          rows_pad, out);
 }
 
 // tail: K-blocked hi/lo input [plane][K/8][rows_pad][8] -> 20 outputs per row.
-// A CTA owns TAIL_ROWS rows (lane = row); each of its TAIL_WARPS warps contracts one K slice (the
-// weights of a slice are warp-uniform loads, so they are broadcast from L1 without staging), the
-// slice partials meet in shared memory and are added in slice order (fixed, so the result does not
-// depend on how rows are chunked).  One thread per (row, latent d) then finishes mean/logvar (+ sample).
+// A CTA owns TAIL_ROWS rows (lane = row); each of its TAIL_WARPS warps contracts one K slice.  The [20][K] weights are
+// staged in shared memory by one coalesced sweep of the whole CTA while the activation loads are in flight (read per warp
+// straight from global memory, every 32-byte sector of them was a first-touch L2 miss of exactly one warp: 320 serialised
+// L2 latencies per warp, 21 us for a 512 -> 20 layer).  The slice partials meet in shared memory (over the weights,
+// once every warp is done with them) and are added in slice order (fixed, so the result does not depend on how rows are
+// chunked).  One thread per (row, latent d) then finishes mean/logvar (+ sample).
 constexpr int TAIL_ROWS = 32, TAIL_WARPS = 8, TAIL_NT = TAIL_ROWS * TAIL_WARPS;
+template <int K>
+__host__ __device__ constexpr int tail_smem_floats() { return 20 * K > TAIL_WARPS * 20 * TAIL_ROWS ? 20 * K : TAIL_WARPS * 20 * TAIL_ROWS; }
 
 template <int K>
 __device__ __forceinline__ void tail20_partial(const unsigned short* __restrict__ in, size_t rows_pad, int row, int slice,
-                                               const float* __restrict__ W /*[20][K] global*/, float* red /*smem [WARPS][20][ROWS]*/) {
+                                               const float* __restrict__ W /*[20][K] global*/, float* sm /*tail_smem_floats<K>()*/) {
     constexpr int KC_PER = K / 8 / TAIL_WARPS;
     const size_t plane = (size_t)(K / 8) * rows_pad * 8;
+    static_assert(20 * K / 4 % TAIL_NT == 0, "the weight sweep has no remainder");
+    float4 wv[20 * K / 4 / TAIL_NT];
+#pragma unroll
+    for (int i = 0; i < 20 * K / 4 / TAIL_NT; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(W) + i * TAIL_NT + threadIdx.x);
+    pdl_wait();                                       // the weights do not depend on the kernel before; the activations do
+    uint4 h[KC_PER], l[KC_PER];
+#pragma unroll
+    for (int i = 0; i < KC_PER; ++i) {
+        const int kc = slice * KC_PER + i;
+        h[i] = *reinterpret_cast<const uint4*>(in + ((size_t)kc * rows_pad + row) * 8);
+        l[i] = *reinterpret_cast<const uint4*>(in + plane + ((size_t)kc * rows_pad + row) * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 20 * K / 4 / TAIL_NT; ++i) reinterpret_cast<float4*>(sm)[i * TAIL_NT + threadIdx.x] = wv[i];
+    __syncthreads();
     float o[20];
 #pragma unroll
     for (int n = 0; n < 20; ++n) o[n] = 0.0f;
 #pragma unroll
     for (int i = 0; i < KC_PER; ++i) {
         const int kc = slice * KC_PER + i;
-        const uint4 h = *reinterpret_cast<const uint4*>(in + ((size_t)kc * rows_pad + row) * 8);
-        const uint4 l = *reinterpret_cast<const uint4*>(in + plane + ((size_t)kc * rows_pad + row) * 8);
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        const uint32_t hw[4] = {h[i].x, h[i].y, h[i].z, h[i].w}, lw[4] = {l[i].x, l[i].y, l[i].z, l[i].w};
         float x[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -949,15 +986,16 @@ __device__ __forceinline__ void tail20_partial(const unsigned short* __restrict_
         }
 #pragma unroll
         for (int n = 0; n < 20; ++n) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + n * K + kc * 8));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + n * K + kc * 8 + 4));
+            const float4 w0 = *reinterpret_cast<const float4*>(sm + n * K + kc * 8);       // warp-uniform: broadcast
+            const float4 w1 = *reinterpret_cast<const float4*>(sm + n * K + kc * 8 + 4);
             o[n] = fmaf(x[0], w0.x, o[n]); o[n] = fmaf(x[1], w0.y, o[n]); o[n] = fmaf(x[2], w0.z, o[n]); o[n] = fmaf(x[3], w0.w, o[n]);
             o[n] = fmaf(x[4], w1.x, o[n]); o[n] = fmaf(x[5], w1.y, o[n]); o[n] = fmaf(x[6], w1.z, o[n]); o[n] = fmaf(x[7], w1.w, o[n]);
         }
     }
+    __syncthreads();                                  // every warp is done with the weights: the partials go over them
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int n = 0; n < 20; ++n) red[(slice * 20 + n) * TAIL_ROWS + lane] = o[n];
+    for (int n = 0; n < 20; ++n) sm[(slice * 20 + n) * TAIL_ROWS + lane] = o[n];
 }
 
 __device__ __forceinline__ float tail20_sum(const float* red, int n, int r, float bias) {
@@ -968,7 +1006,7 @@ __device__ __forceinline__ float tail20_sum(const float* red, int n, int r, floa
 }
 
 __global__ void __launch_bounds__(TAIL_NT) k_ps_tail(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, const unsigned short* in) {
-    __shared__ float red[TAIL_WARPS * 20 * TAIL_ROWS];
+    __shared__ __align__(16) float red[tail_smem_floats<512>()];
     const int rows = (a.nA + a.nB) * a.B;
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     // rows beyond `rows` lie inside the padded operand (rows_pad >= rows + 128): read, never stored
@@ -1000,7 +1038,7 @@ __global__ void __launch_bounds__(TAIL_NT) k_ps_tail(DevWeights w, PsArgs a, Noi
 }
 
 __global__ void __launch_bounds__(TAIL_NT) k_qs_tail(DevWeights w, QsArgs a, size_t rows_pad, const unsigned short* in) {
-    __shared__ float red[TAIL_WARPS * 20 * TAIL_ROWS];
+    __shared__ __align__(16) float red[tail_smem_floats<256>()];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     tail20_partial<256>(in, rows_pad, blockIdx.x * TAIL_ROWS + lane, slice, w.qf3, red);
     __syncthreads();
@@ -1019,6 +1057,11 @@ __global__ void __launch_bounds__(TAIL_NT) k_qs_tail(DevWeights w, QsArgs a, siz
             a.samp[oo] = reparam(eps, mean, lv);
         }
     }
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("DAI_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
 }
 
 NoiseRows ps_noise_rows(const PsArgs& a) {
@@ -1041,27 +1084,27 @@ NoiseRows map_noise_rows(const RowMap& m) {
 int launch_ps_l0(const DevWeights& w, const PsArgs& a, size_t rows_pad, void* out, cudaStream_t st) {
     const int rows = (a.nA + a.nB) * a.B;
     if (rows <= 0) return 0;
-    k_ps_l0<<<(rows + 31) / 32, 256, 0, st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<unsigned short*>(out));
+    k_ps_l0<<<dim3((rows + L0_ROWS - 1) / L0_ROWS, 512 / 64), L0_NT, 0, st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<unsigned short*>(out));
     return 1;
 }
 
 int launch_ps_tail(const DevWeights& w, const PsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
     const int rows = (a.nA + a.nB) * a.B;
     if (rows <= 0) return 0;
-    k_ps_tail<<<(rows + TAIL_ROWS - 1) / TAIL_ROWS, TAIL_NT, 0, st>>>(w, a, ps_noise_rows(a), rows_pad, static_cast<const unsigned short*>(in));
+    launch_dep(k_ps_tail, dim3((rows + TAIL_ROWS - 1) / TAIL_ROWS), dim3(TAIL_NT), 0, st, true, w, a, ps_noise_rows(a), rows_pad, static_cast<const unsigned short*>(in));
     return 1;
 }
 
 int launch_po_l0(const DevWeights& w, const PoFcArgs& a, size_t rows_pad, void* out, cudaStream_t st) {
     const int rows = a.map.rows();
     if (rows <= 0) return 0;
-    k_po_l0<<<(rows + 31) / 32, 256, 0, st>>>(w, a, rows_pad, static_cast<unsigned short*>(out));
+    launch_dep(k_po_l0, dim3((rows + L0_ROWS - 1) / L0_ROWS, 256 / 64), dim3(L0_NT), 0, st, true, w, a, rows_pad, static_cast<unsigned short*>(out));
     return 1;
 }
 
 int launch_qs_tail20(const DevWeights& w, const QsArgs& a, size_t rows_pad, const void* in, cudaStream_t st) {
     if (a.rows <= 0) return 0;
-    k_qs_tail<<<(a.rows + TAIL_ROWS - 1) / TAIL_ROWS, TAIL_NT, 0, st>>>(w, a, rows_pad, static_cast<const unsigned short*>(in));
+    launch_dep(k_qs_tail, dim3((a.rows + TAIL_ROWS - 1) / TAIL_ROWS), dim3(TAIL_NT), 0, st, true, w, a, rows_pad, static_cast<const unsigned short*>(in));
     return 1;
 }
 
