@@ -375,6 +375,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int ntiles = p.nrows * C::TILES;
+    // programmatic dependent launch: everything above (and the weight loads below) may overlap the tail of the kernel
+    // before; the halo planes it wrote and the buffers this kernel writes may be touched only after it has completed
+    if (warp != W_WGT) pdl_wait();
+    pdl_trigger();
 
     if (warp == W_PROD) {
         // ===== halo producer: one TMA box per (tile, plane) =====
@@ -748,6 +752,8 @@ __global__ void __launch_bounds__(384, 1) k_tc_dense(const DenseParams p) {
     const int mtiles = (p.nrows + 127) / 128;
     const int ntiles = mtiles * p.ntn;
     const int nplanes = p.nprod == 3 ? 2 : 1;
+    pdl_wait();               // programmatic dependent launch (see k_tc_conv): set-up above overlaps the previous kernel
+    pdl_trigger();
 
     if (warp == 8) {          // producer (single-thread roles use the highest warp ids: see k_tc_conv)
         if (lane == 0) {
@@ -1206,6 +1212,8 @@ k_tc_ct23(const __grid_constant__ CUtensorMap tmapIn, const __grid_constant__ CU
     const int J = pair < pairs_total ? (pairs_total - pair + npairs - 1) / npairs : 0;
     const int srow0 = (int)blockIdx.x * 2;           // this CTA's two scratch images
     const bool timing = DBG && p.counters != nullptr;
+    if (warp != W_WGT) pdl_wait();     // programmatic dependent launch (see k_tc_conv); no early trigger: the kernel after this
+                                       // one has no set-up worth hiding, its CTAs would only sit next to these for 1.4 ms
     // Every role numbers the items it walks with `seq` (items that exist in this stage, in list order): item seq uses
     // TMEM buffer seq & 3, in its (seq >> 2)-th use.
 #define F23_FOR_ITEMS(j, k, L, t)                                                   \
@@ -1606,6 +1614,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) k_tc_fc4_pai
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int t0 = (int)(total * pair / npairs), t1 = (int)(total * (pair + 1) / npairs);
     const int nplanes = p.nprod == 3 ? 2 : 1;
+    pdl_wait();               // programmatic dependent launch (see k_tc_conv)
+    pdl_trigger();
 
     if (warp == 8) {          // producer (both CTAs): own A rows when the row block changes, own half of the B columns per stage
         if (lane == 0) {
@@ -1917,7 +1927,7 @@ int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precisio
         if (!attr_dbg) { cudaFuncSetAttribute(k_tc_conv<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES); attr_dbg = true; }
         k_tc_conv<C, true><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     } else {
-        k_tc_conv<C, false><<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+        launch_dep(k_tc_conv<C, false>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, true, map, p);
     }
     if (want_counters) {
         static int printed = 0;
@@ -2139,7 +2149,7 @@ int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = ((rows + 127) / 128) * p.ntn;
-    k_tc_dense<128, EPI_HIDDEN><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<128, EPI_HIDDEN>::SMEM, st>>>(p);
+    launch_dep(k_tc_dense<128, EPI_HIDDEN>, dim3(ntiles < sms ? ntiles : sms), dim3(384), DenseCfg<128, EPI_HIDDEN>::SMEM, st, true, p);
     return 1;
 }
 
@@ -2148,6 +2158,7 @@ int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* i
 __global__ void __launch_bounds__(256) k_conv4_im2col(const float* __restrict__ c3, int M, size_t m_pad, __nv_bfloat16* __restrict__ out) {
     const size_t n = (size_t)M * 72;
     const size_t plane = 72 * m_pad * 8;
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(i % M), kc = (int)(i / M);
         const int img = m / 9, px = m - img * 9, oy = px / 3, ox = px - oy * 3;
@@ -2194,7 +2205,7 @@ int tc_qs_conv4(const TcWeights& tw, int precision, const float* c3, int rows, v
     if (!im || !im->dense_w[TC_QC4]) { *err = "conv4 tensor-core weights not packed"; return -1; }
     const int M = rows * 9;
     const size_t m_pad = ((size_t)M + 127) / 128 * 128 + 128;
-    k_conv4_im2col<<<1184, 256, 0, st>>>(c3, M, m_pad, static_cast<__nv_bfloat16*>(scratch));
+    launch_dep(k_conv4_im2col, dim3(1184), dim3(256), 0, st, true, c3, M, m_pad, static_cast<__nv_bfloat16*>(scratch));
     DenseParams p{};
     p.a = static_cast<const __nv_bfloat16*>(scratch);
     p.a_kc_stride = m_pad * 8; p.a_plane = 72 * m_pad * 8;
@@ -2207,7 +2218,7 @@ int tc_qs_conv4(const TcWeights& tw, int precision, const float* c3, int rows, v
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = (M + 127) / 128;
-    k_tc_dense<64, EPI_CONV4><<<ntiles < sms ? ntiles : sms, 384, DenseCfg<64, EPI_CONV4>::SMEM, st>>>(p);
+    launch_dep(k_tc_dense<64, EPI_CONV4>, dim3(ntiles < sms ? ntiles : sms), dim3(384), DenseCfg<64, EPI_CONV4>::SMEM, st, true, p);
     return 2;
 }
 
@@ -2321,6 +2332,10 @@ int tc_ct23(const TcWeights& tw, const DevWeights& w, int precision, const void*
         attr[0].val.accessPolicyWindow.hitRatio = bytes <= l2_persist ? 1.0f : (float)((double)l2_persist / (double)bytes);
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    } else if (pdl_enabled() && !want_counters) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // see pdl_wait() in the kernel
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
     if ((want_counters ? cudaLaunchKernelEx(&cfg, k_tc_ct23<true>, mapIn, mapScr, p)
