@@ -399,7 +399,10 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     const int nchunks = (rows + h->dec_chunk - 1) / h->dec_chunk;
     const int ch = std::min(rows, ((rows + nchunks - 1) / nchunks + 31) / 32 * 32);
     const size_t esz = sizeof(float);   // fp32 planes, or bf16 hi+lo planes: 4 bytes per element either way
-    RET(reserve(h, h->mask, (size_t)ch * 512 * sizeof(uint32_t)));
+    // FC4's dropout bit planes depend on the noise key alone: they are generated for ALL rows of the call on the side
+    // stream, next to the (latency-bound) FC1..3 launches, instead of per chunk between the decoder's kernels
+    const bool fork_mask = tc && fc.nk.training && h->side != nullptr && !h->timer.on && (size_t)rows * 2048 <= ((size_t)1 << 30);
+    RET(reserve(h, h->mask, (size_t)(fork_mask ? rows : ch) * 512 * sizeof(uint32_t)));
     RET(reserve(h, h->act0, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act1, (size_t)ch * 16384 * esz));
     RET(reserve(h, h->act2, std::max((size_t)ch * 65536 * esz, tc ? tc_ct23_scratch_bytes(ch) : (size_t)0)));
@@ -407,9 +410,6 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
     fc.h3 = tc ? nullptr : ptr<float>(h->h3);
     fc.h3b = tc ? ptr<unsigned short>(h->h3) : nullptr;
     fc.rows_pad = rows_pad;
-    // FC4's dropout bit planes depend on the noise key alone: with one chunk per call they are generated on the side
-    // stream next to the (latency-bound) FC1..3 launches instead of between them and FC4
-    const bool fork_mask = tc && fc.nk.training && nchunks == 1 && h->side != nullptr && !h->timer.on;
     if (fork_mask) {
         CK(cudaEventRecord(h->ev_fork, st));
         CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
@@ -434,9 +434,9 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
         const int n = std::min(ch, rows - r0);
         const uint32_t* mask = nullptr;
         if (fc.nk.training) {
-            if (fork_mask) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-            else h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), tc ? 1 : 0, st);
-            mask = ptr<uint32_t>(h->mask);
+            if (fork_mask && r0 == 0) CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+            if (!fork_mask) h->launches += launch_fc4_mask(fc.map, fc.nk, r0, n, ptr<uint32_t>(h->mask), tc ? 1 : 0, st);
+            mask = ptr<uint32_t>(h->mask) + (fork_mask ? (size_t)r0 * 512 : 0);
         }
         const float* h3c = tc ? nullptr : fc.h3 + (size_t)r0 * 256;
         Ct4Args c4{};
@@ -462,7 +462,7 @@ int run_decoder(dai_handle* h, cudaStream_t st, PoFcArgs fc, int img_rows, float
 // Runs Qs on `rows` images with noise map (B, Sl, sample0, site); outputs [rows][10] each.  Rows are ordered (slot, b);
 // a launch covers either whole slots (B <= chunk) or a run of rows of ONE slot (B > chunk: noise row = b0 + local row).
 int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl, int sample0, int site,
-                const NoiseKey& nk, float* mean, float* logvar, float* samp) {
+                const NoiseKey& nk, float* mean, float* logvar, float* samp, int sps = 0) {
     const int rows = B * Sl;
     if (rows <= 0) return DAI_OK;
     // equal chunks rather than a full one and a short one
@@ -494,7 +494,7 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
             const int n = ns * nb;                      // (rows_per == B) or (ns == 1)
             QsArgs a{};
             a.img = img + (size_t)r0 * IMG; a.rows = n;
-            a.map.B = nb; a.map.Sl = ns; a.map.sample0 = sample0 + s0; a.map.nsets = 1; a.map.b0 = b0;
+            a.map.B = nb; a.map.Sl = ns; a.map.sample0 = sample0; a.map.slot0 = s0; a.map.sps = sps; a.map.nsets = 1; a.map.b0 = b0;
             a.map.site[0] = site; a.map.site[1] = site; a.map.site[2] = site;
             a.c1 = ptr<float>(h->qc1); a.c2 = ptr<float>(h->qc2); a.c3 = ptr<float>(h->qc3); a.c4 = ptr<float>(h->qc4);
             a.mean = mean + (size_t)r0 * S_DIM; a.logvar = logvar + (size_t)r0 * S_DIM;
@@ -622,20 +622,15 @@ uint64_t mix64(uint64_t h, uint64_t v) {
     return h;
 }
 
-// run_step through a cached CUDA graph: the first evaluation with a given signature runs eagerly (it sizes the
+// A cached CUDA graph per launch sequence: the first evaluation with a given signature runs eagerly (it sizes the
 // workspaces), the second is captured (stream capture of the very same launch code) and instantiated, later ones are
-// ONE cudaGraphLaunch — ~30 kernels without per-launch host work or launch gaps.  The noise key of the call and the
-// step index are the only things that change between replays; the kernels read them from h->keybuf (NoiseKey::dyn),
-// which a one-thread kernel writes ahead of every launch.
-int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
-    if (!h->graphs_enabled || h->timer.on) return run_step(h, st, sp);
-    uint64_t sig = 1469598103934665603ull;
-    const uint64_t fields[] = {(uint64_t)(uintptr_t)sp.s0, (uint64_t)(uintptr_t)sp.pi, (uint64_t)sp.B, (uint64_t)sp.samples, (uint64_t)sp.j0,
-                               (uint64_t)sp.j1, (uint64_t)sp.mean_variant, (uint64_t)(uintptr_t)sp.acc, (uint64_t)(uintptr_t)sp.carry_dst,
-                               (uint64_t)sp.carry_mean, (uint64_t)(uintptr_t)sp.out_ps1, (uint64_t)(uintptr_t)sp.out_mean,
-                               (uint64_t)(uintptr_t)sp.out_logvar, (uint64_t)(uintptr_t)sp.out_po1, (uint64_t)h->cfg.precision,
-                               (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk, (uint64_t)(uintptr_t)st};
-    for (uint64_t f : fields) sig = mix64(sig, f);
+// ONE cudaGraphLaunch — the kernels of a step (or of a whole time-batched rollout) without per-launch host work or
+// launch gaps.  The noise key of the call and the step index are the only things that change between replays; the
+// kernels read them from h->keybuf (NoiseKey::dyn), which a one-thread kernel writes ahead of every launch.
+// `body(dyn)` enqueues the sequence on `st` with NoiseKey::dyn = dyn (null: eager, the key travels as a parameter).
+template <class Body>
+int run_cached(dai_handle* h, cudaStream_t st, uint64_t sig, const NoiseKey& nk, Body&& body) {
+    if (!h->graphs_enabled || h->timer.on) return body(nullptr);
     dai_handle::StepGraph* g = nullptr;
     for (auto& e : h->graphs)
         if (e.sig == sig) { g = &e; break; }
@@ -657,32 +652,30 @@ int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
     g->stamp = ++h->graph_stamp;
     if (!h->keybuf) CK(cudaMalloc(&h->keybuf, 16));
     if (g->exec) {
-        k_set_key<<<1, 1, 0, st>>>(h->keybuf, sp.nk.k0, sp.nk.k1, sp.nk.step);
+        k_set_key<<<1, 1, 0, st>>>(h->keybuf, nk.k0, nk.k1, nk.step);
         CK(cudaGraphLaunch(g->exec, st));
         h->launches += g->nlaunch + 1;
         ++h->graph_replays;
-        return post_launch(h, "step graph");
+        return post_launch(h, "graph replay");
     }
     if (g->seen++ == 0) {                        // first time: eager (grows the workspaces), and see whether anything moved
         const uint64_t gen0 = h->alloc_gen;
-        RET(run_step(h, st, sp));
+        RET(body(nullptr));
         g->gen = h->alloc_gen;
         if (h->alloc_gen != gen0) g->seen = 1;
         return DAI_OK;
     }
     // capture
-    StepSpec cs = sp;
-    cs.nk.dyn = h->keybuf;
-    k_set_key<<<1, 1, 0, st>>>(h->keybuf, sp.nk.k0, sp.nk.k1, sp.nk.step);
+    k_set_key<<<1, 1, 0, st>>>(h->keybuf, nk.k0, nk.k1, nk.step);
     const uint64_t l0 = h->launches;
     h->capturing = true; h->capture_failed = false;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         h->capturing = false;
         h->graphs_enabled = 0;                   // this stream cannot be captured (e.g. the legacy default stream): stay eager
-        return run_step(h, st, sp);
+        return body(nullptr);
     }
-    const int rc = run_step(h, st, cs);
+    const int rc = body(h->keybuf);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     h->capturing = false;
@@ -691,9 +684,9 @@ int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
         if (graph) cudaGraphDestroy(graph);
         h->launches = l0;
         g->seen = 1;                             // try again on a later call
-        if (h->capture_failed) { h->capture_failed = false; return run_step(h, st, sp); }
+        if (h->capture_failed) { h->capture_failed = false; return body(nullptr); }
         if (rc != DAI_OK) return rc;
-        return run_step(h, st, sp);
+        return body(nullptr);
     }
     cudaGraphExec_t exec = nullptr;
     if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
@@ -701,14 +694,125 @@ int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
         cudaGraphDestroy(graph);
         h->launches = l0;
         h->graphs_enabled = 0;
-        return run_step(h, st, sp);
+        return body(nullptr);
     }
     cudaGraphDestroy(graph);
     g->exec = exec; g->nlaunch = h->launches - l0; g->gen = h->alloc_gen;
     CK(cudaGraphLaunch(g->exec, st));
     h->launches += 1;
     ++h->graph_replays;
-    return post_launch(h, "step graph (first launch)");
+    return post_launch(h, "graph (first launch)");
+}
+
+uint64_t sig_of(std::initializer_list<uint64_t> fields) {
+    uint64_t sig = 1469598103934665603ull;
+    for (uint64_t f : fields) sig = mix64(sig, f);
+    return sig;
+}
+
+// run_step through a cached graph (keyed by everything its launches depend on except the noise key)
+int run_step_cached(dai_handle* h, cudaStream_t st, const StepSpec& sp) {
+    const uint64_t sig = sig_of({1, (uint64_t)(uintptr_t)sp.s0, (uint64_t)(uintptr_t)sp.pi, (uint64_t)sp.B, (uint64_t)sp.samples, (uint64_t)sp.j0,
+                                 (uint64_t)sp.j1, (uint64_t)sp.mean_variant, (uint64_t)(uintptr_t)sp.acc, (uint64_t)(uintptr_t)sp.carry_dst,
+                                 (uint64_t)sp.carry_mean, (uint64_t)(uintptr_t)sp.out_ps1, (uint64_t)(uintptr_t)sp.out_mean,
+                                 (uint64_t)(uintptr_t)sp.out_logvar, (uint64_t)(uintptr_t)sp.out_po1, (uint64_t)h->cfg.precision,
+                                 (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk, (uint64_t)(uintptr_t)st});
+    return run_cached(h, st, sig, sp.nk, [&](const uint32_t* dyn) {
+        StepSpec cs = sp;
+        cs.nk.dyn = dyn;
+        if (dyn) cs.nk.step = 0;                 // the replay's base step comes from the key buffer
+        return run_step(h, st, cs);
+    });
+}
+
+// ---- the horizon of a rollout, time-batched -------------------------------------------------------------------------
+// The steps of calculate_G_repeated (src/torchmodel.py:329-349) are chained only through the transition net: the state a
+// step starts from is the previous step's ps1 (or its mean) of the last MC sample, which Ps alone produces; the decoder
+// and encoder passes of a step feed nothing but that step's own EFE terms.  So the latent chain of ALL steps runs first
+// (4 small launches per step), and the pixel work of a GROUP of steps then runs as one launch sequence whose slots are
+// (step, sample) pairs (RowMap::sps): a single root's 600 decoder rows per step become 6,000-row launches that fill
+// the machine, and the ~25 latency-bound launches of a step are paid once per group instead of once per step.
+// Row sets stay set-major ([set][step][sample][b]), so the images of set 0 are the encoder's input as they lie; the
+// noise of a row is keyed on (sample, step) exactly as in a launch of that step alone, and the steps' fp64 sums are
+// accumulated in step order — the results are those of the step-by-step schedule.
+int run_rollout_steps(dai_handle* h, cudaStream_t st, const float* s_root, const float* pi, int B, int T, int samples, int j0in, int j1,
+                      int mean_variant, int calc_mean, NoiseKey nk, double* acc, float* out_po1) {
+    const int Sl = mean_variant ? 1 : (j1 - j0in);
+    const int S = mean_variant ? 1 : samples;
+    const int j0 = mean_variant ? 0 : j0in;
+    const bool own_last = (j0 + Sl == S) && Sl > 0;
+    const int nA = Sl + (own_last ? 0 : 1);
+    const int last_slot = nA - 1;
+    const size_t slab = (size_t)B * S_DIM;
+    // ps buffer: meanA, logvarA, sampA [T][nA] ; meanB, sampB [T][Sl]
+    RET(reserve(h, h->ps, (size_t)T * (3 * (size_t)nA + 2 * (size_t)Sl) * slab * sizeof(float)));
+    float* meanA = ptr<float>(h->ps);
+    float* logvarA = meanA + (size_t)T * nA * slab;
+    float* sampA = logvarA + (size_t)T * nA * slab;
+    float* meanB = sampA + (size_t)T * nA * slab;
+    float* sampB = meanB + (size_t)T * Sl * slab;
+    // 1. the latent chain
+    for (int t = 0; t < T; ++t) {
+        PsArgs pa{};
+        pa.pi = pi;
+        pa.s0 = t == 0 ? s_root : (calc_mean ? meanA : sampA) + ((size_t)(t - 1) * nA + last_slot) * slab;
+        pa.B = B; pa.nA = nA; pa.nB = Sl; pa.sample0 = j0;
+        pa.extra_slot = own_last ? -1 : Sl; pa.extra_sample = S - 1;
+        pa.siteA = SITE_PS_A; pa.siteB = SITE_PS_B;
+        pa.meanA = meanA + (size_t)t * nA * slab; pa.logvarA = logvarA + (size_t)t * nA * slab; pa.sampA = sampA + (size_t)t * nA * slab;
+        pa.meanB = meanB + (size_t)t * Sl * slab; pa.logvarB = nullptr; pa.sampB = sampB + (size_t)t * Sl * slab;
+        pa.nk = nk; pa.nk.step = nk.step + (uint32_t)t;
+        RET(run_ps(h, st, pa));
+    }
+    if (Sl > 0) {
+        // 2. pixel work, in groups of steps of about two decoder chunks
+        const int rows_step = 3 * Sl * B;
+        const int tg_max = std::max(1, std::min(T, std::min(255, (2 * h->dec_chunk) / std::max(rows_step, 1))));
+        const int ngroups = (T + tg_max - 1) / tg_max;
+        const int tg = (T + ngroups - 1) / ngroups;
+        RET(reserve(h, h->img, (size_t)tg * Sl * B * IMG * sizeof(float)));
+        RET(reserve(h, h->hsum, (size_t)tg * rows_step * sizeof(float)));
+        RET(reserve(h, h->reward, (size_t)tg * rows_step * sizeof(float)));
+        RET(reserve(h, h->qs_out, (size_t)tg * Sl * slab * 2 * sizeof(float)));
+        for (int t0 = 0; t0 < T; t0 += tg) {
+            const int n = std::min(tg, T - t0);
+            float* qs_mean = ptr<float>(h->qs_out);
+            float* qs_logvar = qs_mean + (size_t)n * Sl * slab;
+            NoiseKey gk = nk;
+            gk.step = nk.step + (uint32_t)t0;
+            PoFcArgs fc{};
+            fc.map.B = B; fc.map.Sl = n * Sl; fc.map.sps = Sl; fc.map.sample0 = j0; fc.map.nsets = 3;
+            fc.map.site[0] = SITE_PO_A; fc.map.site[1] = SITE_PO_B1; fc.map.site[2] = SITE_PO_B2;
+            fc.z[0] = (mean_variant ? meanA : sampA) + (size_t)t0 * nA * slab; fc.zslots[0] = nA;
+            fc.z[1] = (mean_variant ? meanB : sampB) + (size_t)t0 * Sl * slab; fc.zslots[1] = Sl;
+            fc.z[2] = nullptr;
+            fc.mode[0] = 0; fc.mode[1] = 0; fc.mode[2] = 1;
+            fc.rp_mean = meanA + ((size_t)t0 * nA + last_slot) * slab; fc.rp_logvar = logvarA + ((size_t)t0 * nA + last_slot) * slab;
+            fc.rp_tstride = (size_t)nA * slab; fc.rp_site = SITE_RP_B;
+            fc.nk = gk;
+            RET(run_decoder(h, st, fc, n * Sl * B, ptr<float>(h->img), ptr<float>(h->hsum), ptr<float>(h->reward)));
+            RET(run_encoder(h, st, ptr<float>(h->img), B, n * Sl, j0, SITE_QS_A, gk, qs_mean, qs_logvar, nullptr, Sl));
+            StepFinalizeArgs fa{};
+            fa.B = B; fa.Sl = Sl; fa.T = n; fa.lvA_tstride = (size_t)nA * slab;
+            fa.logvarA = logvarA + (size_t)t0 * nA * slab; fa.qs_logvar = qs_logvar;
+            fa.reward = ptr<float>(h->reward); fa.hsum = ptr<float>(h->hsum); fa.acc = acc;
+            if (out_po1 && own_last && t0 + n == T)
+                CK(cudaMemcpyAsync(out_po1, ptr<float>(h->img) + ((size_t)(n - 1) * Sl + (Sl - 1)) * B * IMG, (size_t)B * IMG * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+            h->launches += launch_step_finalize(fa, st);
+        }
+    }
+    if (out_po1 && !own_last) {
+        // this rank does not hold the last sample: decode it once more (same noise key => same image on every rank)
+        PoFcArgs fc{};
+        fc.map.B = B; fc.map.Sl = 1; fc.map.sample0 = S - 1; fc.map.nsets = 1;
+        fc.map.site[0] = SITE_PO_A; fc.map.site[1] = SITE_PO_A; fc.map.site[2] = SITE_PO_A;
+        fc.z[0] = sampA + ((size_t)(T - 1) * nA + last_slot) * slab; fc.mode[0] = 0;
+        fc.nk = nk; fc.nk.step = nk.step + (uint32_t)(T - 1);
+        RET(reserve(h, h->scratch, (size_t)2 * B * sizeof(float)));
+        RET(run_decoder(h, st, fc, B, out_po1, ptr<float>(h->scratch), ptr<float>(h->scratch) + B));
+    }
+    return post_launch(h, "rollout steps");
 }
 
 __global__ void k_fill_eye(float* pi, int B) {
@@ -750,6 +854,22 @@ int rollout_impl(dai_handle* h, cudaStream_t st, const float* o, const float* pi
         pi = ptr<float>(h->pi_eye);
     }
     const int mean_variant = (four && calc_mean) ? 1 : 0;
+    // time-batched horizon (run_rollout_steps) on the tensor-core path; env DAI_TBATCH=0 or the fp32 CUDA-core
+    // precision: one launch sequence per step
+    static const bool tbatch_env = !(getenv("DAI_TBATCH") && atoi(getenv("DAI_TBATCH")) == 0);
+    if (tbatch_env && h->cfg.precision != DAI_PREC_FP32_SIMT && steps > 1 && samples <= (int)SAMPLE_MASK) {
+        const uint64_t sig = sig_of({2, (uint64_t)(uintptr_t)pi, (uint64_t)B, (uint64_t)steps, (uint64_t)samples, (uint64_t)j0, (uint64_t)j1,
+                                     (uint64_t)mean_variant, (uint64_t)calc_mean, (uint64_t)(uintptr_t)po1, (uint64_t)h->cfg.precision,
+                                     (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk, (uint64_t)(uintptr_t)st});
+        RET(run_cached(h, st, sig, nk, [&](const uint32_t* dyn) {
+            NoiseKey k = nk;
+            k.dyn = dyn;
+            k.step = 0;
+            return run_rollout_steps(h, st, ptr<float>(h->carry), pi, B, steps, samples, j0, j1, mean_variant, calc_mean, k,
+                                     ptr<double>(h->acc), po1);
+        }));
+        return finish_outputs(h, st, B, mean_variant ? 1 : samples, sums, G, t0, t1, t2);
+    }
     for (int t = 0; t < steps; ++t) {
         StepSpec sp;
         sp.s0 = ptr<float>(h->carry); sp.pi = pi; sp.B = B;

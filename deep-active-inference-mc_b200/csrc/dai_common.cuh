@@ -18,8 +18,9 @@ struct NoiseKey {
     uint32_t k0, k1;     // seed + call_index
     uint32_t step;
     int32_t training;    // 0: dropout is identity
-    const uint32_t* dyn; // non-null: {k0, k1, step} are read from device memory instead (replayed CUDA graphs: the
-                         // captured kernels keep their parameters, the key of the call / step is written before each launch)
+    const uint32_t* dyn; // non-null: {k0, k1, base step} are read from device memory instead and `step` is an offset from that
+                         // base (replayed CUDA graphs: the captured kernels keep their parameters, the key of the call / step is
+                         // written before each launch)
 };
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -34,12 +35,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     return c;
 }
 
-// 128 random bits for (site, block) of (row, sample) at this key/step
+// 128 random bits for (site, block) of (row, sample) at this key/step.  `sample` carries the MC sample in its low 24 bits
+// and, for launches that batch several horizon steps (RowMap::sps), the row's step offset in the high 8: the counter the
+// reference stream is keyed on is (.., sample, nk.step + offset), the same as a launch of that step alone would use.
+constexpr uint32_t SAMPLE_BITS = 24, SAMPLE_MASK = (1u << SAMPLE_BITS) - 1u;
 __device__ __forceinline__ uint4 noise_block(const NoiseKey& nk, uint32_t site, uint32_t blk,
                                              uint32_t row, uint32_t sample) {
     uint32_t k0 = nk.k0, k1 = nk.k1, step = nk.step;
-    if (nk.dyn) { k0 = __ldg(nk.dyn); k1 = __ldg(nk.dyn + 1); step = __ldg(nk.dyn + 2); }
-    return philox4x32_10(make_uint4(blk | (site << 16), row, sample, step), k0, k1);
+    if (nk.dyn) { k0 = __ldg(nk.dyn); k1 = __ldg(nk.dyn + 1); step += __ldg(nk.dyn + 2); }   // nk.step: offset from the replay's base step
+    return philox4x32_10(make_uint4(blk | (site << 16), row, sample & SAMPLE_MASK, step + (sample >> SAMPLE_BITS)), k0, k1);
 }
 
 // standard normal for element e: Box-Muller in fp64 on words 0,1 of block e, rounded once
@@ -71,13 +75,27 @@ struct RowMap {
     int32_t nsets;
     int32_t site[3];    // noise site base per set
     int32_t b0;         // row offset of this launch inside the call's batch (encoder row chunks: noise row = b0 + local row)
+    int32_t slot0;      // slot offset of this launch inside the call's slots (encoder slot chunks)
+    int32_t sps;        // > 0: the slots are (horizon step, sample) pairs, `sps` samples per step (time-batched rollout:
+                        // slot g = t * sps + j stands for local sample j of step nk.step + t); 0: one step
     __device__ __forceinline__ void decode(int r, int& set, int& slot, int& b) const {
         b = r % B + b0;
         const int q = r / B;
         slot = q % Sl;
         set = q / Sl;
     }
-    __device__ __forceinline__ uint32_t sample_of(int slot) const { return (uint32_t)(sample0 + slot); }
+    // step offset of a (launch-local) slot and its sample slot within that step
+    __device__ __forceinline__ void split(int slot, int& t, int& j) const {
+        const int g = slot + slot0;
+        t = sps > 0 ? g / sps : 0;
+        j = g - t * sps;
+    }
+    // global MC sample of a slot, with the step offset in the high bits (see noise_block)
+    __device__ __forceinline__ uint32_t sample_of(int slot) const {
+        int t, j;
+        split(slot, t, j);
+        return (uint32_t)(sample0 + j) | ((uint32_t)t << SAMPLE_BITS);
+    }
     __host__ __device__ int rows() const { return nsets * Sl * B; }
 };
 
@@ -91,13 +109,17 @@ struct NoiseRows {
     int32_t extra_slot;     // set 0 only: slot that stands for global sample `extra_sample` (or -1)
     int32_t extra_sample;
     int32_t b0;             // see RowMap::b0
+    int32_t slot0, sps;     // see RowMap::slot0, RowMap::sps
     __device__ __forceinline__ void decode(int r, int& site_out, int& b, uint32_t& sample) const {
         const int set = r < set_end[0] ? 0 : (r < set_end[1] ? 1 : 2);
         const int q = r - (set == 0 ? 0 : set_end[set - 1]);
         const int slot = q / B;
         b = q - slot * B + b0;
         site_out = site[set];
-        sample = (set == 0 && slot == extra_slot) ? (uint32_t)extra_sample : (uint32_t)(sample0 + slot);
+        const int g = slot + slot0;
+        const int t = sps > 0 ? g / sps : 0;
+        const int j = g - t * sps;
+        sample = ((set == 0 && j == extra_slot) ? (uint32_t)extra_sample : (uint32_t)(sample0 + j)) | ((uint32_t)t << SAMPLE_BITS);
     }
 };
 

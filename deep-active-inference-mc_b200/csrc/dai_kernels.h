@@ -80,7 +80,9 @@ struct PoFcArgs {
     const float* z[3];     // per set: latent rows [Sl][B][10] (mode 0)
     int32_t mode[3];       // 0: direct, 1: reparameterize(rp_mean[b], rp_logvar[b]) with site rp_site
     int32_t zbcast[3];     // 1: z is [B][10] shared by all slots
+    int32_t zslots[3];     // time-batched maps (map.sps > 0): slots per horizon step in z[set] (row = (t*zslots + j)*B + b)
     const float *rp_mean, *rp_logvar;   // [B][10]
+    size_t rp_tstride;     // time-batched maps: floats between the [B][10] slabs of consecutive steps
     int32_t rp_site;
     float* h3;             // [rows][256] fp32 (CUDA-core FC4), or null
     unsigned short* h3b;   // [plane hi|lo][kc 32][rows_pad][8] bf16 (tensor-core FC4), or null
@@ -153,10 +155,12 @@ int  launch_qpi(const DevWeights& w, const float* s, int B, float* logits, float
 // ---- scalar glue -----------------------------------------------------------------------
 struct StepFinalizeArgs {
     int32_t B, Sl;
-    const float* logvarA;  // [>=Sl][B][10] transition logvar of the loop-2a slots
-    const float* qs_logvar;// [Sl][B][10]
-    const float* reward;   // [3*Sl*B] (set 0 used)
-    const float* hsum;     // [3*Sl*B] (sets 1,2 used)
+    int32_t T;             // horizon steps held by the buffers (0 or 1: one); steps are accumulated in order
+    size_t lvA_tstride;    // floats between the steps' logvarA blocks
+    const float* logvarA;  // [T][>=Sl][B][10] transition logvar of the loop-2a slots
+    const float* qs_logvar;// [T*Sl][B][10]
+    const float* reward;   // [3][T*Sl*B] (set 0 used)
+    const float* hsum;     // [3][T*Sl*B] (sets 1,2 used)
     double* acc;           // [4][B] += sums of term0, term1, term2_1, term2_2
     const float* carry_src;// [B][10] or null
     float* carry_dst;      // [B][10]

@@ -921,12 +921,15 @@ __global__ void __launch_bounds__(L0_NT) k_po_l0(DevWeights w, PoFcArgs a, size_
         int set, slot, b;
         a.map.decode(min((int)blockIdx.x * L0_ROWS + r, rows - 1), set, slot, b);
         float x;
+        int t, j;
+        a.map.split(slot, t, j);                       // (0, slot) unless the launch batches horizon steps
         if (a.mode[set] == 0) {
-            const size_t zr = a.zbcast[set] ? (size_t)b : (size_t)slot * a.map.B + b;
+            const size_t zr = a.zbcast[set] ? (size_t)b : ((size_t)t * (a.map.sps > 0 ? a.zslots[set] : 0) + j) * a.map.B + b;
             x = a.z[set][zr * S_DIM + k];
         } else {
             const float eps = noise_normal(a.nk, (uint32_t)a.rp_site, (uint32_t)k, (uint32_t)b, a.map.sample_of(slot));
-            x = reparam(eps, a.rp_mean[b * S_DIM + k], a.rp_logvar[b * S_DIM + k]);
+            const size_t o = (size_t)t * a.rp_tstride + b * S_DIM + k;
+            x = reparam(eps, a.rp_mean[o], a.rp_logvar[o]);
         }
         xs[r][k] = x;
     }
@@ -1077,7 +1080,7 @@ NoiseRows map_noise_rows(const RowMap& m) {
     NoiseRows nr{};
     nr.B = m.B;
     for (int i = 0; i < 3; ++i) { nr.set_end[i] = (i < m.nsets ? i + 1 : m.nsets) * m.Sl * m.B; nr.site[i] = m.site[i < m.nsets ? i : m.nsets - 1]; }
-    nr.sample0 = m.sample0; nr.extra_slot = -1; nr.extra_sample = 0; nr.b0 = m.b0;
+    nr.sample0 = m.sample0; nr.extra_slot = -1; nr.extra_sample = 0; nr.b0 = m.b0; nr.slot0 = m.slot0; nr.sps = m.sps;
     return nr;
 }
 
@@ -1176,16 +1179,19 @@ __global__ void __launch_bounds__(FIN_NT) k_step_finalize(StepFinalizeArgs a) {
     // loaded before any is used (the kernel is pure latency otherwise).
     __shared__ double red[4][FIN_NT / 32];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int SB = a.Sl * a.B;
+    const int T = a.T > 1 ? a.T : 1;
+    const int SB = T * a.Sl * a.B;                          // rows per set of the decoder launch
     // per-sample terms are fp32 (as in the reference); their sums over samples / steps / shards are
     // kept in fp64 so that any sample partition adds up to the same value
+    for (int t = 0; t < T; ++t) {
     double t0 = 0.0, t1 = 0.0, t21 = 0.0, t22 = 0.0;
     for (int j = threadIdx.x; j < a.Sl; j += FIN_NT) {
-        const int r = j * a.B + b;
+        const int rs = j * a.B + b;                         // row within the step's loop-2a slots
+        const int r = t * a.Sl * a.B + rs;                  // row within a set of the (time-batched) decoder / encoder launch
         float la[S_DIM], lq[S_DIM];
 #pragma unroll
         for (int d = 0; d < S_DIM; ++d) {
-            la[d] = a.logvarA[(size_t)r * S_DIM + d];
+            la[d] = a.logvarA[(size_t)t * a.lvA_tstride + (size_t)rs * S_DIM + d];
             lq[d] = a.qs_logvar[(size_t)r * S_DIM + d];
         }
         const float rw = a.reward[r], h1 = a.hsum[SB + r], h2 = a.hsum[2 * SB + r];
@@ -1211,6 +1217,8 @@ __global__ void __launch_bounds__(FIN_NT) k_step_finalize(StepFinalizeArgs a) {
 #pragma unroll
         for (int w = 0; w < FIN_NT / 32; ++w) v += red[threadIdx.x][w];
         a.acc[threadIdx.x * a.B + b] += v;
+    }
+    __syncthreads();
     }
     if (a.carry_src && threadIdx.x >= 32 && threadIdx.x < 32 + S_DIM)
         a.carry_dst[b * S_DIM + threadIdx.x - 32] = a.carry_src[b * S_DIM + threadIdx.x - 32];
