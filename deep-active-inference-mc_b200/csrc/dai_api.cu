@@ -338,7 +338,7 @@ int plan_weights(dai_handle* h) {
 }
 
 // Re-pack the images of every dirty tensor on `st` (one gather kernel per image; nothing leaves the device except the
-// 288 floats of po_net.19.weight, which travel as a kernel parameter of ct3).
+// 288 floats of po_net.19.weight and the 320 of qs_net.0, which travel as kernel parameters of ct3 / conv2).
 int commit(dai_handle* h, cudaStream_t st) {
     for (int i = 0; i < kNumSpecs; ++i)
         if (!h->have[i]) return fail(h, DAI_E_WEIGHTS, "missing weight %s", kSpecs[i].key);
@@ -357,6 +357,15 @@ int commit(dai_handle* h, cudaStream_t st) {
         CK(cudaMemcpyAsync(w19, h->raw_dev[i19], sizeof(w19), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         tc_set_w4(&h->tcw, w19);
+    }
+    const int iq0 = spec_index("qs_net.0.weight"), iq0b = spec_index("qs_net.0.bias");
+    if (h->dirty[iq0] || h->dirty[iq0b]) {
+        // the encoder's first conv is computed inside conv2's kernel, its 320 parameters are constant-bank operands there
+        float wq[288], bq[32];
+        CK(cudaMemcpyAsync(wq, h->raw_dev[iq0], sizeof(wq), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(bq, h->raw_dev[iq0b], sizeof(bq), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tc_set_conv1(&h->tcw, wq, bq);
     }
     for (int i = 0; i < kNumSpecs; ++i) h->dirty[i] = false;
     h->committed = true;
@@ -504,9 +513,11 @@ int run_encoder(dai_handle* h, cudaStream_t st, const float* img, int B, int Sl,
                 h->launches += launch_qs(h->w, a, st);
                 continue;
             }
-            h->launches += launch_qs_conv1(h->w, a.img, n, nullptr, h->qc1.p, st);
+            // conv1 inside conv2's kernel (env DAI_TC_FUSE_C1=0: the two-kernel path through a 128 KB/row HBM activation)
+            static const bool fuse_c1 = !(getenv("DAI_TC_FUSE_C1") && atoi(getenv("DAI_TC_FUSE_C1")) == 0);
+            if (!fuse_c1) h->launches += launch_qs_conv1(h->w, a.img, n, nullptr, h->qc1.p, st);
             std::string terr;
-            const int nl = tc_qs_convs(h->tcw, h->w, h->cfg.precision, h->qc1.p, h->qc2.p, a.c3, n, st, &terr);
+            const int nl = tc_qs_convs(h->tcw, h->w, h->cfg.precision, h->qc1.p, h->qc2.p, a.c3, n, st, &terr, fuse_c1 ? a.img : nullptr);
             if (nl < 0) return fail(h, DAI_E_CUDA, "tensor-core encoder convs: %s", terr.c_str());
             h->launches += nl;
             // conv4 as im2col + GEMM -> K-blocked operand; FC1..3 on tensor cores; tail (256 -> 20) on CUDA cores
@@ -765,9 +776,9 @@ int run_rollout_steps(dai_handle* h, cudaStream_t st, const float* s_root, const
         RET(run_ps(h, st, pa));
     }
     if (Sl > 0) {
-        // 2. pixel work, in groups of steps of about two decoder chunks
+        // 2. pixel work, in equal groups of steps of up to 2.5 decoder chunks (R = 16, T = 10: two groups of five steps)
         const int rows_step = 3 * Sl * B;
-        const int tg_max = std::max(1, std::min(T, std::min(255, (2 * h->dec_chunk) / std::max(rows_step, 1))));
+        const int tg_max = std::max(1, std::min(T, std::min(255, (5 * h->dec_chunk / 2) / std::max(rows_step, 1))));
         const int ngroups = (T + tg_max - 1) / tg_max;
         const int tg = (T + ngroups - 1) / ngroups;
         RET(reserve(h, h->img, (size_t)tg * Sl * B * IMG * sizeof(float)));

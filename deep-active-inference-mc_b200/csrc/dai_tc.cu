@@ -184,10 +184,12 @@ struct ConvParams {
     const uint8_t* wpack;    // packed weights (see pack_layer)
     const float* bias;       // [Cout]
     void* out;               // blocked bf16 planes (ct1, ct2) or the last deconv's row planes + border terms [row][PROJ_ROW_FLOATS] (ct3)
-    float2 w4[288];          // ct3 only: last deconv's weights [c 32][tap 9], each duplicated (w, w) for packed
-                             // fp32x2 FMAs over the (left, right) output pixel pair (kernel params = constant bank)
+    float2 w4[288];          // ct3: last deconv's weights [c 32][tap 9], each duplicated (w, w) for packed fp32x2 FMAs over the
+                             // (left, right) output pixel pair (kernel params = constant bank).  GEN layers: conv1's weights as
+                             // channel pairs [tap 9][16] and its bias [16] (entries 0..159)
     int32_t two_pass;        // 1: per tile all hi-plane MMAs, then all lo-plane MMAs (each ring slot is released as soon
                              // as its plane is done); 0: both planes waited for, products interleaved per k step
+    const float* gen_img;    // GEN layers: fp32 images [nrows][64][64] (conv1's weights and bias travel in w4)
     int32_t dbg;             // experiments only (env DAI_TC_DBG): 1 = epilogue does no work, 2 = no MMAs issued
     long long* counters;     // experiments only: per CTA {mma_total, mma_wait_acc, mma_wait_a, epi_total, epi_wait, tiles, 0, 0}
 };
@@ -207,20 +209,26 @@ enum { OUT_BLOCKED = 0, OUT_PROJ = 1, OUT_PARITY = 2, OUT_NHWC_F32 = 3 };
 //            ~46-cycle cost of a small-N MMA is paid twice per tap instead of three times; the hi*lo part lands in a
 //            second column block that the epilogue adds
 struct TrCt1 { static constexpr int ID = 0, MODE = 0, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 3,
-               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = true, CONCAT = true; };
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = true, CONCAT = true, GEN = false; };
 struct TrCt2 { static constexpr int ID = 1, MODE = 1, NPH = 64, KCIN = 8, GH = 16, GW = 16, VH = 16, VW = 16, PH = 16, PW = 16, NA = 4,
-               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false; };
+               EPI_WARPS = 8, OUT = OUT_BLOCKED; static constexpr bool TWO_PASS = false, CONCAT = false, GEN = false; };
 struct TrCt3 { static constexpr int ID = 2, MODE = 1, NPH = 32, KCIN = 8, GH = 32, GW = 32, VH = 32, VW = 32, PH = 32, PW = 32, NA = 7,
-               EPI_WARPS = 8, OUT = OUT_PROJ; static constexpr bool TWO_PASS = false, CONCAT = false; };
+               EPI_WARPS = 8, OUT = OUT_PROJ; static constexpr bool TWO_PASS = false, CONCAT = false, GEN = false; };
 // encoder: Conv2d 32->32 (31x31 -> 15x15) and 32->64 (15x15 -> 7x7), k3 s2 valid
 struct TrQc2 { static constexpr int ID = 3, MODE = 2, NPH = 32, KCIN = 4, GH = 16, GW = 16, VH = 15, VW = 15, PH = 16, PW = 16, NA = 4,
-               EPI_WARPS = 8, OUT = OUT_PARITY; static constexpr bool TWO_PASS = false, CONCAT = false; };
+               EPI_WARPS = 8, OUT = OUT_PARITY; static constexpr bool TWO_PASS = false, CONCAT = false, GEN = false; };
 struct TrQc3 { static constexpr int ID = 4, MODE = 2, NPH = 64, KCIN = 4, GH = 16, GW = 8, VH = 7, VW = 7, PH = 8, PW = 8, NA = 4,
-               EPI_WARPS = 8, OUT = OUT_NHWC_F32; static constexpr bool TWO_PASS = false, CONCAT = false; };
+               EPI_WARPS = 8, OUT = OUT_NHWC_F32; static constexpr bool TWO_PASS = false, CONCAT = false, GEN = false; };
+// conv2 with conv1 (Conv2d 1->32, k3 s2 valid, 64x64 -> 31x31, + ReLU) computed IN the kernel: GEN_WARPS generator warps
+// write each tile's halo planes (conv1's output around the tile, bf16 hi/lo, parity-split) straight into the ring slots the
+// MMAs read, from the fp32 image — the 128 KB/row activation between the two layers (conv1 was bound by writing it to HBM,
+// conv2 by reading it back) never exists in global memory.
+struct TrQc2G : TrQc2 { static constexpr int ID = 5; static constexpr bool GEN = true; };
 
 template <class T>
 struct Cfg : T {
-    static constexpr int THREADS = 128 + 32 * T::EPI_WARPS;
+    static constexpr int GEN_WARPS = T::GEN ? 12 : 0;                    // generator warps (after the four single-role warps)
+    static constexpr int THREADS = 128 + 32 * T::EPI_WARPS + 32 * GEN_WARPS;
     static constexpr int TH = 16, TW = 8;    // tile of the m-grid: 128 pixels
     static constexpr int HY = T::MODE == 0 ? TH + 2 : TH + 1;
     static constexpr int HX = T::MODE == 0 ? TW + 2 : TW + 1;
@@ -239,7 +247,8 @@ struct Cfg : T {
     static constexpr int W_BYTES = 9 * T::NPH * T::KCIN * 32;  // all 9 taps, hi + lo, resident
     static constexpr int SMEM_A = T::NA * PLANE_A;
     static constexpr int SMEM_TAIL = 1024;                     // barriers, tmem slot, bias
-    static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + SMEM_TAIL;
+    static constexpr int SMEM_GEN = T::GEN ? 16384 : 0;        // the current tile's fp32 image (generator warps)
+    static constexpr int SMEM_BYTES = W_BYTES + SMEM_A + SMEM_TAIL + SMEM_GEN;
 };
 
 // The unit table of a layer as a function of compile-time traits (build_layer packs the weights in this order and
@@ -362,8 +371,10 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int W_PROD = C::EPI_WARPS, W_MMA = C::EPI_WARPS + 1, W_ALLOC = C::EPI_WARPS + 2, W_WGT = C::EPI_WARPS + 3;
     const int nplanes = p.nprod == 3 ? 2 : 1;
+    float* simg = reinterpret_cast<float*>(smem + C::W_BYTES + C::SMEM_A + C::SMEM_TAIL);   // GEN: the current tile's image
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        // a_full: one arrival with the TMA's transaction bytes, or one per generator warp
+        for (int i = 0; i < C::NA; ++i) { mbar_init(&a_full[i], C::GEN ? C::GEN_WARPS : 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], C::EPI_WARPS); }
         mbar_init(w_full, 1);
         fence_barrier_init();
@@ -380,7 +391,119 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_tc_conv(const __grid_constant
     if (warp != W_WGT) pdl_wait();
     pdl_trigger();
 
-    if (warp == W_PROD) {
+    if (C::GEN && warp > W_WGT) {
+        // ===== halo generators (GEN layers): conv1 + ReLU of the tile's surroundings -> the ring slots, hi and lo =====
+        // One thread per halo position (parity plane, y, x): 9 image pixels, 32 channels x 9 FMAs in the order of
+        // k_qs_conv1 (the same bits), eight 16-byte shared-memory stores (4 channel groups x hi/lo; consecutive positions
+        // are consecutive 16-byte units: conflict-free).  Positions outside the parity plane or outside conv1's 31 x 31
+        // output are zero, like the TMA's out-of-bounds fill of the two-kernel path.
+        // The tile's image is staged in shared memory by one coalesced sweep (the next tile's is in flight, in registers,
+        // while this tile is computed): read per position straight from global memory, the nine pixel loads of each of a
+        // thread's two or three positions were serialised L2 round trips and the generators, not the MMAs, paced the kernel.
+        const int gtid = (warp - W_WGT - 1) * 32 + lane;
+        constexpr int NPOS = 4 * C::HY * C::HX, GT = 32 * C::GEN_WARPS;
+        constexpr int NPRE = C::GEN ? (1024 + GT - 1) / (GT > 0 ? GT : 1) : 1;     // float4 of the 16 KB image per generator thread
+        float4 pre[NPRE];
+        auto fetch = [&](int tile) {
+            const float4* src = reinterpret_cast<const float4*>(p.gen_img + (size_t)(tile / C::TILES) * 4096);
+#pragma unroll
+            for (int i = 0; i < NPRE; ++i)
+                if (gtid + i * GT < 1024) pre[i] = __ldg(src + gtid + i * GT);
+        };
+        if ((int)blockIdx.x < ntiles) fetch(blockIdx.x);
+        int cnt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            asm volatile("bar.sync 1, %0;" ::"n"(GT > 0 ? GT : 32) : "memory");      // every generator is done with the previous image
+#pragma unroll
+            for (int i = 0; i < NPRE; ++i)
+                if (gtid + i * GT < 1024) reinterpret_cast<float4*>(simg)[gtid + i * GT] = pre[i];
+            asm volatile("bar.sync 1, %0;" ::"n"(GT > 0 ? GT : 32) : "memory");
+            if (tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x);
+            const int t = tile % C::TILES;
+            const int y0 = (t / C::TILES_X) * C::TH, x0 = (t % C::TILES_X) * C::TW;
+            const int s_hi = cnt % C::NA;
+            const uint32_t ph_hi = (uint32_t)(cnt / C::NA) & 1u;
+            ++cnt;
+            int s_lo = s_hi;
+            uint32_t ph_lo = ph_hi;
+            if (nplanes == 2) { s_lo = cnt % C::NA; ph_lo = (uint32_t)(cnt / C::NA) & 1u; ++cnt; }
+            if (lane == 0) {
+                mbar_wait(&a_empty[s_hi], ph_hi ^ 1u);
+                if (nplanes == 2) mbar_wait(&a_empty[s_lo], ph_lo ^ 1u);
+            }
+            __syncwarp();
+            uint8_t* dhi = smA + (size_t)s_hi * C::PLANE_A;
+            uint8_t* dlo = smA + (size_t)s_lo * C::PLANE_A;
+            // Positions are enumerated (row parity, y, c = 2x + column parity): consecutive lanes read consecutive pixel pairs
+            // of the image (8-byte loads, conflict-free) and write 16-byte units that alternate between two parity planes 64
+            // bytes apart modulo 128 — conflict-free as well.  A thread's (up to) two positions are computed together with
+            // packed fp32x2 FMAs (two channels per instruction, the same IEEE fma per lane as k_qs_conv1's) whose weight
+            // operands come from the constant bank: fetched from shared memory (warp-uniform 16-byte loads, four passes
+            // each) the weights alone kept the shared-memory pipe busy for 3.8k cycles per tile, longer than the tile's MMAs.
+            constexpr int NP = C::GEN ? (NPOS + GT - 1) / (GT > 0 ? GT : 1) : 1;
+            const unsigned long long* gw = reinterpret_cast<const unsigned long long*>(p.w4);
+            float v[NP][9];
+            uint32_t off[NP];
+            bool valid[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int pos = gtid + q * GT;
+                const int py = pos / (C::HY * 2 * C::HX), rem = pos - py * (C::HY * 2 * C::HX);
+                const int hy = rem / (2 * C::HX), c = rem - hy * (2 * C::HX);
+                const int hx = c >> 1, px = c & 1;
+                const int Y = y0 + hy, X = x0 + hx;                       // position in the parity plane
+                const int oy = 2 * Y + py, ox = 2 * X + px;               // conv1 output pixel
+                valid[q] = pos < NPOS && Y < C::PH && X < C::PW && oy < 31 && ox < 31;
+                off[q] = (uint32_t)((py * 2 + px) * 4) * C::KC_STRIDE + (uint32_t)(hy * C::HX + hx) * 16u;
+                const float* in = simg + (valid[q] ? (2 * oy) * 64 + 2 * ox : 0);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const float2 a = *reinterpret_cast<const float2*>(in + kh * 64);
+                    v[q][kh * 3 + 0] = a.x; v[q][kh * 3 + 1] = a.y; v[q][kh * 3 + 2] = in[kh * 64 + 2];
+                }
+            }
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) {
+                unsigned long long acc[NP][4];
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[q][e] = gw[144 + kc * 4 + e];
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const unsigned long long vv = pack_f32x2(v[q][i], v[q][i]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[q][e] = ffma2(vv, gw[i * 16 + kc * 4 + e], acc[q][e]);
+                    }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (gtid + q * GT >= NPOS) continue;
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float v0 = fmaxf(__uint_as_float((uint32_t)acc[q][e]), 0.0f), v1 = fmaxf(__uint_as_float((uint32_t)(acc[q][e] >> 32)), 0.0f);
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                        hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        const __nv_bfloat162 ll = __floats2bfloat162_rn(v0 - __uint_as_float(hi[e] << 16), v1 - __uint_as_float(hi[e] & 0xffff0000u));
+                        lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    if (!valid[q]) { hi[0] = hi[1] = hi[2] = hi[3] = 0u; lo[0] = lo[1] = lo[2] = lo[3] = 0u; }
+                    const uint32_t o = off[q] + (uint32_t)kc * C::KC_STRIDE;
+                    *reinterpret_cast<uint4*>(dhi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    if (nplanes == 2) *reinterpret_cast<uint4*>(dlo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads, then one arrival per warp
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a_full[s_hi]);
+                if (nplanes == 2) mbar_arrive(&a_full[s_lo]);
+            }
+        }
+    } else if (warp == W_PROD && !C::GEN) {
         // ===== halo producer: one TMA box per (tile, plane) =====
         if (lane == 0) {
             int cnt = 0;
@@ -1761,6 +1884,7 @@ using CfgCt2 = Cfg<TrCt2>;   // 144 KB of weights + 4 x 19.1 KB halo planes (2 t
 using CfgCt3 = Cfg<TrCt3>;   //  72 KB of weights + 7 x 19.1 KB halo planes (3.5 tiles in flight)
 using CfgQc2 = Cfg<TrQc2>;   //  36 KB of weights + 4 x 38.3 KB halo planes (4 parities x 4 kc)
 using CfgQc3 = Cfg<TrQc3>;   //  72 KB of weights + 4 x 38.3 KB halo planes
+using CfgQc2G = Cfg<TrQc2G>; //  conv1 -> conv2 in one kernel: as CfgQc2, the halo planes generated in shared memory
 
 // ---------------------------------------------------------------------------------------
 // host: weight packing, tensor maps, launches
@@ -1775,6 +1899,7 @@ struct LayerPack {
 struct TcImpl {
     LayerPack ct1, ct2, ct3, qc2, qc3;
     float w4[288];               // po_net.19.weight as [c][tap]
+    float genw[320];             // qs_net.0.weight as [tap][c] (288), then qs_net.0.bias (32): the fused conv1 of k_tc_conv<CfgQc2G>
     uint8_t* dense_w[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // TC_PS1 .. TC_QS2, TC_QC4
     float* dense_b[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int dense_k[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dense_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1890,14 +2015,17 @@ int make_map(TcImpl* im, const void* base, int rows, int H, int W, int kplanes, 
 
 template <class C>
 int launch_conv(TcImpl* im, const LayerPack& lp, const float* bias, int precision, const void* in, void* out, int nrows,
-                cudaStream_t st, std::string* err, const float* w4 = nullptr) {
+                cudaStream_t st, std::string* err, const float* w4 = nullptr, const float* gen_img = nullptr) {
     CUtensorMap map;
     if (make_map(im, in, nrows, C::PH, C::PW, C::KPLANES, C::HX, C::HY, &map, err) != 0) return -1;
     ConvParams p{};
+    p.gen_img = gen_img;
     for (int i = 0; i < lp.nunits; ++i) p.units[i] = lp.units[i];
     p.nunits = lp.nunits; p.nrows = nrows; p.nprod = precision == DAI_PREC_BF16X1 ? 1 : 3;
     p.wpack = lp.wpack; p.bias = bias; p.out = out;
     if (w4) for (int i = 0; i < 288; ++i) p.w4[i] = make_float2(w4[i], w4[i]);
+    if (C::GEN)      // conv1's weights / bias as channel pairs [tap 9][16], [16]: constant-bank operands of the generators' packed FMAs
+        for (int i = 0; i < 160; ++i) p.w4[i] = make_float2(im->genw[2 * i], im->genw[2 * i + 1]);
     for (int i = 0; i < C::NUNITS; ++i) {
         const Unit a = lp.units[i], b = unit_at<C>(i);
         if (lp.nunits != C::NUNITS || a.oy != b.oy || a.ox != b.ox || a.col != b.col || a.n != b.n || a.init != b.init ||
@@ -2042,6 +2170,7 @@ int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* e
             cudaFuncSetAttribute(k_tc_conv<CfgCt3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgCt3::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_conv<CfgQc3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc3::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_tc_conv<CfgQc2G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgQc2G::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_ct23<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_ct23<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F23::SMEM_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(k_tc_fc4_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fc4Pair::SMEM) != cudaSuccess ||
@@ -2108,6 +2237,14 @@ int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* e
 }
 
 // po_net.19.weight (Cin 32, Cout 1, 3, 3) = [c][tap]: travels as a kernel parameter of ct3 (constant bank)
+void tc_set_conv1(TcWeights* w, const float* w_raw /*[32][9]*/, const float* bias /*[32]*/) {
+    TcImpl* im = static_cast<TcImpl*>(w->impl);
+    if (!im) return;
+    for (int c = 0; c < 32; ++c)
+        for (int t = 0; t < 9; ++t) im->genw[t * 32 + c] = w_raw[c * 9 + t];
+    memcpy(im->genw + 288, bias, 32 * sizeof(float));
+}
+
 void tc_set_w4(TcWeights* w, const float* w19) {
     TcImpl* im = static_cast<TcImpl*>(w->impl);
     if (im) memcpy(im->w4, w19, sizeof(im->w4));
@@ -2184,10 +2321,13 @@ __global__ void __launch_bounds__(256) k_conv4_im2col(const float* __restrict__ 
 // encoder conv2 + conv3 on tensor cores: c1 = conv1 output in parity-split blocked planes
 // [plane][row][parity 4][kc 4][16][16][8]; c2 = same form of the 15x15x32 map ([..][8][8][8]); c3 = fp32 NHWC (7,7,64)
 int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
-                cudaStream_t st, std::string* err) {
+                cudaStream_t st, std::string* err, const float* img) {
     TcImpl* im = static_cast<TcImpl*>(tw.impl);
     if (!im) { *err = "tensor-core weights not packed"; return -1; }
-    if (launch_conv<CfgQc2>(im, im->qc2, w.qc2_b, precision, c1, c2, rows, st, err) < 0) return -1;
+    if (img) {
+        // conv1 computed inside conv2's kernel (c1 only backs the unused tensor map)
+        if (launch_conv<CfgQc2G>(im, im->qc2, w.qc2_b, precision, c1, c2, rows, st, err, nullptr, img) < 0) return -1;
+    } else if (launch_conv<CfgQc2>(im, im->qc2, w.qc2_b, precision, c1, c2, rows, st, err) < 0) return -1;
     if (launch_conv<CfgQc3>(im, im->qc3, w.qc3_b, precision, c2, c3, rows, st, err) < 0) return -1;
     return 2;
 }

@@ -19,6 +19,7 @@ struct TcWeights {
 // Nothing is packed on the host; the handle runs the jobs on the device whenever their source tensor changes.
 int tc_plan_weights(TcWeights* out, std::vector<RepackJob>* jobs, std::string* err);
 void tc_set_w4(TcWeights* w, const float* w19_host);     // po_net.19.weight, 288 floats
+void tc_set_conv1(TcWeights* w, const float* w_host /*qs_net.0.weight (32,1,3,3)*/, const float* bias_host /*[32]*/);
 void tc_release(TcWeights* w);
 
 // FC4 -> ct1 -> ct2 -> ct3 -> pixel terms for one chunk of decoder rows on the tensor cores.
@@ -52,8 +53,10 @@ int tc_dense_hidden(const TcWeights& tw, int which, int precision, const void* i
 
 // Encoder conv2 (32->32, 31x31->15x15) and conv3 (32->64, 15x15->7x7) on tensor cores.  c1 / c2 are parity-split
 // channel-blocked bf16 hi/lo planes, c3 is fp32 NHWC (rows,7,7,64).  Returns launches or -1.
+// img != null: conv1 (1->32, 64x64 -> 31x31) is computed inside conv2's kernel from the fp32 images (rows,64,64) and c1 is
+// not read (it must still be a valid buffer of the c1 size); img == null: c1 holds conv1's output (launch_qs_conv1).
 int tc_qs_convs(const TcWeights& tw, const DevWeights& w, int precision, const void* c1, void* c2, float* c3, int rows,
-                cudaStream_t st, std::string* err);
+                cudaStream_t st, std::string* err, const float* img = nullptr);
 
 // Encoder conv4 (64->64, k3 s2, 7x7 -> 3x3) as im2col + tcgen05 GEMM.  c3 fp32 NHWC (rows,7,7,64); out = the K-blocked
 // bf16 hi/lo operand of the encoder's FC1 ([plane][72][rows_pad][8], k = pixel*64 + c).  Returns launches or -1.
