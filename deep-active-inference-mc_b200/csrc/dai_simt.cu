@@ -861,21 +861,19 @@ __device__ __forceinline__ void mlp_l0_group(const float* xs, int kc, const floa
                                              const float* __restrict__ bias, const NoiseKey& nk, int site, int b, uint32_t sample,
                                              bool valid, int row, size_t rows_pad, unsigned short* out) {
     const size_t plane = (size_t)(N / 8) * rows_pad * 8;
-    float4 w0[KIN], w1[KIN];
-#pragma unroll
-    for (int k = 0; k < KIN; ++k) {
-        w0[k] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8));
-        w1[k] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8 + 4));
-    }
+    // (the weight loads are left to the compiler's scheduling under the kernels' register bound: holding all 2 x KIN float4
+    // at once cost 146 registers and one resident CTA per SM — 24 us at 6,464 rows for 4 us of work per wave)
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + kc * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + kc * 8 + 4));
     uint4 drop = make_uint4(0, 0, 0, 0);
     if (nk.training) drop = noise_block(nk, (uint32_t)site, (uint32_t)(kc >> 4), (uint32_t)b, sample);   // 128 columns per Philox block
     float v[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int k = 0; k < KIN; ++k) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * N + kc * 8 + 4));
         const float x = xs[k];
-        v[0] = fmaf(x, w0[k].x, v[0]); v[1] = fmaf(x, w0[k].y, v[1]); v[2] = fmaf(x, w0[k].z, v[2]); v[3] = fmaf(x, w0[k].w, v[3]);
-        v[4] = fmaf(x, w1[k].x, v[4]); v[5] = fmaf(x, w1[k].y, v[5]); v[6] = fmaf(x, w1[k].z, v[6]); v[7] = fmaf(x, w1[k].w, v[7]);
+        v[0] = fmaf(x, w0.x, v[0]); v[1] = fmaf(x, w0.y, v[1]); v[2] = fmaf(x, w0.z, v[2]); v[3] = fmaf(x, w0.w, v[3]);
+        v[4] = fmaf(x, w1.x, v[4]); v[5] = fmaf(x, w1.y, v[5]); v[6] = fmaf(x, w1.z, v[6]); v[7] = fmaf(x, w1.w, v[7]);
     }
     if (nk.training) {
         const int wsel = (kc >> 2) & 3;
@@ -890,7 +888,7 @@ __device__ __forceinline__ void mlp_l0_group(const float* xs, int kc, const floa
     if (valid) store_kblocked8(out, plane, ((size_t)kc * rows_pad + row) * 8, v);
 }
 
-__global__ void __launch_bounds__(L0_NT) k_ps_l0(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, unsigned short* out) {
+__global__ void __launch_bounds__(L0_NT, 3) k_ps_l0(DevWeights w, PsArgs a, NoiseRows nr, size_t rows_pad, unsigned short* out) {
     __shared__ float xs[L0_ROWS][15];                 // odd stride: lane = row reads are conflict-free
     pdl_wait();
     const int rows = (a.nA + a.nB) * a.B;
@@ -911,7 +909,7 @@ __global__ void __launch_bounds__(L0_NT) k_ps_l0(DevWeights w, PsArgs a, NoiseRo
     mlp_l0_group<14, 512>(xs[lane], blockIdx.y * 8 + warp, w.ps_w0t, w.ps_b0, a.nk, site, b, sample, valid, row, rows_pad, out);
 }
 
-__global__ void __launch_bounds__(L0_NT) k_po_l0(DevWeights w, PoFcArgs a, size_t rows_pad, unsigned short* out) {
+__global__ void __launch_bounds__(L0_NT, 3) k_po_l0(DevWeights w, PoFcArgs a, size_t rows_pad, unsigned short* out) {
     __shared__ float xs[L0_ROWS][11];
     pdl_wait();
     const int rows = a.map.rows();
