@@ -854,33 +854,41 @@ int rollout_impl(dai_handle* h, cudaStream_t st, const float* o, const float* pi
     float* m0 = ptr<float>(h->root);
     float* lv0 = m0 + slab;
     float* smp0 = lv0 + slab;
-    // qs0 = encoder(o) (+ reparameterize), src/torchmodel.py:228-229 / :248-249
-    RET(run_encoder(h, st, o, B, 1, 0, SITE_QS_ROOT, nk, m0, lv0, smp0));
-    CK(cudaMemcpyAsync(h->carry.p, calc_mean ? m0 : smp0, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
-    if (!pi) {
-        RET(reserve(h, h->pi_eye, (size_t)B * 4 * sizeof(float)));
-        k_fill_eye<<<(B * 4 + 255) / 256, 256, 0, st>>>(ptr<float>(h->pi_eye), B);
-        ++h->launches;
-        pi = ptr<float>(h->pi_eye);
-    }
     const int mean_variant = (four && calc_mean) ? 1 : 0;
-    // time-batched horizon (run_rollout_steps) on the tensor-core path; env DAI_TBATCH=0 or the fp32 CUDA-core
-    // precision: one launch sequence per step
+    // qs0 = encoder(o) (+ reparameterize), src/torchmodel.py:228-229 / :248-249; the carry starts from it
+    auto begin = [&](const NoiseKey& k, const float*& pp) -> int {
+        RET(run_encoder(h, st, o, B, 1, 0, SITE_QS_ROOT, k, m0, lv0, smp0));
+        CK(cudaMemcpyAsync(h->carry.p, calc_mean ? m0 : smp0, slab * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemsetAsync(h->acc.p, 0, (size_t)4 * B * sizeof(double), st));
+        if (!pp) {
+            RET(reserve(h, h->pi_eye, (size_t)B * 4 * sizeof(float)));
+            k_fill_eye<<<(B * 4 + 255) / 256, 256, 0, st>>>(ptr<float>(h->pi_eye), B);
+            ++h->launches;
+            pp = ptr<float>(h->pi_eye);
+        }
+        return DAI_OK;
+    };
+    // time-batched horizon (run_rollout_steps) on the tensor-core path — the whole call, root encode and final combine
+    // included, is ONE cached graph; env DAI_TBATCH=0 or the fp32 CUDA-core precision: one launch sequence per step
     static const bool tbatch_env = !(getenv("DAI_TBATCH") && atoi(getenv("DAI_TBATCH")) == 0);
     if (tbatch_env && h->cfg.precision != DAI_PREC_FP32_SIMT && steps > 1 && samples <= (int)SAMPLE_MASK) {
-        const uint64_t sig = sig_of({2, (uint64_t)(uintptr_t)pi, (uint64_t)B, (uint64_t)steps, (uint64_t)samples, (uint64_t)j0, (uint64_t)j1,
-                                     (uint64_t)mean_variant, (uint64_t)calc_mean, (uint64_t)(uintptr_t)po1, (uint64_t)h->cfg.precision,
-                                     (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk, (uint64_t)(uintptr_t)st});
-        RET(run_cached(h, st, sig, nk, [&](const uint32_t* dyn) {
+        const uint64_t sig = sig_of({2, (uint64_t)(uintptr_t)o, (uint64_t)(uintptr_t)pi, (uint64_t)B, (uint64_t)steps, (uint64_t)samples,
+                                     (uint64_t)j0, (uint64_t)j1, (uint64_t)mean_variant, (uint64_t)calc_mean, (uint64_t)(uintptr_t)po1,
+                                     (uint64_t)(uintptr_t)sums, (uint64_t)(uintptr_t)G, (uint64_t)(uintptr_t)t0, (uint64_t)(uintptr_t)t1,
+                                     (uint64_t)(uintptr_t)t2, (uint64_t)h->cfg.precision, (uint64_t)h->cfg.training, (uint64_t)h->dec_chunk,
+                                     (uint64_t)(uintptr_t)st});
+        return run_cached(h, st, sig, nk, [&](const uint32_t* dyn) -> int {
             NoiseKey k = nk;
             k.dyn = dyn;
             k.step = 0;
-            return run_rollout_steps(h, st, ptr<float>(h->carry), pi, B, steps, samples, j0, j1, mean_variant, calc_mean, k,
-                                     ptr<double>(h->acc), po1);
-        }));
-        return finish_outputs(h, st, B, mean_variant ? 1 : samples, sums, G, t0, t1, t2);
+            const float* pp = pi;
+            RET(begin(k, pp));
+            RET(run_rollout_steps(h, st, ptr<float>(h->carry), pp, B, steps, samples, j0, j1, mean_variant, calc_mean, k,
+                                  ptr<double>(h->acc), po1));
+            return finish_outputs(h, st, B, mean_variant ? 1 : samples, sums, G, t0, t1, t2);
+        });
     }
+    RET(begin(nk, pi));
     for (int t = 0; t < steps; ++t) {
         StepSpec sp;
         sp.s0 = ptr<float>(h->carry); sp.pi = pi; sp.B = B;
