@@ -329,18 +329,19 @@ def main():
     if not args.quick and not args.no_extras:
         ks = max(2, min(args.steps, 5))
         if world == 1:
-            # configs[2]: N=200, T=10 (4 roots per step); single-root latency of configs[1] (test_demo.py:150 is R=1)
+            # single-root latency of configs[1] (test_demo.py:150 is R=1); first of the extra legs, 10 timed calls
+            d1, e1, _, _ = make_steps(1, N, T, None, None, 2)
+            ms1 = timed(d1, max(ks, 10), 5)
+            ms1e = timed(e1, max(ks, 10), 1)
+            extra["r1_latency_ms"] = {"value": ms1, "e2e": ms1e, "unit": "ms per rollout", "rollouts_s": 1e3 / ms1,
+                                      "config": "configs[1] with R=1: one root (4 action rows), N=%d, T=%d" % (N, T)}
+            # configs[2]: N=200, T=10 (4 roots per step)
             d3, e3, _, _ = make_steps(4, 200, 10, None, None, 1)
             ms3 = timed(d3, ks, 2)
             ms3e = timed(e3, ks, 1)
             extra["c3_rollouts_s"] = {"value": 4 / (ms3 * 1e-3), "e2e": 4 / (ms3e * 1e-3), "unit": "rollouts/s", "ms_per_step": ms3,
                                       "config": "configs[2]: N=200, T=10, R=4 roots per step",
                                       "algorithmic_tflops": rollout_flops(200, 10) * 4 / (ms3 * 1e-3) / 1e12}
-            d1, e1, _, _ = make_steps(1, N, T, None, None, 2)
-            ms1 = timed(d1, max(ks, 5), 3)
-            ms1e = timed(e1, max(ks, 5), 1)
-            extra["r1_latency_ms"] = {"value": ms1, "e2e": ms1e, "unit": "ms per rollout", "rollouts_s": 1e3 / ms1,
-                                      "config": "configs[1] with R=1: one root (4 action rows), N=%d, T=%d" % (N, T)}
             # configs[3]: full MCTS decision (host wall clock)
             dseq = mcts_decisions(model, 50, 10, 1, False, 3)
             dtree = mcts_decisions(model, 50, 10, 16, True, 5)
