@@ -102,7 +102,8 @@ struct dai_handle {
     // step's launches depend on except the noise key, which the kernels then read from `keybuf`
     struct StepGraph { uint64_t sig = 0; uint64_t gen = 0; cudaGraphExec_t exec = nullptr; uint64_t nlaunch = 0; int seen = 0; uint64_t stamp = 0; };
     std::vector<StepGraph> graphs;
-    uint64_t alloc_gen = 0;            // bumped whenever a workspace is (re)allocated: invalidates every cached graph
+    uint64_t alloc_gen = 0;            // bumped whenever a workspace is (re)allocated or a weight that travels as a kernel parameter
+                                       // changes: invalidates every cached graph
     bool capturing = false, capture_failed = false;
     int graphs_enabled = 1;            // env DAI_GRAPHS=0 disables (A/B)
     uint32_t* keybuf = nullptr;        // device {k0, k1, step}
@@ -357,6 +358,7 @@ int commit(dai_handle* h, cudaStream_t st) {
         CK(cudaMemcpyAsync(w19, h->raw_dev[i19], sizeof(w19), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         tc_set_w4(&h->tcw, w19);
+        ++h->alloc_gen;          // these weights are kernel PARAMETERS: a graph captured with the old values must not be replayed
     }
     const int iq0 = spec_index("qs_net.0.weight"), iq0b = spec_index("qs_net.0.bias");
     if (h->dirty[iq0] || h->dirty[iq0b]) {
@@ -366,6 +368,7 @@ int commit(dai_handle* h, cudaStream_t st) {
         CK(cudaMemcpyAsync(bq, h->raw_dev[iq0b], sizeof(bq), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         tc_set_conv1(&h->tcw, wq, bq);
+        ++h->alloc_gen;          // kernel parameters as well (see above)
     }
     for (int i = 0; i < kNumSpecs; ++i) h->dirty[i] = false;
     h->committed = true;

@@ -171,3 +171,39 @@ def test_checkpoint_written_by_the_reference_is_ingested(tmp_path):
     for mod_r, mod_g in ((ref2.model_down, gpu.model_down), (ref2.model_mid, gpu.model_mid), (ref2.model_top, gpu.model_top)):
         for k, v in mod_r.state_dict().items():
             assert torch.equal(v.cpu(), mod_g.state_dict()[k].cpu()), k
+
+
+@pytest.mark.gpu
+def test_weights_that_travel_as_kernel_parameters_invalidate_cached_graphs():
+    """po_net.19.weight (the last deconv, contracted in ct3's epilogue) and qs_net.0 (the encoder's first conv, computed
+    inside conv2's kernel) reach their kernels as launch PARAMETERS, which a captured CUDA graph freezes: after an update
+    of either, a rollout whose graph was captured and replayed before must equal a fresh handle's with the new weights."""
+    from dai_b200.torchmodel import ActiveInferenceModel
+    w = cases.weights_for("w0")
+    m = ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, device="cuda:0").load_numpy_weights(w)
+    o = torch.from_numpy(np.random.default_rng(5).random((4, 4096), dtype=np.float32)).cuda()
+
+    def run(model):
+        model._sync()
+        outs = []
+        for _ in range(3):                       # eager, captured, replayed
+            model._engine.set_rng(21, 0)
+            outs.append(model._engine.rollout(o, None, 3, 4, four=True))
+        assert torch.equal(outs[0]["G"], outs[2]["G"]) and torch.equal(outs[0]["po1"], outs[2]["po1"])
+        return outs[2]
+
+    before = run(m)
+    w2 = {k: v.copy() for k, v in w.items()}
+    rng = np.random.default_rng(9)
+    for key, mod in (("po_net.19.weight", m.model_down.po_net[19]), ("qs_net.0.weight", m.model_down.qs_net[0]),
+                     ("qs_net.0.bias", m.model_down.qs_net[0])):
+        p = getattr(mod, key.rsplit(".", 1)[1])
+        delta = (rng.standard_normal(tuple(p.shape)) * 5e-2).astype(np.float32)
+        with torch.no_grad():
+            p.add_(torch.from_numpy(delta).cuda())
+        w2[key] = w2[key] + delta
+    after = run(m)
+    fresh = run(ActiveInferenceModel(10, 4, 1.0, 1.0, 1.0, device="cuda:0").load_numpy_weights(w2))
+    assert not torch.equal(before["G"], after["G"])
+    for k in ("G", "t0", "t1", "t2", "po1"):
+        assert torch.equal(after[k], fresh[k]), k
