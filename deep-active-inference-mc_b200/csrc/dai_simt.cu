@@ -1395,7 +1395,196 @@ __global__ void __launch_bounds__(512) k_sim_rollout(DevWeights w, SimArgs a) {
     }
 }
 
+// ---- the same rollout on a CLUSTER of 16 CTAs per starting state ------------------------------------------------------
+// One CTA streams the 2 MB of the two 512 x 512 transition layers from L2 at every step, at the ~30 B/clk a single SM gets:
+// 39 us per step, 394 us per 10-step rollout — 41 % of the GPU time of a sequential MCTS decision.  Here sixteen CTAs (a
+// non-portable cluster size, opt-in) each keep 32 columns of both layers (2 x 64 KB) and the habit net's 128 x 128 layer
+// (64 KB) RESIDENT in shared memory for the whole rollout; a 512-wide layer is 32 column threads per CTA running the same
+// k-ascending FMA chain as dense_hidden (so the results are bit-equal to k_sim_rollout's), the 16 slices are exchanged by
+// distributed-shared-memory stores into every CTA's copy of the layer output and one cluster barrier.  Everything small (habit
+// net, categorical draw, first layer, tail, reparameterisation) is computed redundantly by every CTA, so a step has exactly
+// two cluster barriers; rank 0 writes the trajectory.
+constexpr int SIMC = 16;                       // CTAs per cluster
+constexpr int SIMC_COLS = 512 / SIMC;          // columns of a 512-wide layer per CTA
+constexpr int SIMC_SMEM = (2 * 512 * SIMC_COLS + 128 * 128) * (int)sizeof(float);
+
+__device__ __forceinline__ uint32_t simc_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void simc_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// value -> the same shared-memory word in every CTA of the cluster
+__device__ __forceinline__ void simc_broadcast(float* local, float v) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(local);
+#pragma unroll
+    for (uint32_t c = 0; c < SIMC; ++c) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(c));
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+    }
+}
+// this CTA's SIMC_COLS columns of y = relu(bias + x * Wt) (* dropout) from the resident slice sw[k][SIMC_COLS], FMAs in
+// dense_hidden's order, broadcast into every CTA's ys
+__device__ __forceinline__ void simc_layer512(const float* sw, const float* __restrict__ bias, const float* xs, float* ys,
+                                              const uint32_t* mw, uint32_t rank) {
+    if (threadIdx.x < SIMC_COLS) {
+        const int n = (int)rank * SIMC_COLS + threadIdx.x;
+        float acc = __ldg(bias + n);
+#pragma unroll 4
+        for (int k = 0; k < 512; k += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(xs + k);
+            acc = fmaf(x.x, sw[(k + 0) * SIMC_COLS + threadIdx.x], acc);
+            acc = fmaf(x.y, sw[(k + 1) * SIMC_COLS + threadIdx.x], acc);
+            acc = fmaf(x.z, sw[(k + 2) * SIMC_COLS + threadIdx.x], acc);
+            acc = fmaf(x.w, sw[(k + 3) * SIMC_COLS + threadIdx.x], acc);
+        }
+        float v = fmaxf(acc, 0.0f);
+        if (mw) v = ((mw[n >> 5] >> (n & 31)) & 1u) ? v * 2.0f : 0.0f;
+        simc_broadcast(ys + n, v);
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_sim_rollout_cluster(DevWeights w, SimArgs a) {
+    extern __shared__ __align__(16) float simc_smem[];
+    float* sw1 = simc_smem;                              // ps_net.3 columns [32 rank, +32): [k 512][32]
+    float* sw2 = sw1 + 512 * SIMC_COLS;                  // ps_net.6, same
+    float* swp = sw2 + 512 * SIMC_COLS;                  // qpi_net.2: [k 128][128]
+    __shared__ __align__(16) float s_cur[12];
+    __shared__ __align__(16) float x0[16];
+    __shared__ __align__(16) float pA[128];              // habit net activations (local)
+    __shared__ __align__(16) float pB[128];
+    __shared__ __align__(16) float h0[512];              // first transition layer (local)
+    __shared__ __align__(16) float g1[512];              // second / third layer outputs: written by all CTAs of the cluster
+    __shared__ __align__(16) float g2[512];
+    __shared__ uint32_t mw[16];
+    __shared__ float out[20];
+    __shared__ float lg[4];
+    __shared__ int act;
+    const int tid = threadIdx.x;
+    const uint32_t rank = simc_rank();
+    const int kq = blockIdx.x / SIMC;
+    const bool writer = rank == 0;
+    const size_t r0 = (size_t)kq * a.depth;               // first trajectory row of this leaf
+    // resident weights: one coalesced sweep
+    for (int i = tid; i < 512 * (SIMC_COLS / 4); i += 512) {
+        const int k = i / (SIMC_COLS / 4), q = i % (SIMC_COLS / 4);
+        reinterpret_cast<float4*>(sw1)[i] = __ldg(reinterpret_cast<const float4*>(w.ps_w1t + (size_t)k * 512 + rank * SIMC_COLS) + q);
+        reinterpret_cast<float4*>(sw2)[i] = __ldg(reinterpret_cast<const float4*>(w.ps_w2t + (size_t)k * 512 + rank * SIMC_COLS) + q);
+    }
+    for (int i = tid; i < 128 * 128 / 4; i += 512) reinterpret_cast<float4*>(swp)[i] = __ldg(reinterpret_cast<const float4*>(w.pi_w1t) + i);
+    if (tid < 12) s_cur[tid] = tid < S_DIM ? a.start[kq * S_DIM + tid] : 0.0f;
+    __syncthreads();
+    simc_sync();                                          // every CTA of the cluster is running before anyone stores into it
+    int rsite[1] = {SITE_PS_A}, rb[1] = {kq};
+    uint32_t rsample[1] = {0};
+    for (int t = 0; t < a.depth; ++t) {
+        NoiseKey nk = a.nk;
+        nk.step = (uint32_t)t;
+        // habit prior on the current state (every CTA computes all of it)
+        dense_hidden<1, 512>(w.pi_w0t, w.pi_b0, 12, 128, s_cur, 12, pA, 128, nullptr, 0);
+        __syncthreads();
+        if (tid < 128) {
+            float acc = __ldg(w.pi_b1 + tid);
+#pragma unroll 4
+            for (int k = 0; k < 128; k += 4) {
+                const float4 x = *reinterpret_cast<const float4*>(pA + k);
+                acc = fmaf(x.x, swp[(k + 0) * 128 + tid], acc);
+                acc = fmaf(x.y, swp[(k + 1) * 128 + tid], acc);
+                acc = fmaf(x.z, swp[(k + 2) * 128 + tid], acc);
+                acc = fmaf(x.w, swp[(k + 3) * 128 + tid], acc);
+            }
+            pB[tid] = fmaxf(acc, 0.0f);
+        }
+        __syncthreads();
+        dense_tail<1, 512>(w.pi_w2, w.pi_b2, 128, 4, pB, 128, lg);
+        __syncthreads();
+        if (tid == 0) {
+            const float mx = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+            float q[4], sum = 0.0f;
+            for (int i = 0; i < 4; ++i) { q[i] = expf(lg[i] - mx); sum += q[i]; }
+            bool ok = true;
+            float cdf[4], c = 0.0f;
+            for (int i = 0; i < 4; ++i) {
+                q[i] = q[i] / sum;
+                ok = ok && isfinite(q[i]) && q[i] >= 0.0f;
+                c = __fadd_rn(c, q[i]);
+                cdf[i] = c;
+            }
+            ok = ok && c > 0.0f;
+            int choice = 0;
+            if (ok) {
+                const float u = noise_uniform24(nk, SITE_CAT, (uint32_t)kq, 0);
+                const float thr = __fmul_rn(u, cdf[3]);
+                choice = 3;
+                for (int i = 0; i < 4; ++i) if (thr < cdf[i]) { choice = i; break; }
+            }
+            act = choice;
+            if (writer) {
+                for (int i = 0; i < 4; ++i) a.pi0[(r0 + t) * 4 + i] = (i == choice) ? 1.0f : 0.0f;
+                if (t == 0) for (int i = 0; i < 4; ++i) a.qpi[kq * 4 + i] = ok ? q[i] : (i == 0 ? 1.0f : 0.0f);
+                for (int d = 0; d < S_DIM; ++d) a.s0[(r0 + t) * S_DIM + d] = s_cur[d];
+            }
+        }
+        __syncthreads();
+        if (tid < 16) x0[tid] = tid < 4 ? (tid == act ? 1.0f : 0.0f) : (tid < 14 ? s_cur[tid - 4] : 0.0f);
+        const bool drop = nk.training != 0;
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 0, rsite, rb, rsample);
+        __syncthreads();
+        dense_hidden<1, 512>(w.ps_w0t, w.ps_b0, 16, 512, x0, 16, h0, 512, drop ? mw : nullptr, 16);
+        __syncthreads();
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 1, rsite, rb, rsample);
+        __syncthreads();
+        simc_layer512(sw1, w.ps_b1, h0, g1, drop ? mw : nullptr, rank);
+        simc_sync();                                      // g1 complete in every CTA (and everyone is done with g2 of the step before)
+        if (drop) fill_masks<1, 512>(mw, 512, nk, 2, rsite, rb, rsample);
+        __syncthreads();
+        simc_layer512(sw2, w.ps_b2, g1, g2, drop ? mw : nullptr, rank);
+        simc_sync();                                      // g2 complete in every CTA (and everyone is done with g1)
+        dense_tail<1, 512>(w.ps_w3, w.ps_b3, 512, 20, g2, 512, out);
+        __syncthreads();
+        if (tid < S_DIM) {
+            const float mean = out[tid], lv = out[S_DIM + tid];
+            const float eps = noise_normal(nk, SITE_PS_A + 3, (uint32_t)tid, (uint32_t)kq, 0);
+            const float s = reparam(eps, mean, lv);
+            if (writer) { a.ps1[(r0 + t) * S_DIM + tid] = s; a.mean[(r0 + t) * S_DIM + tid] = mean; a.logvar[(r0 + t) * S_DIM + tid] = lv; }
+            s_cur[tid] = a.use_means ? mean : s;
+        }
+        __syncthreads();
+    }
+    simc_sync();                                          // no CTA leaves while a peer may still store into its shared memory
+}
+
 int launch_sim_rollout(const DevWeights& w, const SimArgs& a, cudaStream_t st) {
+    // cluster version where the device grants 16-CTA clusters (env DAI_SIM_CLUSTER=0: the one-CTA kernel)
+    static int cluster_ok = -1;
+    if (cluster_ok < 0) {
+        const char* e = getenv("DAI_SIM_CLUSTER");
+        cluster_ok = 0;
+        if (!(e && atoi(e) == 0) &&
+            cudaFuncSetAttribute(k_sim_rollout_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+            cudaFuncSetAttribute(k_sim_rollout_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, SIMC_SMEM) == cudaSuccess) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(SIMC); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = SIMC_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = SIMC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_sim_rollout_cluster, &cfg) == cudaSuccess && nclusters >= 1) cluster_ok = 1;
+        }
+        cudaGetLastError();
+    }
+    if (cluster_ok == 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(a.K * SIMC); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = SIMC_SMEM; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = SIMC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, k_sim_rollout_cluster, w, a) == cudaSuccess) return 1;
+        cudaGetLastError();
+        cluster_ok = 0;
+    }
     k_sim_rollout<<<a.K, 512, 0, st>>>(w, a);
     return 1;
 }
