@@ -144,7 +144,11 @@ DAI_API int  dai_G_given_trajectory(dai_handle* h, const float* s0, const float*
  * 1 call index.  o (B,4096); pi (B,4) or NULL for eye(4) tiled over B/4 roots (row =
  * root*4 + action, src/util.py:57-60).  `four` selects the _4_ semantics (calculate_G_mean
  * when calc_mean).  T = steps sequential calculate_G evaluations with the s0 carry kept on
- * the device.  Sample sharding and outputs as in dai_calculate_G; sums accumulate over steps. */
+ * the device.  Sample sharding and outputs as in dai_calculate_G; sums accumulate over steps.
+ * The steps are chained only through the transition net, so the evaluation order inside the call
+ * is: the latent chain of all T steps, then the decoder / encoder / EFE work of groups of steps
+ * batched over (step, sample) — same noise keys, same sums, same results as step by step.  A call
+ * whose sizes and pointers repeat is replayed as one CUDA graph. */
 DAI_API int  dai_rollout(dai_handle* h, const float* o, const float* pi, int B, int steps, int samples,
                  int calc_mean, int four, int sample_begin, int sample_end,
                  double* sums, float* G, float* t0, float* t1, float* t2, float* po1, void* stream);
