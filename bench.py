@@ -329,12 +329,14 @@ def main():
     if not args.quick and not args.no_extras:
         ks = max(2, min(args.steps, 5))
         if world == 1:
-            # single-root latency of configs[1] (test_demo.py:150 is R=1); first of the extra legs, 10 timed calls
+            # single-root latency of configs[1] (test_demo.py:150 is R=1); first of the extra legs, 10 timed calls, after a 2 s
+            # pause: a lone request meets an idle GPU, not one still at the clock the power cap left after the main leg
+            time.sleep(2.0)
             d1, e1, _, _ = make_steps(1, N, T, None, None, 2)
             ms1 = timed(d1, max(ks, 10), 5)
             ms1e = timed(e1, max(ks, 10), 1)
             extra["r1_latency_ms"] = {"value": ms1, "e2e": ms1e, "unit": "ms per rollout", "rollouts_s": 1e3 / ms1,
-                                      "config": "configs[1] with R=1: one root (4 action rows), N=%d, T=%d" % (N, T)}
+                                      "config": "configs[1] with R=1: one root (4 action rows), N=%d, T=%d; measured after a 2 s pause" % (N, T)}
             # configs[2]: N=200, T=10 (4 roots per step)
             d3, e3, _, _ = make_steps(4, 200, 10, None, None, 1)
             ms3 = timed(d3, ks, 2)
